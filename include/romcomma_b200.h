@@ -1,0 +1,117 @@
+/* romcomma_b200.h - C ABI of the B200-native (sm_100a) dense-GP hot path of rom-comma.
+ *
+ * The reference (C-O-M-M-A/rom-comma) has no FFI of its own: its hot path is Python calling tf.* ops.  Every entry point
+ * below therefore replaces a group of TensorFlow/GPflow call sites; the citation names them (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to row-major float64 unless it says "host"; the caller owns all buffers;
+ *  - `stream` is a cudaStream_t (may be NULL = legacy default stream); calls are asynchronous on it;
+ *  - return value: 0 ok; < 0 bad argument (-2) or CUDA error (-1000 - cudaError); text via rc_last_error();
+ *    a failed Cholesky (the reference's tf InvalidArgumentError) is reported through the device-side `info` word:
+ *    0, or the 1-based index of the first non-positive pivot (LAPACK convention);
+ *  - no global state, thread-safe per (device, stream); nothing here allocates device memory: workspaces are sized by
+ *    the *_bufsize twins and provided by the caller;
+ *  - factorisation matrices are stored padded: n_pad = rc_padded(n) (multiple of 128), identity in the padding,
+ *    row stride `ld` (even, >= n_pad).  Only the lower triangle is meaningful.
+ *  - multi-output index convention: row (l, n) -> l*N + n  (romcomma/gpf/kernels.py:103-104, gpf/models.py:130).
+ *  - `batch` lays independent problems `stride*` doubles apart (variant path: one N x N problem per output).
+ */
+#ifndef ROMCOMMA_B200_H
+#define ROMCOMMA_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rc_stream_t;
+
+int rc_version(void);
+const char* rc_last_error(void);
+int rc_padded(int n);
+
+/* ---- gram ---------------------------------------------------------------------------------------------------------
+ * out[(l,n),(l',n')] = F[l,l'] * exp(-1/2 sum_m (X[n,m]/ls[l,m] - X2[n',m]/ls[l',m])^2) + E[l,l'] * [n == n']
+ * Replaces MOStationary.K_unit_variance / K_d_apply_variance / K_d / __call__ (romcomma/gpf/kernels.py:74-116,153-154),
+ * Variance.value_to_broadcast / value_times_eye (romcomma/gpf/base.py:57-69) and MOGaussian.add_to
+ * (romcomma/gpf/likelihoods.py:64-67).  F == NULL: unit variance (K_unit_variance); E == NULL: no noise term.
+ * X2 == NULL means X2 = X.  rows_pad/cols_pad: multiples of 64 >= L*N, L*N2; lower_only computes 64-tiles on/below the
+ * diagonal only; pad_identity puts 1 on the padded diagonal (factorisation input) instead of 0.
+ * batch > 1 (variant path, gpflow kernels.RBF per output, romcomma/gpr/kernels.py:176-177, gpr/models.py:340-342):
+ * problem z uses ls + z*L*M, F + z*L*L, E + z*L*L and writes out + z*stride_out (X, X2 shared). */
+int rc_gram(const double* X, int N, const double* X2, int N2, int M, const double* ls, int L, const double* F, const double* E,
+            double* out, long ld_out, long stride_out, int rows_pad, int cols_pad, int lower_only, int pad_identity, int batch,
+            rc_stream_t stream);
+
+/* K = F (x) Kunit + E (x) I from a cached unit gram: MOGPR.KXX cached branch (romcomma/gpf/models.py:66-68,139). */
+int rc_apply_variance_noise(const double* Kunit, long ldu, const double* F, const double* E, int L, int N, int n_pad, double* out,
+                            long ld_out, int lower_only, rc_stream_t stream);
+
+/* ---- Cholesky and solves -------------------------------------------------------------------------------------------
+ * tf.linalg.cholesky at romcomma/gpf/models.py:81, romcomma/gpr/models.py:439 and inside gpflow base_conditional.
+ * `work` (rc_potrf_bufsize bytes) receives the inverted 128x128 diagonal blocks and per-block log-determinant sums that
+ * rc_logdet / rc_trsv / rc_trsm_fwd / rc_potri consume. */
+size_t rc_potrf_bufsize(int n_pad, int batch);
+int rc_potrf(double* A, int n_pad, long ld, long strideA, int batch, void* work, int* info, rc_stream_t stream);
+/* out[z] = sum_i log L_ii  (gpflow multivariate_normal, used at romcomma/gpf/models.py:82) */
+int rc_logdet(const void* work, int n_pad, int batch, double* out, rc_stream_t stream);
+/* x = L^-1 w (transpose = 0) or L^-T w (transpose = 1); w is overwritten.  tf.linalg.triangular_solve in
+ * multivariate_normal; the two solves of tf.linalg.cholesky_solve at romcomma/gpr/models.py:444. */
+int rc_trsv(const double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* w, double* x, long strideV,
+            int transpose, rc_stream_t stream);
+/* B <- L^-1 B, B is n_pad x nrhs_pad (multiple of 128): `A = Lm^-1 Kmn` of gpflow base_conditional (romcomma/gpf/models.py:97). */
+int rc_trsm_fwd(const double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* B, int nrhs_pad, long ldb,
+                long strideB, rc_stream_t stream);
+/* A (holding L) <- L^-1 in place, Kinv (lower 128-tiles) <- L^-T L^-1.  Kinv doubles as scratch and must hold n_pad*ldk doubles
+ * per matrix.  Provides the explicit inverse behind the analytic gradient that replaces tf.GradientTape through
+ * CholeskyGrad (romcomma/gpr/models.py:359-361). */
+int rc_potri(double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* Kinv, long ldk, long strideK,
+             rc_stream_t stream);
+/* Layout helpers between caller matrices (n x n dense) and padded storage. */
+int rc_pad_identity(const double* src, int n, long stride_src, double* dst, int n_pad, long ld, long stride_dst, int batch, rc_stream_t stream);
+int rc_extract_lower(const double* src, long ld, long stride_src, double* dst, int n, long stride_dst, int batch, int symmetrize,
+                     rc_stream_t stream);
+
+/* ---- fused LML + gradient ------------------------------------------------------------------------------------------
+ * One evaluation of MOGPR.log_marginal_likelihood (romcomma/gpf/models.py:73-82) or of gpflow GPR.log_marginal_likelihood
+ * per output (variant path), plus its gradient with respect to the ENTRIES of F, E and the lengthscales - the quantity
+ * tf.GradientTape delivers inside gf.optimizers.Scipy.minimize (romcomma/gpr/models.py:359-361) before the chain rule
+ * through the Variance / softplus parametrisation, which stays on the host (L x L work).
+ * Problem z of `batch` uses outputs Y[:, z*L:(z+1)*L] (Y is N x (batch*L) row-major), ls + z*L*M, F + z*L*L, E + z*L*L.
+ * Covariant model: batch = 1; variant model: batch = number of outputs, L = 1.
+ * Kunit (optional, may be NULL; batch == 1 only): cached unpadded (L*N)^2 unit gram, ld = L*N.
+ * flags: RC_GRAD_NONE = value only, RC_GRAD_VARIANCE = dF and dE, RC_GRAD_LENGTHSCALES adds dls.
+ * out[z*rc_lml_grad_stride(L,M) + ...] = { lml, dF[L*L], dE[L*L], dls[L*M] }   (entries not requested are zero). */
+#define RC_GRAD_NONE 0
+#define RC_GRAD_VARIANCE 1
+#define RC_GRAD_LENGTHSCALES 2
+int rc_lml_grad_stride(int L, int M);
+size_t rc_lml_grad_bufsize(int N, int M, int L, int batch, int flags);
+int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch, const double* ls, const double* F, const double* E,
+                const double* Kunit, int flags, void* work, size_t work_bytes, double* out, int* info, rc_stream_t stream);
+
+/* ---- prediction reductions -----------------------------------------------------------------------------------------
+ * With A = L^-1 Kmn (n_pad x c_pad, from rc_trsm_fwd) and a = L^-1 y: mean[c] = sum_k A[k][c] a[k], ss[c] = sum_k A[k][c]^2,
+ * i.e. fmean and the diagonal of A^T A of gpflow base_conditional (romcomma/gpf/models.py:97-109) without forming the full
+ * (L n*)^2 covariance.  parts: rc_predict_bufsize bytes. */
+size_t rc_predict_bufsize(int c_pad, int batch);
+int rc_predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n_pad, int c_pad, int batch, void* parts,
+                      double* mean, double* ss, rc_stream_t stream);
+
+/* ---- Sobol ---------------------------------------------------------------------------------------------------------
+ * rc_sobol_prepare: Phi, g0, g0KY (mean-centred) of ClosedSobol._calibrate / _Lambda2 (romcomma/gsa/calibrators.py:82-92,99-109,
+ * 134-138).  P = L (is_F_diagonal) or L*L.  Lam (L,M); F (L) if diagonal else (L,L); KinvY (L,N).  Outputs Phi (P,M), g0 (P,N),
+ * g0KY (P,N).
+ * rc_sobol_contract: V[s][l][j] for a list of marginal subsets - ClosedSobol._V / marginalize (romcomma/gsa/calibrators.py:49-80)
+ * and the slice loop of GSA.calibrate (romcomma/gsa/models.py:127-134).  masks_host[s] has bit m set iff input m is in subset s
+ * (the reference's slice [m0:m1] is bits m0..m1-1; M <= 64).  c is g0KY (P,N).  parts: rc_sobol_bufsize bytes. */
+size_t rc_sobol_bufsize(int N, int P, int nslices);
+int rc_sobol_prepare(const double* X, int N, int M, const double* Lam, const double* F, const double* KinvY, int L, int is_F_diagonal,
+                     double* Phi, double* g0, double* g0KY, rc_stream_t stream);
+int rc_sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int is_F_diagonal,
+                      const unsigned long long* masks_host, int nslices, void* parts, double* V, rc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

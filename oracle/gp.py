@@ -1,0 +1,279 @@
+"""Oracle (float64 numpy/scipy) for gram, LML, gradients and prediction.  TEST INFRASTRUCTURE ONLY.
+
+Two model families, exactly as the reference dispatches them (romcomma/gpr/models.py:332-343):
+
+* covariant ("mo"): one (LN,LN) gram, romcomma/gpf/kernels.py:74-113,153-154 + gpf/likelihoods.py:64-67 +
+  gpf/models.py:73-111.  Index (l,n) -> l*N+n (gpf/kernels.py:103-104), y = vec(Y^T) (gpf/models.py:130).
+* variant ("rbf"): L independent gpflow ``GPR(kernels.RBF, likelihoods.Gaussian)`` models
+  (gpr/models.py:340-342, gpr/kernels.py:176-177); gpflow's ``square_distance`` form of r^2.
+
+Hyper-parameter transforms follow gpflow ``positive()`` (softplus, optionally shifted), see
+romcomma/gpf/base.py:88-94 and gpflow.likelihoods.Gaussian (lower bound 1e-6).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+LOG2PI = np.log(2.0 * np.pi)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# transforms (gpflow.utilities.positive == tfp Softplus [+ Shift])
+# ----------------------------------------------------------------------------------------------------------------
+def softplus(u):
+    u = np.asarray(u, dtype=np.float64)
+    return np.logaddexp(0.0, u)
+
+
+def softplus_inverse(y):
+    y = np.asarray(y, dtype=np.float64)
+    return y + np.log(-np.expm1(-y))
+
+
+def sigmoid(u):
+    u = np.asarray(u, dtype=np.float64)
+    return 0.5 * (1.0 + np.tanh(0.5 * u))
+
+
+def variance_unpack(u_diag, lower, floor=1e-3):
+    """gpf/base.py:42-55 - Variance.cholesky / .value from (unconstrained diagonal, strict lower triangle row-major)."""
+    L = len(u_diag)
+    C = np.zeros((L, L))
+    C[np.tril_indices(L, -1)] = np.asarray(lower, dtype=np.float64)  # row-major strict lower == mask of base.py:93
+    C[np.diag_indices(L)] = softplus(u_diag) + floor
+    return C, C @ C.T
+
+
+def variance_pack(value, floor=1e-3):
+    """gpf/base.py:71-96 - the parameters a Variance(value) is created with."""
+    value = np.atleast_2d(np.asarray(value, dtype=np.float64))
+    C = np.linalg.cholesky(value)
+    d = np.diag(C).copy()
+    if d.min() <= floor:
+        raise ValueError('Cholesky diagonal must exceed its lower bound')
+    return softplus_inverse(d - floor), C[np.tril_indices(len(d), -1)].copy()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# covariant gram
+# ----------------------------------------------------------------------------------------------------------------
+def gram_mo_unit(X, X2, ls):
+    """K_unit[l,n,l',n'] = exp(-1/2 sum_m (X[n,m]/ls[l,m] - X2[n',m]/ls[l',m])^2), gpf/kernels.py:82,154. Returns (L,N,L,N2)."""
+    X, X2, ls = np.asarray(X, float), np.asarray(X if X2 is None else X2, float), np.atleast_2d(np.asarray(ls, float))
+    L = ls.shape[0]
+    A = X[None, :, :] / ls[:, None, :]       # (L,N,M)
+    B = X2[None, :, :] / ls[:, None, :]      # (L,N2,M)
+    out = np.empty((L, X.shape[0], L, X2.shape[0]))
+    for l in range(L):
+        for j in range(L):
+            d = A[l][:, None, :] - B[j][None, :, :]
+            out[l, :, j, :] = np.exp(-0.5 * np.einsum('abm,abm->ab', d, d))
+    return out
+
+
+def gram_mo(X, X2, ls, F):
+    """gpf/kernels.py:94-116: (LN, LN2) = reshape(F[l,1,l',1] * K_unit)."""
+    K = gram_mo_unit(X, X2, ls)
+    F = np.asarray(F, float)
+    L, N, _, N2 = K.shape
+    return (F[:, None, :, None] * K).reshape(L * N, L * N2)
+
+
+def add_noise_mo(K, E):
+    """gpf/likelihoods.py:64-67 + gpf/base.py:62-69: K + E[l,l'] * delta(n,n')."""
+    E = np.asarray(E, float)
+    L = E.shape[0]
+    N = K.shape[0] // L
+    return K + np.kron(E, np.eye(N))
+
+
+def diag_noise(noise_variance, L):
+    """gpf/models.py:131-133 (quirk Q1): noise is always broadcast to (L,L) and stripped to its diagonal."""
+    return np.diag(np.diag(np.broadcast_to(np.asarray(noise_variance, float), (L, L))))
+
+
+def lml_from_K(K, y):
+    """gpflow.logdensities.multivariate_normal with mu = 0, as used at gpf/models.py:81-82."""
+    Lc = np.linalg.cholesky(K)
+    alpha = sla.solve_triangular(Lc, y, lower=True)
+    return float(-0.5 * alpha @ alpha - 0.5 * len(y) * LOG2PI - np.log(np.diag(Lc)).sum()), Lc, alpha
+
+
+def lml_mo(X, Y, ls, F, E):
+    X, Y = np.asarray(X, float), np.asarray(Y, float)
+    y = Y.T.reshape(-1)
+    K = add_noise_mo(gram_mo(X, None, ls, F), E)
+    return lml_from_K(K, y)[0]
+
+
+def lml_grad_mo(X, Y, ls, F, E):
+    """LML and its gradient w.r.t. the entries of F, E (treated as independent) and the lengthscales.
+
+    Returns dict(lml, dF (L,L), dE (L,L), dls (L,M)).  W = a a^T - K^-1, dLML/dtheta = 1/2 tr(W dK/dtheta).
+    """
+    X, Y, ls, F, E = (np.asarray(a, float) for a in (X, Y, np.atleast_2d(ls), F, E))
+    N, M = X.shape
+    L = Y.shape[1]
+    y = Y.T.reshape(-1)
+    U = gram_mo_unit(X, None, ls)
+    K = add_noise_mo((F[:, None, :, None] * U).reshape(L * N, L * N), E)
+    lml, Lc, _ = lml_from_K(K, y)
+    Kinv = sla.cho_solve((Lc, True), np.eye(L * N))
+    a = Kinv @ y
+    W = (np.outer(a, a) - Kinv).reshape(L, N, L, N)
+    dF = 0.5 * np.einsum('anbm,anbm->ab', W, U)
+    dE = 0.5 * np.einsum('anbn->ab', W)
+    WFU = W * F[:, None, :, None] * U
+    Xs = X[None, :, :] / ls[:, None, :]                       # (L,N,M)
+    dls = np.zeros((L, M))
+    for l in range(L):
+        for j in range(L):
+            d = Xs[l][:, None, :] - Xs[j][None, :, :]          # (N,N,M)
+            dls[l] += np.einsum('ab,abm,am->m', WFU[l, :, j, :], d, X / ls[l] ** 2)
+    return {'lml': lml, 'dF': dF, 'dE': dE, 'dls': dls}
+
+
+def chain_variance(dV, u_diag, lower, floor=1e-3):
+    """Push d/dV (entries independent) through V = C C^T and the softplus(+floor) diagonal (gpf/base.py:42-55,88-94)."""
+    C, _ = variance_unpack(u_diag, lower, floor)
+    dC = np.tril((dV + dV.T) @ C)
+    return np.diag(dC) * sigmoid(u_diag), dC[np.tril_indices(len(u_diag), -1)]
+
+
+def predict_mo(X, Y, ls, F, E, Xs, y_instead_of_f=True):
+    """gpf/models.py:84-111 + gpflow base_conditional + gpf/likelihoods.py:80-89. Returns (mean (n,L), var (n,L))."""
+    X, Y, ls, F, E, Xs = (np.asarray(a, float) for a in (X, Y, np.atleast_2d(ls), F, E, Xs))
+    L = Y.shape[1]
+    n = Xs.shape[0]
+    y = Y.T.reshape(-1)
+    Kmm = add_noise_mo(gram_mo(X, None, ls, F), E)
+    Kmn = gram_mo(X, Xs, ls, F)
+    Lm = np.linalg.cholesky(Kmm)
+    A = sla.solve_triangular(Lm, Kmn, lower=True)
+    knn_diag = np.repeat(np.diag(F), n)                       # diag of kernel(Xs, Xs): F[l,l] * exp(0)
+    fvar = knn_diag - np.einsum('ki,ki->i', A, A)
+    A = sla.solve_triangular(Lm.T, A, lower=False)
+    fmean = A.T @ y
+    mean, var = fmean.reshape(L, n).T, fvar.reshape(L, n).T
+    if y_instead_of_f:
+        var = var + np.diag(E)[None, :]
+    return mean, var
+
+
+def k_cho_mo(X, ls, F, E):
+    """gpr/models.py:427-431,439 (covariant): chol(add_to(KXX)), shape (LN,LN)."""
+    return np.linalg.cholesky(add_noise_mo(gram_mo(X, None, ls, F), E))
+
+
+def k_inv_y_mo(X, Y, ls, F, E):
+    """gpr/models.py:441-444 (covariant): cholesky_solve(K_cho, vec(Y^T)) reshaped (L,1,N)."""
+    Y = np.asarray(Y, float)
+    Lc = k_cho_mo(X, ls, F, E)
+    return sla.cho_solve((Lc, True), Y.T.reshape(-1)).reshape(Y.shape[1], 1, Y.shape[0])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# variant path: gpflow GPR + kernels.RBF (SquaredExponential) + likelihoods.Gaussian
+# ----------------------------------------------------------------------------------------------------------------
+def gram_rbf(X, X2, ls, variance):
+    """gpflow SquaredExponential: variance * exp(-1/2 square_distance(X/ls, X2/ls)), with
+    square_distance = -2 X X2^T + |X|^2 + |X2|^2 (gpflow.utilities.ops.square_distance)."""
+    X = np.asarray(X, float) / np.asarray(ls, float)
+    if X2 is None:
+        Xs = np.sum(X * X, axis=-1, keepdims=True)
+        r2 = -2.0 * (X @ X.T) + Xs + Xs.T
+    else:
+        X2 = np.asarray(X2, float) / np.asarray(ls, float)
+        r2 = -2.0 * (X @ X2.T) + np.sum(X * X, -1)[:, None] + np.sum(X2 * X2, -1)[None, :]
+    return variance * np.exp(-0.5 * r2)
+
+
+def lml_rbf(X, y, ls, variance, noise):
+    """gpflow.models.GPR.log_marginal_likelihood for one output column y (N,)."""
+    K = gram_rbf(X, None, ls, variance)
+    K[np.diag_indices_from(K)] += noise
+    return lml_from_K(K, np.asarray(y, float).reshape(-1))[0]
+
+
+def lml_grad_rbf(X, y, ls, variance, noise):
+    """LML and d/d(ls[m]), d/d(variance), d/d(noise) for one gpflow GPR (variant)."""
+    X, y, ls = np.asarray(X, float), np.asarray(y, float).reshape(-1), np.broadcast_to(np.asarray(ls, float), (np.shape(X)[1],))
+    Kf = gram_rbf(X, None, ls, variance)
+    K = Kf.copy()
+    K[np.diag_indices_from(K)] += noise
+    lml, Lc, _ = lml_from_K(K, y)
+    Kinv = sla.cho_solve((Lc, True), np.eye(len(y)))
+    a = Kinv @ y
+    W = np.outer(a, a) - Kinv
+    WK = W * Kf
+    d2 = (X[:, None, :] - X[None, :, :]) ** 2
+    return {'lml': lml, 'dls': 0.5 * np.einsum('ab,abm->m', WK, d2) / ls ** 3,
+            'dvariance': 0.5 * WK.sum() / variance, 'dnoise': 0.5 * np.trace(W)}
+
+
+def predict_rbf(X, y, ls, variance, noise, Xs, y_instead_of_f=True):
+    """gpflow.models.GPR.predict_f / predict_y (full_cov=False) for one output. Returns (mean (n,), var (n,))."""
+    X, y, Xs = np.asarray(X, float), np.asarray(y, float).reshape(-1), np.asarray(Xs, float)
+    Kmm = gram_rbf(X, None, ls, variance)
+    Kmm[np.diag_indices_from(Kmm)] += noise
+    Kmn = gram_rbf(X, Xs, ls, variance)
+    Lm = np.linalg.cholesky(Kmm)
+    A = sla.solve_triangular(Lm, Kmn, lower=True)
+    fvar = variance - np.einsum('ki,ki->i', A, A)
+    A = sla.solve_triangular(Lm.T, A, lower=False)
+    mean = A.T @ y
+    return mean, fvar + (noise if y_instead_of_f else 0.0)
+
+
+def k_cho_rbf(X, ls, variance, noise):
+    """gpr/models.py:432-439 (variant): stacked (L,N,N) Cholesky factors. ls (L,M), variance (L,), noise (L,)."""
+    out = []
+    for l in range(len(variance)):
+        K = gram_rbf(X, None, ls[l], variance[l])
+        K[np.diag_indices_from(K)] += noise[l]
+        out.append(np.linalg.cholesky(K))
+    return np.stack(out)
+
+
+def k_inv_y_rbf(X, Y, ls, variance, noise):
+    """gpr/models.py:441-444 (variant): (L,1,N)."""
+    Y = np.asarray(Y, float)
+    cho = k_cho_rbf(X, ls, variance, noise)
+    return np.stack([sla.cho_solve((cho[l], True), Y[:, l]) for l in range(Y.shape[1])])[:, None, :]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the timed CPU unit: one LML + gradient evaluation through LAPACK (potrf + potri), blocked gram
+# ----------------------------------------------------------------------------------------------------------------
+def lml_grad_mo_lapack(X, Y, ls, F, E, with_lengthscales=False):
+    """Same numbers as lml_grad_mo, organised the way a tuned CPU code would run it (dpotrf + dpotri through OpenBLAS,
+    gram built block by block); used as bench.py's cpu_baseline.  Memory: 2 n^2 doubles."""
+    X, Y, ls, F, E = (np.asarray(a, float) for a in (X, Y, np.atleast_2d(ls), F, E))
+    N, M = X.shape
+    L = Y.shape[1]
+    n = L * N
+    y = Y.T.reshape(-1)
+    U = np.empty((n, n))
+    Xs = X[None, :, :] / ls[:, None, :]
+    sq = np.einsum('lnm,lnm->ln', Xs, Xs)
+    for l in range(L):
+        for j in range(L):
+            r2 = sq[l][:, None] + sq[j][None, :] - 2.0 * (Xs[l] @ Xs[j].T)  # blocked BLAS form; fine for a timing baseline
+            np.exp(-0.5 * r2, out=U[l * N:(l + 1) * N, j * N:(j + 1) * N])
+    K = U * np.kron(F, np.ones((N, N)))
+    K += np.kron(E, np.eye(N))
+    c, info = sla.lapack.dpotrf(K, lower=1, overwrite_a=1)
+    if info != 0:
+        raise np.linalg.LinAlgError(f'dpotrf info={info}')
+    alpha = sla.solve_triangular(c, y, lower=True)
+    lml = float(-0.5 * alpha @ alpha - 0.5 * n * LOG2PI - np.log(np.diag(c)).sum())
+    a = sla.solve_triangular(c, alpha, lower=True, trans='T')
+    Kinv, info = sla.lapack.dpotri(c, lower=1, overwrite_c=1)
+    Kinv = np.tril(Kinv) + np.tril(Kinv, -1).T
+    W = np.outer(a, a) - Kinv
+    W4, U4 = W.reshape(L, N, L, N), U.reshape(L, N, L, N)
+    out = {'lml': lml, 'dF': 0.5 * np.einsum('anbm,anbm->ab', W4, U4), 'dE': 0.5 * np.einsum('anbn->ab', W4)}
+    if with_lengthscales:
+        out['dls'] = lml_grad_mo(X, Y, ls, F, E)['dls']
+    return out

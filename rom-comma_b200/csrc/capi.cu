@@ -1,0 +1,252 @@
+// extern "C" boundary (include/romcomma_b200.h).  Plain pointers and sizes only; no torch types.
+#include "../../include/romcomma_b200.h"
+#include "chol.h"
+#include "common.cuh"
+#include "gp_ops.h"
+#include "sobol.h"
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+
+namespace rc {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
+struct PotrfWork {
+  double* dinv;
+  double* logdet_parts;
+};
+static PotrfWork split_potrf_work(void* work, int n_pad, int batch) {
+  PotrfWork w;
+  w.dinv = static_cast<double*>(work);
+  w.logdet_parts = w.dinv + (size_t)batch * (n_pad / TILE) * TILE * TILE;
+  return w;
+}
+
+// y_z[l*N + n] = Y[n][z*L + l], zero padded
+__global__ void pack_y_kernel(const double* __restrict__ Y, int N, int L, int batch, int n_pad, double* __restrict__ y) {
+  const int z = blockIdx.y;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (long)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    if (i < (long)L * N) {
+      const int l = (int)(i / N), n = (int)(i - (long)l * N);
+      v = Y[(long)n * (batch * L) + z * L + l];
+    }
+    y[(long)z * n_pad + i] = v;
+  }
+}
+
+// out_z = { lml, dF, dE, dls } from the raw sums { SF, SE, dls_row, dls_col }
+__global__ void lml_finalize_kernel(const double* __restrict__ logdet, const double* __restrict__ quad, const double* __restrict__ raw, int L, int M,
+                                    int n_real, int flags, double* __restrict__ out) {
+  const int z = blockIdx.x;
+  const int stride = 1 + 2 * L * L + L * M, nvals = 2 * L * L + 2 * L * M;
+  double* o = out + (long)z * stride;
+  const double* r = raw + (long)z * nvals;
+  for (int e = threadIdx.x; e < stride; e += blockDim.x) {
+    double v = 0.0;
+    if (e == 0) {
+      v = -0.5 * quad[z] - 0.5 * (double)n_real * 1.8378770664093454835606594728112 - logdet[z];
+    } else if (flags != RC_GRAD_NONE) {
+      const int k = e - 1;
+      if (k < 2 * L * L) {
+        const int which = k / (L * L), ij = k - which * L * L, i = ij / L, j = ij - i * L;
+        const int hi = max(i, j), lo = min(i, j);
+        v = 0.5 * r[which * L * L + hi * L + lo];
+      } else if (flags & RC_GRAD_LENGTHSCALES) {
+        const int lm = k - 2 * L * L;
+        v = r[2 * L * L + lm] + r[2 * L * L + L * M + lm];
+      }
+    }
+    o[e] = v;
+  }
+}
+}  // namespace rc
+
+using namespace rc;
+
+extern "C" {
+
+int rc_version(void) { return 100; }
+const char* rc_last_error(void) { return g_err; }
+int rc_padded(int n) { return round_up(n, TILE); }
+
+int rc_gram(const double* X, int N, const double* X2, int N2, int M, const double* ls, int L, const double* F, const double* E, double* out,
+            long ld_out, long stride_out, int rows_pad, int cols_pad, int lower_only, int pad_identity, int batch, rc_stream_t stream) {
+  RC_REQUIRE(X && ls && out && N > 0 && M > 0 && L > 0 && batch > 0, -2, "rc_gram: null pointer or non-positive size");
+  GramArgs a{};
+  a.X = X; a.N = N;
+  a.X2 = X2 ? X2 : X; a.N2 = X2 ? N2 : N;
+  a.M = M; a.L = L;
+  a.ls = ls; a.stride_ls = (long)L * M;
+  a.F = F; a.E = E; a.stride_FE = (long)L * L;
+  a.out = out; a.ld_out = ld_out; a.stride_out = stride_out;
+  a.rows_pad = rows_pad; a.cols_pad = cols_pad;
+  a.lower_only = lower_only; a.pad_identity = pad_identity;
+  RC_REQUIRE(rows_pad >= L * a.N && cols_pad >= L * a.N2 && ld_out >= cols_pad, -2, "rc_gram: padded sizes too small");
+  return gram(a, batch, (cudaStream_t)stream);
+}
+
+int rc_apply_variance_noise(const double* Kunit, long ldu, const double* F, const double* E, int L, int N, int n_pad, double* out, long ld_out,
+                            int lower_only, rc_stream_t stream) {
+  RC_REQUIRE(Kunit && F && out, -2, "rc_apply_variance_noise: null pointer");
+  return apply_variance_noise(Kunit, ldu, F, E, L, N, n_pad, out, ld_out, lower_only, (cudaStream_t)stream);
+}
+
+size_t rc_potrf_bufsize(int n_pad, int batch) { return align256(potrf_workspace_bytes(n_pad, batch)); }
+
+int rc_potrf(double* A, int n_pad, long ld, long strideA, int batch, void* work, int* info, rc_stream_t stream) {
+  RC_REQUIRE(A && work && info, -2, "rc_potrf: null pointer");
+  PotrfWork w = split_potrf_work(work, n_pad, batch);
+  return potrf_lower(A, n_pad, ld, strideA, batch, w.dinv, w.logdet_parts, info, (cudaStream_t)stream);
+}
+
+int rc_logdet(const void* work, int n_pad, int batch, double* out, rc_stream_t stream) {
+  PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, batch);
+  return sum_parts(w.logdet_parts, n_pad / TILE, batch, out, 1.0, (cudaStream_t)stream);
+}
+
+int rc_trsv(const double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* wv, double* x, long strideV, int transpose,
+            rc_stream_t stream) {
+  PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, batch);
+  return trsv_lower(A, n_pad, ld, strideA, batch, w.dinv, wv, x, strideV, transpose, (cudaStream_t)stream);
+}
+
+int rc_trsm_fwd(const double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* B, int nrhs_pad, long ldb, long strideB,
+                rc_stream_t stream) {
+  PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, batch);
+  return trsm_lower_fwd(A, n_pad, ld, strideA, batch, w.dinv, B, nrhs_pad, ldb, strideB, (cudaStream_t)stream);
+}
+
+int rc_potri(double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* Kinv, long ldk, long strideK, rc_stream_t stream) {
+  PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, batch);
+  int rc = trtri_lower(A, n_pad, ld, strideA, batch, w.dinv, Kinv, strideK, (cudaStream_t)stream);
+  if (rc) return rc;
+  return lauum_lower(A, n_pad, ld, strideA, batch, Kinv, ldk, strideK, (cudaStream_t)stream);
+}
+
+int rc_pad_identity(const double* src, int n, long stride_src, double* dst, int n_pad, long ld, long stride_dst, int batch, rc_stream_t stream) {
+  return pad_identity(src, n, stride_src, dst, n_pad, ld, stride_dst, batch, (cudaStream_t)stream);
+}
+
+int rc_extract_lower(const double* src, long ld, long stride_src, double* dst, int n, long stride_dst, int batch, int symmetrize,
+                     rc_stream_t stream) {
+  return extract_lower(src, ld, stride_src, dst, n, stride_dst, batch, symmetrize, (cudaStream_t)stream);
+}
+
+int rc_lml_grad_stride(int L, int M) { return 1 + 2 * L * L + L * M; }
+
+namespace {
+struct LmlLayout {
+  size_t A, Kinv, potrf, vec, scal, gparts, graw, total;
+  int n_pad;
+};
+LmlLayout lml_layout(int N, int M, int L, int batch, int flags) {
+  LmlLayout o{};
+  o.n_pad = round_up(L * N, TILE);
+  const size_t mat = align256((size_t)batch * o.n_pad * o.n_pad * sizeof(double));
+  size_t off = 0;
+  o.A = off; off += mat;
+  o.Kinv = off; off += (flags != RC_GRAD_NONE) ? mat : 0;
+  o.potrf = off; off += align256(potrf_workspace_bytes(o.n_pad, batch));
+  o.vec = off; off += align256((size_t)4 * batch * o.n_pad * sizeof(double));
+  o.scal = off; off += align256((size_t)2 * batch * sizeof(double));
+  o.gparts = off; off += (flags != RC_GRAD_NONE) ? align256(grad_workspace_bytes(o.n_pad, L, M, batch)) : 0;
+  o.graw = off; off += align256((size_t)batch * grad_nvals(L, M) * sizeof(double));
+  o.total = off;
+  return o;
+}
+}  // namespace
+
+size_t rc_lml_grad_bufsize(int N, int M, int L, int batch, int flags) { return lml_layout(N, M, L, batch, flags).total; }
+
+int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch, const double* ls, const double* F, const double* E,
+                const double* Kunit, int flags, void* work, size_t work_bytes, double* out, int* info, rc_stream_t stream) {
+  RC_REQUIRE(X && Y && ls && F && E && work && out && info, -2, "rc_lml_grad: null pointer");
+  RC_REQUIRE(N > 0 && M > 0 && L > 0 && batch > 0, -2, "rc_lml_grad: non-positive size");
+  RC_REQUIRE(!Kunit || batch == 1, -2, "rc_lml_grad: a cached unit gram is only supported for batch == 1");
+  const LmlLayout lay = lml_layout(N, M, L, batch, flags);
+  RC_REQUIRE(work_bytes >= lay.total, -2, "rc_lml_grad: workspace too small (%zu < %zu)", work_bytes, lay.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = static_cast<char*>(work);
+  const int n_pad = lay.n_pad, n = L * N;
+  const long mat = (long)n_pad * n_pad;
+  double* A = reinterpret_cast<double*>(base + lay.A);
+  double* Kinv = reinterpret_cast<double*>(base + lay.Kinv);
+  PotrfWork pw = split_potrf_work(base + lay.potrf, n_pad, batch);
+  double* yv = reinterpret_cast<double*>(base + lay.vec);
+  double* alpha = yv + (size_t)batch * n_pad;
+  double* wv = alpha + (size_t)batch * n_pad;
+  double* kinvy = wv + (size_t)batch * n_pad;
+  double* logdet = reinterpret_cast<double*>(base + lay.scal);
+  double* quad = logdet + batch;
+  double* gparts = reinterpret_cast<double*>(base + lay.gparts);
+  double* graw = reinterpret_cast<double*>(base + lay.graw);
+  int rc;
+  // 1. K = F (x) Kunit + E (x) I, lower tiles, identity padding
+  if (Kunit) {
+    if ((rc = apply_variance_noise(Kunit, n, F, E, L, N, n_pad, A, n_pad, 1, st))) return rc;
+  } else {
+    GramArgs g{};
+    g.X = X; g.N = N; g.X2 = X; g.N2 = N; g.M = M; g.L = L;
+    g.ls = ls; g.stride_ls = (long)L * M; g.F = F; g.E = E; g.stride_FE = (long)L * L;
+    g.out = A; g.ld_out = n_pad; g.stride_out = mat; g.rows_pad = n_pad; g.cols_pad = n_pad; g.lower_only = 1; g.pad_identity = 1;
+    if ((rc = gram(g, batch, st))) return rc;
+  }
+  // 2. factor, log-determinant
+  if ((rc = potrf_lower(A, n_pad, n_pad, mat, batch, pw.dinv, pw.logdet_parts, info, st))) return rc;
+  if ((rc = sum_parts(pw.logdet_parts, n_pad / TILE, batch, logdet, 1.0, st))) return rc;
+  // 3. alpha = L^-1 y, quad = alpha^T alpha
+  pack_y_kernel<<<dim3((n_pad + 255) / 256, batch), 256, 0, st>>>(Y, N, L, batch, n_pad, yv);
+  RC_LAUNCH_OK();
+  if ((rc = trsv_lower(A, n_pad, n_pad, mat, batch, pw.dinv, yv, alpha, n_pad, 0, st))) return rc;
+  if ((rc = dot_batched(alpha, alpha, n_pad, n_pad, batch, quad, st))) return rc;
+  RC_CUDA_OK(cudaMemsetAsync(graw, 0, (size_t)batch * grad_nvals(L, M) * sizeof(double), st));
+  if (flags != RC_GRAD_NONE) {
+    // 4. K^-1 y = L^-T alpha ; K^-1 = L^-T L^-1
+    RC_CUDA_OK(cudaMemcpyAsync(wv, alpha, (size_t)batch * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if ((rc = trsv_lower(A, n_pad, n_pad, mat, batch, pw.dinv, wv, kinvy, n_pad, 1, st))) return rc;
+    if ((rc = trtri_lower(A, n_pad, n_pad, mat, batch, pw.dinv, Kinv, mat, st))) return rc;
+    if ((rc = lauum_lower(A, n_pad, n_pad, mat, batch, Kinv, n_pad, mat, st))) return rc;
+    // 5. contractions
+    GradArgs ga{};
+    ga.X = X; ga.N = N; ga.M = M; ga.L = L; ga.ls = ls; ga.stride_ls = (long)L * M; ga.F = F; ga.stride_FE = (long)L * L;
+    ga.Kinv = Kinv; ga.ldk = n_pad; ga.stride_K = mat; ga.alpha = kinvy; ga.stride_alpha = n_pad; ga.parts = gparts;
+    ga.with_ls = (flags & RC_GRAD_LENGTHSCALES) ? 1 : 0;
+    if ((rc = grad_reduce(ga, n_pad, batch, graw, st))) return rc;
+  }
+  lml_finalize_kernel<<<batch, 128, 0, st>>>(logdet, quad, graw, L, M, n, flags, out);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+size_t rc_predict_bufsize(int c_pad, int batch) { return align256(predict_workspace_bytes(c_pad, batch)); }
+
+int rc_predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n_pad, int c_pad, int batch, void* parts,
+                      double* mean, double* ss, rc_stream_t stream) {
+  RC_REQUIRE(A && a && parts && mean && ss, -2, "rc_predict_reduce: null pointer");
+  return predict_reduce(A, lda, strideA, a, stride_a, n_pad, c_pad, batch, static_cast<double*>(parts), mean, ss, (cudaStream_t)stream);
+}
+
+size_t rc_sobol_bufsize(int N, int P, int nslices) { return align256(sobol_workspace_bytes(N, P, nslices)); }
+
+int rc_sobol_prepare(const double* X, int N, int M, const double* Lam, const double* F, const double* KinvY, int L, int is_F_diagonal, double* Phi,
+                     double* g0, double* g0KY, rc_stream_t stream) {
+  RC_REQUIRE(X && Lam && F && KinvY && Phi && g0 && g0KY, -2, "rc_sobol_prepare: null pointer");
+  return sobol_prepare(X, N, M, Lam, F, KinvY, L, is_F_diagonal, Phi, g0, g0KY, (cudaStream_t)stream);
+}
+
+int rc_sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int is_F_diagonal,
+                      const unsigned long long* masks_host, int nslices, void* parts, double* V, rc_stream_t stream) {
+  RC_REQUIRE(X && Phi && c && masks_host && parts && V && nslices > 0, -2, "rc_sobol_contract: null pointer or empty subset list");
+  return sobol_contract(X, N, M, Phi, c, L, is_F_diagonal ? 1 : L, masks_host, nslices, static_cast<double*>(parts), V, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,406 @@
+// Blocked FP64 Cholesky, triangular solves, triangular inverse and LAUUM on row-major lower-triangular storage.
+// Replaces the tf.linalg.cholesky / triangular_solve / cholesky_solve call sites of the reference
+// (romcomma/gpf/models.py:81-82, romcomma/gpr/models.py:439,444, gpflow base_conditional) and provides the explicit
+// inverse the analytic LML gradient needs.  All O(n^3) work runs through gemm_dmma_kernel.
+//
+// Conventions: n is a multiple of 128 (callers pad with identity), `ld` is the row stride in doubles, `batch` independent
+// matrices are `strideA` doubles apart.  `dinv` holds one 128x128 inverse per diagonal block (upper triangle zero):
+// block b of batch z lives at dinv + z*strideD + b*128*128.
+#include "chol.h"
+#include "gemm_dmma.cuh"
+
+namespace rc {
+
+// ----------------------------------------------------------------------------------------------------------------
+// Diagonal block: L = chol(A_kk) in place (lower part only is read/written), Dinv = L^-1, partial log-determinant.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int DB = 128;
+constexpr int DB_LD = DB + 1;
+constexpr int DB_THREADS = 256;
+constexpr size_t DB_SMEM = (size_t)(DB * DB_LD + 2 * DB + 32) * sizeof(double);
+
+__global__ void __launch_bounds__(DB_THREADS, 1)
+diag_potrf_inv_kernel(double* __restrict__ A, long ld, long strideA, double* __restrict__ dinv, long strideD, int blk,
+                      double* __restrict__ logdet_parts, int nblk, int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;
+  double* part = sm + DB * DB_LD;      // [2][DB]
+  double* red = part + 2 * DB;
+  const int tid = threadIdx.x, z = blockIdx.x;
+  double* Ab = A + (long)z * strideA + (long)blk * DB * (ld + 1);
+  double* Db = dinv + (long)z * strideD + (long)blk * DB * DB;
+
+  for (int idx = tid; idx < DB * DB; idx += DB_THREADS) {
+    const int i = idx >> 7, j = idx & 127;
+    S[i * DB_LD + j] = (j <= i) ? Ab[(long)i * ld + j] : 0.0;
+  }
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int j = 0; j < DB; ++j) {
+    __syncthreads();
+    const double d = S[j * DB_LD + j];
+    if (!(d > 0.0)) {
+      if (tid == 0) atomicCAS(info + z, 0, blk * DB + j + 1);
+    }
+    const double ljj = sqrt(d);
+    const double rinv = 1.0 / ljj;
+    for (int i = j + 1 + tid; i < DB; i += DB_THREADS) S[i * DB_LD + j] *= rinv;
+    __syncthreads();
+    if (tid == 0) S[j * DB_LD + j] = ljj;
+    for (int i = j + 1 + ty; i < DB; i += 16) {
+      const double li = S[i * DB_LD + j];
+      for (int c = j + 1 + tx; c <= i; c += 16) S[i * DB_LD + c] -= li * S[c * DB_LD + j];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < DB * DB; idx += DB_THREADS) {
+    const int i = idx >> 7, j = idx & 127;
+    if (j <= i) Ab[(long)i * ld + j] = S[i * DB_LD + j];
+  }
+  {
+    double v = (tid < DB) ? log(S[tid * DB_LD + tid]) : 0.0;
+    v = block_sum(v, red);
+    if (tid == 0) logdet_parts[(long)z * nblk + blk] = v;
+  }
+  // In-place inverse, row by row: X[i][j] = -(1/L_ii) sum_{k<i} L[i][k] X[k][j]  (X upper triangle is zero, so k starts at 0).
+  const int j = tid & (DB - 1), half = tid >> 7;
+  for (int i = 0; i < DB; ++i) {
+    __syncthreads();
+    const int kmid = i >> 1;
+    const int kb = half ? kmid : 0, ke = half ? i : kmid;
+    double s0 = 0.0, s1 = 0.0;
+    int k = kb;
+    for (; k + 1 < ke; k += 2) {
+      s0 = fma(S[i * DB_LD + k], S[k * DB_LD + j], s0);
+      s1 = fma(S[i * DB_LD + k + 1], S[(k + 1) * DB_LD + j], s1);
+    }
+    if (k < ke) s0 = fma(S[i * DB_LD + k], S[k * DB_LD + j], s0);
+    part[half * DB + j] = s0 + s1;
+    const double inv_ii = 1.0 / S[i * DB_LD + i];
+    __syncthreads();
+    if (half == 0) {
+      if (j < i) S[i * DB_LD + j] = -(part[j] + part[DB + j]) * inv_ii;
+      else if (j == i) S[i * DB_LD + i] = inv_ii;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < DB * DB; idx += DB_THREADS) {
+    const int i = idx >> 7, jj = idx & 127;
+    Db[idx] = (jj <= i) ? S[i * DB_LD + jj] : 0.0;
+  }
+}
+
+static int launch_diag(double* A, long ld, long strideA, double* dinv, long strideD, int blk, double* logdet_parts, int nblk, int* info,
+                       int batch, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    RC_CUDA_OK(cudaFuncSetAttribute(diag_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+    configured = true;
+  }
+  diag_potrf_inv_kernel<<<batch, DB_THREADS, DB_SMEM, st>>>(A, ld, strideA, dinv, strideD, blk, logdet_parts, nblk, info);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// potrf
+// ----------------------------------------------------------------------------------------------------------------
+size_t potrf_workspace_bytes(int n, int batch) {
+  const size_t nblk = (size_t)n / DB;
+  return (size_t)batch * nblk * DB * DB * sizeof(double)   // dinv
+         + (size_t)batch * nblk * sizeof(double);          // logdet parts
+}
+
+int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st) {
+  RC_REQUIRE(n > 0 && n % DB == 0, -2, "potrf_lower: n=%d must be a positive multiple of 128", n);
+  RC_REQUIRE(ld >= n && ld % 2 == 0, -2, "potrf_lower: ld=%ld must be even and >= n", ld);
+  const int nblk = n / DB;
+  const long strideD = (long)nblk * DB * DB;
+  RC_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
+  int rc;
+  auto trsm_panel = [&](int blk) -> int {   // rows below block `blk`, its 128 columns:  P <- P * Dinv^T
+    const int r0 = (blk + 1) * DB;
+    if (r0 >= n) return 0;
+    GemmArgs g{};
+    g.A = A + (long)r0 * ld + (long)blk * DB; g.lda = ld; g.strideA = strideA;
+    g.B = dinv + (long)blk * DB * DB; g.ldb = DB; g.strideB = strideD;
+    g.C = A + (long)r0 * ld + (long)blk * DB; g.ldc = ld; g.strideC = strideA;
+    g.M = n - r0; g.N = DB; g.K = DB; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kmode = K_FULL;
+    return launch_gemm<false, false>(g, batch, st);
+  };
+  for (int b0 = 0; b0 < nblk; b0 += 2) {
+    const int w = (b0 + 1 < nblk) ? 2 : 1;
+    if ((rc = launch_diag(A, ld, strideA, dinv, strideD, b0, logdet_parts, nblk, info, batch, st))) return rc;
+    if ((rc = trsm_panel(b0))) return rc;
+    if (w == 2) {
+      // columns of block b0+1, rows from block b0+1 down:  A -= P0 * P0[b0+1]^T
+      GemmArgs g{};
+      const long r0 = (long)(b0 + 1) * DB;
+      g.A = A + r0 * ld + (long)b0 * DB; g.lda = ld; g.strideA = strideA;
+      g.B = A + r0 * ld + (long)b0 * DB; g.ldb = ld; g.strideB = strideA;
+      g.C = A + r0 * ld + r0; g.ldc = ld; g.strideC = strideA;
+      g.M = n - (int)r0; g.N = DB; g.K = DB; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kmode = K_FULL;
+      if ((rc = launch_gemm<false, false>(g, batch, st))) return rc;
+      if ((rc = launch_diag(A, ld, strideA, dinv, strideD, b0 + 1, logdet_parts, nblk, info, batch, st))) return rc;
+      if ((rc = trsm_panel(b0 + 1))) return rc;
+    }
+    const long r0 = (long)(b0 + w) * DB;
+    if (r0 < n) {   // trailing update, lower tiles only, rank 128*w
+      GemmArgs g{};
+      g.A = A + r0 * ld + (long)b0 * DB; g.lda = ld; g.strideA = strideA;
+      g.B = g.A; g.ldb = ld; g.strideB = strideA;
+      g.C = A + r0 * ld + r0; g.ldc = ld; g.strideC = strideA;
+      g.M = g.N = n - (int)r0; g.K = w * DB; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1; g.kmode = K_FULL;
+      if ((rc = launch_gemm<false, false>(g, batch, st))) return rc;
+    }
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Vector triangular solves (one right-hand side per matrix), one launch per block step, no atomics.
+// ----------------------------------------------------------------------------------------------------------------
+// forward:  x = L^-1 y.   Step k: x_k = Dinv_k * w_k ;  w_i -= L[i,k] x_k  for block rows i > k.   (w is a scratch copy of y)
+__global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __restrict__ A, long ld, long strideA, const double* __restrict__ dinv,
+                                                            long strideD, double* __restrict__ w, double* __restrict__ x, long strideV, int k) {
+  __shared__ double wk[DB], xk[DB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, z = blockIdx.y;
+  const double* Az = A + (long)z * strideA;
+  const double* Dk = dinv + (long)z * strideD + (long)k * DB * DB;
+  double* wz = w + (long)z * strideV;
+  if (tid < DB) wk[tid] = wz[(long)k * DB + tid];
+  __syncthreads();
+  for (int r = warp; r < DB; r += 8) {     // x_k[r] = sum_c Dinv[r][c] w_k[c]
+    double s = 0.0;
+    for (int c = lane; c <= (r | 31); c += 32) s = fma(Dk[r * DB + c], wk[c], s);
+    s = warp_sum(s);
+    if (lane == 0) xk[r] = s;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (tid < DB) x[(long)z * strideV + (long)k * DB + tid] = xk[tid];
+    return;
+  }
+  const long i0 = (long)(k + blockIdx.x) * DB;
+  const double* Lik = Az + i0 * ld + (long)k * DB;
+  for (int r = warp; r < DB; r += 8) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = lane; c < DB; c += 32) s = fma(Lik[(long)r * ld + c], xk[c], s);
+    s = warp_sum(s);
+    if (lane == 0) wz[i0 + r] -= s;
+  }
+}
+
+// backward:  x = L^-T y.  Step k (descending): x_k = Dinv_k^T w_k ;  w_j -= L[k,j]^T x_k  for block columns j < k.
+__global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __restrict__ A, long ld, long strideA, const double* __restrict__ dinv,
+                                                            long strideD, double* __restrict__ w, double* __restrict__ x, long strideV, int k) {
+  __shared__ double wk[DB], xk[DB], part[2 * DB];
+  const int tid = threadIdx.x, z = blockIdx.y;
+  const int c = tid & (DB - 1), half = tid >> 7;
+  const double* Az = A + (long)z * strideA;
+  const double* Dk = dinv + (long)z * strideD + (long)k * DB * DB;
+  double* wz = w + (long)z * strideV;
+  if (tid < DB) wk[tid] = wz[(long)k * DB + tid];
+  __syncthreads();
+  {
+    double s = 0.0;
+    for (int r = half * 64; r < half * 64 + 64; ++r) s = fma(Dk[r * DB + c], wk[r], s);   // Dinv upper part is zero
+    part[half * DB + c] = s;
+  }
+  __syncthreads();
+  if (tid < DB) xk[tid] = part[tid] + part[DB + tid];
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (tid < DB) x[(long)z * strideV + (long)k * DB + tid] = xk[tid];
+    return;
+  }
+  const long j0 = (long)(blockIdx.x - 1) * DB;
+  const double* Lkj = Az + (long)k * DB * ld + j0;
+  double s = 0.0;
+  for (int r = half * 64; r < half * 64 + 64; ++r) s = fma(Lkj[(long)r * ld + c], xk[r], s);
+  part[half * DB + c] = s;
+  __syncthreads();
+  if (tid < DB) wz[j0 + tid] -= part[tid] + part[DB + tid];
+}
+
+int trsv_lower(const double* A, int n, long ld, long strideA, int batch, const double* dinv, double* w, double* x, long strideV, int transpose,
+               cudaStream_t st) {
+  RC_REQUIRE(n > 0 && n % DB == 0, -2, "trsv_lower: n=%d must be a positive multiple of 128", n);
+  const int nblk = n / DB;
+  const long strideD = (long)nblk * DB * DB;
+  if (!transpose) {
+    for (int k = 0; k < nblk; ++k) {
+      dim3 grid(nblk - k, batch);
+      trsv_fwd_step_kernel<<<grid, 256, 0, st>>>(A, ld, strideA, dinv, strideD, w, x, strideV, k);
+    }
+  } else {
+    for (int k = nblk - 1; k >= 0; --k) {
+      dim3 grid(k + 1, batch);
+      trsv_bwd_step_kernel<<<grid, 256, 0, st>>>(A, ld, strideA, dinv, strideD, w, x, strideV, k);
+    }
+  }
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Multi right-hand-side forward solve  B <- L^-1 B  (B is n x nrhs row-major, nrhs a multiple of 128), GEMM based.
+// ----------------------------------------------------------------------------------------------------------------
+int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, const double* dinv, double* B, int nrhs, long ldb, long strideB,
+                   cudaStream_t st) {
+  RC_REQUIRE(n % DB == 0 && nrhs % DB == 0, -2, "trsm_lower_fwd: n=%d and nrhs=%d must be multiples of 128", n, nrhs);
+  const int nblk = n / DB;
+  const long strideD = (long)nblk * DB * DB;
+  int rc;
+  for (int k = 0; k < nblk; ++k) {
+    GemmArgs g{};   // B_k <- Dinv_k * B_k   (tile-exclusive in place: a CTA owns its 128 columns over all 128 k-rows)
+    g.A = dinv + (long)k * DB * DB; g.lda = DB; g.strideA = strideD;
+    g.B = B + (long)k * DB * ldb; g.ldb = ldb; g.strideB = strideB;
+    g.C = B + (long)k * DB * ldb; g.ldc = ldb; g.strideC = strideB;
+    g.M = DB; g.N = nrhs; g.K = DB; g.alpha = 1.0; g.beta = 0.0; g.kmode = K_FULL;
+    if ((rc = launch_gemm<false, true>(g, batch, st))) return rc;
+    const int r0 = (k + 1) * DB;
+    if (r0 < n) {   // B[i>k] -= L[i,k] * B_k
+      GemmArgs u{};
+      u.A = A + (long)r0 * ld + (long)k * DB; u.lda = ld; u.strideA = strideA;
+      u.B = B + (long)k * DB * ldb; u.ldb = ldb; u.strideB = strideB;
+      u.C = B + (long)r0 * ldb; u.ldc = ldb; u.strideC = strideB;
+      u.M = n - r0; u.N = nrhs; u.K = DB; u.alpha = -1.0; u.beta = 1.0; u.kmode = K_FULL;
+      if ((rc = launch_gemm<false, true>(u, batch, st))) return rc;
+    }
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Triangular inverse (in place) and K^-1 = L^-T L^-1 (out of place, lower triangle).
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void copy_dinv_to_diag_kernel(double* __restrict__ A, long ld, long strideA, const double* __restrict__ dinv, long strideD) {
+  const int blk = blockIdx.x, z = blockIdx.y;
+  double* Ab = A + (long)z * strideA + (long)blk * DB * (ld + 1);
+  const double* Db = dinv + (long)z * strideD + (long)blk * DB * DB;
+  for (int idx = threadIdx.x; idx < DB * DB; idx += blockDim.x) Ab[(long)(idx >> 7) * ld + (idx & 127)] = Db[idx];
+}
+
+// Bottom-up recursive doubling: with Z11, Z22 the inverses of two adjacent diagonal blocks of size h,
+//   Z21 = -Z22 * (L21 * Z11),  all pairs of a level batched into two launches.  `tmp` needs >= n*n/4 doubles per matrix.
+int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double* dinv, double* tmp, long strideT, cudaStream_t st) {
+  RC_REQUIRE(n > 0 && n % DB == 0, -2, "trtri_lower: n=%d must be a positive multiple of 128", n);
+  const int nblk = n / DB;
+  const long strideD = (long)nblk * DB * DB;
+  copy_dinv_to_diag_kernel<<<dim3(nblk, batch), 256, 0, st>>>(A, ld, strideA, dinv, strideD);
+  RC_LAUNCH_OK();
+  int rc;
+  for (long h = DB; h < n; h *= 2) {
+    const int np = (int)(n / (2 * h));
+    const long rem = n - (long)np * 2 * h;
+    // (count, h2): full problems then the ragged one (second block shorter)
+    for (int pass = 0; pass < 2; ++pass) {
+      const int count = pass == 0 ? np : ((rem > h) ? 1 : 0);
+      if (count == 0) continue;
+      const long h2 = pass == 0 ? h : rem - h;
+      const long base = pass == 0 ? 0 : (long)np * 2 * h;
+      for (int z = 0; z < batch; ++z) {   // batch of matrices x batch of pairs: pairs go to gridDim.z, matrices are looped
+        double* Az = A + (long)z * strideA + base * (ld + 1);
+        double* Tz = tmp + (long)z * strideT;
+        GemmArgs g{};   // T = L21 * Z11     (Z11 lower, stored [k][n]  ->  k >= n0)
+        g.A = Az + h * ld; g.lda = ld; g.strideA = 2 * h * (ld + 1);
+        g.B = Az; g.ldb = ld; g.strideB = 2 * h * (ld + 1);
+        g.C = Tz; g.ldc = h; g.strideC = h * h;
+        g.M = (int)h2; g.N = (int)h; g.K = (int)h; g.alpha = 1.0; g.beta = 0.0; g.kmode = K_GE_N0;
+        if ((rc = launch_gemm<false, true>(g, count, st))) return rc;
+        GemmArgs u{};   // Z21 = -Z22 * T    (Z22 lower, stored [m][k]  ->  k < m0 + 128)
+        u.A = Az + h * ld + h; u.lda = ld; u.strideA = 2 * h * (ld + 1);
+        u.B = Tz; u.ldb = h; u.strideB = h * h;
+        u.C = Az + h * ld; u.ldc = ld; u.strideC = 2 * h * (ld + 1);
+        u.M = (int)h2; u.N = (int)h; u.K = (int)h2; u.alpha = -1.0; u.beta = 0.0; u.kmode = K_LT_M1;
+        if ((rc = launch_gemm<false, true>(u, count, st))) return rc;
+      }
+    }
+  }
+  return 0;
+}
+
+// Kinv (lower tiles) = Z^T Z with Z = L^-1 lower (diagonal 128-blocks carry explicit zeros above the diagonal).
+int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double* Kinv, long ldk, long strideK, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = Z; g.lda = ld; g.strideA = strideZ;
+  g.B = Z; g.ldb = ld; g.strideB = strideZ;
+  g.C = Kinv; g.ldc = ldk; g.strideC = strideK;
+  g.M = g.N = g.K = n; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 1; g.kmode = K_GE_M0;
+  return launch_gemm<true, true>(g, batch, st);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// small utilities
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void sum_parts_kernel(const double* __restrict__ parts, int count, double* __restrict__ out, double scale) {
+  __shared__ double red[32];
+  const int z = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) s += parts[(long)z * count + i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[z] = s * scale;
+}
+
+int sum_parts(const double* parts, int count, int batch, double* out, double scale, cudaStream_t st) {
+  sum_parts_kernel<<<batch, 256, 0, st>>>(parts, count, out, scale);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void dot_kernel(const double* __restrict__ a, const double* __restrict__ b, long n, long stride, double* __restrict__ out) {
+  __shared__ double red[32];
+  const int z = blockIdx.x;
+  double s = 0.0;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) s = fma(a[z * stride + i], b[z * stride + i], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[z] = s;
+}
+
+int dot_batched(const double* a, const double* b, long n, long stride, int batch, double* out, cudaStream_t st) {
+  dot_kernel<<<batch, 1024, 0, st>>>(a, b, n, stride, out);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// dst (n x n, ld=n, zero upper) <- lower triangle of src (n_pad storage)
+__global__ void extract_lower_kernel(const double* __restrict__ src, long lds, long strideS, double* __restrict__ dst, int n, long strideDst,
+                                     int symmetrize) {
+  const int z = blockIdx.z;
+  const long i = blockIdx.y;
+  const double* s = src + z * strideS;
+  double* d = dst + z * strideDst;
+  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long)gridDim.x * blockDim.x) {
+    double v;
+    if (j <= i) v = s[i * lds + j];
+    else v = symmetrize ? s[j * lds + i] : 0.0;
+    d[i * n + j] = v;
+  }
+}
+
+int extract_lower(const double* src, long lds, long strideS, double* dst, int n, long strideDst, int batch, int symmetrize, cudaStream_t st) {
+  dim3 grid((n + 1023) / 1024 > 0 ? (n + 1023) / 1024 : 1, n, batch);
+  extract_lower_kernel<<<grid, 256, 0, st>>>(src, lds, strideS, dst, n, strideDst, symmetrize);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// dst (n_pad storage) <- src (n x n dense) with identity padding
+__global__ void pad_identity_kernel(const double* __restrict__ src, int n, long strideS, double* __restrict__ dst, int n_pad, long ldd, long strideD) {
+  const int z = blockIdx.z;
+  const long i = blockIdx.y;
+  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n_pad; j += (long)gridDim.x * blockDim.x) {
+    double v = (i < n && j < n) ? src[z * strideS + i * n + j] : (i == j ? 1.0 : 0.0);
+    dst[z * strideD + i * ldd + j] = v;
+  }
+}
+
+int pad_identity(const double* src, int n, long strideS, double* dst, int n_pad, long ldd, long strideD, int batch, cudaStream_t st) {
+  dim3 grid((n_pad + 1023) / 1024, n_pad, batch);
+  pad_identity_kernel<<<grid, 256, 0, st>>>(src, n, strideS, dst, n_pad, ldd, strideD);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace rc

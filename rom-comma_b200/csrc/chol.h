@@ -1,0 +1,34 @@
+// Internal (C++) interface of the dense FP64 factorisation layer; the C ABI in capi.cu is built on these.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace rc {
+
+size_t potrf_workspace_bytes(int n, int batch);
+
+// In-place lower Cholesky of `batch` n x n matrices (only the lower triangle is read; the strict upper triangle of
+// diagonal 128-tiles is clobbered). dinv: batch*(n/128) inverse diagonal blocks; logdet_parts: batch*(n/128) partial
+// sums of log L_ii; info[z] = 0 or the 1-based index of the first non-positive pivot.
+int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st);
+
+// x = L^-1 w (transpose=0) or L^-T w (transpose=1); w is destroyed. Vectors of batch z start at z*strideV.
+int trsv_lower(const double* A, int n, long ld, long strideA, int batch, const double* dinv, double* w, double* x, long strideV, int transpose,
+               cudaStream_t st);
+
+// B <- L^-1 B for an n x nrhs block of right-hand sides (nrhs multiple of 128).
+int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, const double* dinv, double* B, int nrhs, long ldb, long strideB,
+                   cudaStream_t st);
+
+// A (holding L) <- L^-1 in place; tmp needs n*n/4 doubles per matrix.
+int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double* dinv, double* tmp, long strideT, cudaStream_t st);
+
+// Kinv(lower 128-tiles) = Z^T Z.
+int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double* Kinv, long ldk, long strideK, cudaStream_t st);
+
+int sum_parts(const double* parts, int count, int batch, double* out, double scale, cudaStream_t st);
+int dot_batched(const double* a, const double* b, long n, long stride, int batch, double* out, cudaStream_t st);
+int extract_lower(const double* src, long lds, long strideS, double* dst, int n, long strideDst, int batch, int symmetrize, cudaStream_t st);
+int pad_identity(const double* src, int n, long strideS, double* dst, int n_pad, long ldd, long strideD, int batch, cudaStream_t st);
+
+}  // namespace rc

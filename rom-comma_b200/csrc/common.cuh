@@ -1,0 +1,74 @@
+// Shared device/host helpers for the rom-comma B200 (sm_100a) FP64 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace rc {
+
+constexpr int TILE = 128;   // every factorisation matrix is padded to a multiple of this (identity padding)
+
+// Thread-local last error text for the C ABI (rc_last_error).
+void set_error(const char* fmt, ...);
+
+#define RC_CUDA_OK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      rc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -1000 - (int)_e;                                                                     \
+    }                                                                                             \
+  } while (0)
+
+#define RC_LAUNCH_OK() RC_CUDA_OK(cudaGetLastError())
+
+#define RC_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) {                  \
+      rc::set_error(__VA_ARGS__);   \
+      return (code);                \
+    }                               \
+  } while (0)
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// One native FP64 tensor-core op (SASS: DMMA.8x8x4): D(8x8) += A(8x4, row) * B(4x8, col).
+// Lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block reduction (fixed tree order); result valid in thread 0. `red` needs >= 32 doubles of smem.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < nw ? red[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace rc

@@ -1,0 +1,399 @@
+// Gram construction, LML-gradient contractions and predictive reductions (FP64, sm_100a).
+//
+// gram_kernel replaces romcomma/gpf/kernels.py:74-116,153-154 (+ gpflow scaled_difference_matrix), the variance
+// broadcast of gpf/base.py:57-60 and the noise term of gpf/likelihoods.py:64-67 / gpf/base.py:62-69 in ONE pass: the
+// (L,N,L,N,M) difference tensor and the dense eye(N) noise tensor of the reference are never formed.
+// grad_reduce_kernel contracts W = a a^T - K^-1 with dK/dtheta, recomputing K_unit on the fly.
+#include "gp_ops.h"
+#include "common.cuh"
+
+namespace rc {
+
+constexpr int GT = 64;          // gram / reduction tile edge
+constexpr int GTHREADS = 256;   // 16 x 16 threads, 4 x 4 outputs each
+
+// Stage the scaled coordinates s[m][r] = X[n_r][m] / ls[l_r][m] of 64 consecutive global indices into shared memory
+// (transposed so that the inner loop reads consecutive doubles). Indices >= L*Npts are padding (coordinate 0, l = -1).
+__device__ __forceinline__ void stage_scaled(double* __restrict__ s, int* __restrict__ lidx, int* __restrict__ nidx, const double* __restrict__ X,
+                                             int Npts, int M, const double* __restrict__ ls, int L, long g0) {
+  for (int e = threadIdx.x; e < GT * M; e += GTHREADS) {
+    const int r = e / M, m = e - r * M;
+    const long gi = g0 + r;
+    double v = 0.0;
+    if (gi < (long)L * Npts) {
+      const int l = (int)(gi / Npts), n = (int)(gi - (long)l * Npts);
+      v = X[(long)n * M + m] / ls[l * M + m];
+    }
+    s[m * GT + r] = v;
+  }
+  for (int r = threadIdx.x; r < GT; r += GTHREADS) {
+    const long gi = g0 + r;
+    if (gi < (long)L * Npts) {
+      lidx[r] = (int)(gi / Npts);
+      nidx[r] = (int)(gi % Npts);
+    } else {
+      lidx[r] = -1;
+      nidx[r] = -1;
+    }
+  }
+}
+
+// out[i][j] = F[l_i,l_j] * exp(-1/2 |s_i - s_j|^2) + E[l_i,l_j] * [n_i == n_j];  identity in the padding (square case).
+__global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  double* sr = sm;
+  double* sc = sm + GT * p.M;
+  int* li = reinterpret_cast<int*>(sm + 2 * GT * p.M);
+  int* ni = li + GT;
+  int* lj = ni + GT;
+  int* nj = lj + GT;
+
+  int ti, tj;
+  if (p.lower_only) {
+    const int idx = blockIdx.x;
+    ti = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while ((long)(ti + 1) * (ti + 2) / 2 <= idx) ++ti;
+    while ((long)ti * (ti + 1) / 2 > idx) --ti;
+    tj = idx - ti * (ti + 1) / 2;
+  } else {
+    const int tcols = p.cols_pad / GT;
+    ti = blockIdx.x / tcols;
+    tj = blockIdx.x - ti * tcols;
+  }
+  const int z = blockIdx.z;
+  const double* ls = p.ls + (long)z * p.stride_ls;
+  const double* F = p.F ? p.F + (long)z * p.stride_FE : nullptr;
+  const double* E = p.E ? p.E + (long)z * p.stride_FE : nullptr;
+  double* out = p.out + (long)z * p.stride_out;
+
+  stage_scaled(sr, li, ni, p.X, p.N, p.M, ls, p.L, (long)ti * GT);
+  stage_scaled(sc, lj, nj, p.X2, p.N2, p.M, ls, p.L, (long)tj * GT);
+  __syncthreads();
+
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+  for (int m = 0; m < p.M; ++m) {
+    double a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = sr[m * GT + ty * 4 + u];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) b[v] = sc[m * GT + tx * 4 + v];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const double d = a[u] - b[v];
+        acc[u][v] = fma(d, d, acc[u][v]);
+      }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = ty * 4 + u;
+    const long gi = (long)ti * GT + r;
+    const int l_i = li[r], n_i = ni[r];
+    double o[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int c = tx * 4 + v;
+      const long gj = (long)tj * GT + c;
+      const int l_j = lj[c], n_j = nj[c];
+      double val;
+      if (l_i >= 0 && l_j >= 0) {
+        val = exp(-0.5 * acc[u][v]);
+        if (F) val *= F[l_i * p.L + l_j];
+        if (E && n_i == n_j) val += E[l_i * p.L + l_j];
+      } else {
+        val = (p.pad_identity && gi == gj) ? 1.0 : 0.0;
+      }
+      o[v] = val;
+    }
+    double2* dst = reinterpret_cast<double2*>(out + gi * p.ld_out + (long)tj * GT + tx * 4);
+    dst[0] = make_double2(o[0], o[1]);
+    dst[1] = make_double2(o[2], o[3]);
+  }
+}
+
+int gram(const GramArgs& a, int batch, cudaStream_t st) {
+  RC_REQUIRE(a.M >= 1 && a.M <= 256, -2, "gram: M=%d out of range [1,256]", a.M);
+  RC_REQUIRE(a.rows_pad % GT == 0 && a.cols_pad % GT == 0 && a.ld_out % 2 == 0, -2, "gram: padded sizes must be multiples of 64");
+  RC_REQUIRE(!a.lower_only || a.rows_pad == a.cols_pad, -2, "gram: lower_only needs a square output");
+  const long tr = a.rows_pad / GT, tc = a.cols_pad / GT;
+  const long tiles = a.lower_only ? tr * (tr + 1) / 2 : tr * tc;
+  const size_t smem = (size_t)2 * GT * a.M * sizeof(double) + 4 * GT * sizeof(int);
+  gram_kernel<<<dim3((unsigned)tiles, 1, batch), GTHREADS, smem, st>>>(a);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// K = F (x) Kunit + E (x) I  from a cached unit-variance gram (gpf/models.py:66-68 cached branch + likelihoods.add_to).
+__global__ void apply_variance_noise_kernel(const double* __restrict__ Ku, long ldu, const double* __restrict__ F, const double* __restrict__ E, int L,
+                                            int N, int n_pad, double* __restrict__ out, long ldo, int lower_only) {
+  const long i = blockIdx.y;
+  const int l_i = i < (long)L * N ? (int)(i / N) : -1;
+  const int n_i = l_i >= 0 ? (int)(i - (long)l_i * N) : -1;
+  const long jend = lower_only ? ((i / TILE + 1) * TILE) : n_pad;
+  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < jend; j += (long)gridDim.x * blockDim.x) {
+    double v;
+    if (l_i >= 0 && j < (long)L * N) {
+      const int l_j = (int)(j / N), n_j = (int)(j - (long)l_j * N);
+      v = F[l_i * L + l_j] * Ku[i * ldu + j];
+      if (E && n_i == n_j) v += E[l_i * L + l_j];
+    } else {
+      v = (i == j) ? 1.0 : 0.0;
+    }
+    out[i * ldo + j] = v;
+  }
+}
+
+int apply_variance_noise(const double* Ku, long ldu, const double* F, const double* E, int L, int N, int n_pad, double* out, long ldo,
+                         int lower_only, cudaStream_t st) {
+  dim3 grid((n_pad + 1023) / 1024, n_pad);
+  apply_variance_noise_kernel<<<grid, 256, 0, st>>>(Ku, ldu, F, E, L, N, n_pad, out, ldo, lower_only);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Gradient contractions over the lower triangle of K^-1.
+// For every stored element (i >= j), W = a_i a_j - Kinv_ij, U = exp(-1/2 |s_i - s_j|^2), weight 2 for the strictly lower
+// elements of the (symmetric) diagonal blocks l_i == l_j so that SF, SE hold full block sums for l_i >= l_j:
+//   SF[l_i,l_j] += wgt * W * U      (-> dLML/dF = 1/2 SF, mirrored)        SE[l_i,l_j] += wgt * W  if n_i == n_j
+//   dls[l_i,m]  += W F U d_m s_i[m] / ls[l_i,m]  ;  dls[l_j,m] -= W F U d_m s_j[m] / ls[l_j,m]   (i > j)
+// Per-CTA partial sums are written out and reduced in a fixed order by grad_finish_kernel: no atomics, bitwise reproducible.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GTHREADS) grad_reduce_kernel(GradArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  double* sr = sm;
+  double* sc = sm + GT * p.M;
+  double* ar = sm + 2 * GT * p.M;   // alpha rows
+  double* ac = ar + GT;             // alpha cols
+  double* red = ac + GT;            // 32
+  double* wpart = red + 32;         // [8 warps][2 (row/col)][slots][M]
+  int* li = reinterpret_cast<int*>(wpart + 8 * 2 * p.slots * p.M);
+  int* ni = li + GT;
+  int* lj = ni + GT;
+  int* nj = lj + GT;
+
+  const int idx = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+  while ((long)(ti + 1) * (ti + 2) / 2 <= idx) ++ti;
+  while ((long)ti * (ti + 1) / 2 > idx) --ti;
+  const int tj = idx - ti * (ti + 1) / 2;
+  const int z = blockIdx.z;
+  const double* ls = p.ls + (long)z * p.stride_ls;
+  const double* F = p.F + (long)z * p.stride_FE;
+  const double* Kinv = p.Kinv + (long)z * p.stride_K;
+  const double* alpha = p.alpha + (long)z * p.stride_alpha;
+  double* parts = p.parts + ((long)z * gridDim.x + idx) * p.nvals;
+  const int L = p.L, M = p.M;
+
+  stage_scaled(sr, li, ni, p.X, p.N, M, ls, L, (long)ti * GT);
+  stage_scaled(sc, lj, nj, p.X, p.N, M, ls, L, (long)tj * GT);
+  for (int r = threadIdx.x; r < GT; r += GTHREADS) {
+    ar[r] = alpha[(long)ti * GT + r];
+    ac[r] = alpha[(long)tj * GT + r];
+  }
+  for (int e = threadIdx.x; e < p.nvals; e += GTHREADS) parts[e] = 0.0;
+  __syncthreads();
+
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double d2[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) d2[u][v] = 0.0;
+  for (int m = 0; m < M; ++m) {
+    double a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = sr[m * GT + ty * 4 + u];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) b[v] = sc[m * GT + tx * 4 + v];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const double d = a[u] - b[v];
+        d2[u][v] = fma(d, d, d2[u][v]);
+      }
+  }
+  // per-element W*U (weighted), W (noise part) and W*F*U
+  double wu[4][4], wn[4][4], wfu[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = ty * 4 + u;
+    const long gi = (long)ti * GT + r;
+    const double2* krow = reinterpret_cast<const double2*>(Kinv + gi * p.ldk + (long)tj * GT + tx * 4);
+    const double2 k01 = krow[0], k23 = krow[1];
+    const double kv[4] = {k01.x, k01.y, k23.x, k23.y};
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int c = tx * 4 + v;
+      const long gj = (long)tj * GT + c;
+      const bool valid = li[r] >= 0 && lj[c] >= 0 && gj <= gi;
+      const double wgt = (gj < gi && li[r] == lj[c]) ? 2.0 : 1.0;   // diagonal (l,l) blocks are symmetric: count the mirror
+      const double W = valid ? (ar[r] * ac[c] - kv[v]) : 0.0;
+      const double U = exp(-0.5 * d2[u][v]);
+      wu[u][v] = wgt * W * U;
+      wn[u][v] = (valid && ni[r] == nj[c]) ? wgt * W : 0.0;
+      wfu[u][v] = (valid && gj < gi) ? W * U * F[li[r] * L + lj[c]] : 0.0;
+    }
+  }
+  // (l_i, l_j) pairs present in this tile
+  const int la0 = max(li[0], 0), lb0 = max(lj[0], 0);
+  int la1 = la0, lb1 = lb0;
+  for (int r = GT - 1; r >= 0; --r) if (li[r] >= 0) { la1 = li[r]; break; }
+  for (int r = GT - 1; r >= 0; --r) if (lj[r] >= 0) { lb1 = lj[r]; break; }
+  for (int la = la0; la <= la1; ++la)
+    for (int lb = lb0; lb <= lb1; ++lb) {
+      double sF = 0.0, sE = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (li[ty * 4 + u] == la && lj[tx * 4 + v] == lb) {
+            sF += wu[u][v];
+            sE += wn[u][v];
+          }
+      sF = block_sum(sF, red);
+      sE = block_sum(sE, red);
+      if (threadIdx.x == 0) {
+        parts[la * L + lb] = sF;
+        parts[L * L + la * L + lb] = sE;
+      }
+    }
+  if (!p.with_ls) return;
+  // lengthscale terms: warp partials -> fixed-order sum over the 8 warps
+  for (int m = 0; m < M; ++m) {
+    double a[4], b[4], rsum[4] = {0, 0, 0, 0}, csum[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = sr[m * GT + ty * 4 + u];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) b[v] = sc[m * GT + tx * 4 + v];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const double t = wfu[u][v] * (a[u] - b[v]);
+        rsum[u] += t;
+        csum[v] += t;
+      }
+    for (int s = 0; s < p.slots; ++s) {
+      const int la = la0 + s, lb = lb0 + s;
+      double vr = 0.0, vc = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (li[ty * 4 + u] == la) vr += rsum[u] * a[u];
+        if (lj[tx * 4 + u] == lb) vc += csum[u] * b[u];
+      }
+      vr = warp_sum(vr);
+      vc = warp_sum(vc);
+      if (lane == 0) {
+        wpart[((warp * 2 + 0) * p.slots + s) * M + m] = vr;
+        wpart[((warp * 2 + 1) * p.slots + s) * M + m] = vc;
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < p.slots * M; e += GTHREADS) {
+    const int s = e / M, m = e - s * M;
+    const int la = la0 + s, lb = lb0 + s;
+    double vr = 0.0, vc = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      vr += wpart[((w * 2 + 0) * p.slots + s) * M + m];
+      vc += wpart[((w * 2 + 1) * p.slots + s) * M + m];
+    }
+    // rows of this tile with output la add +vr/ls[la,m]; columns with output lb add -vc/ls[lb,m].
+    // A tile may have la == lb' for different slots, so row and column parts are kept in separate partial arrays.
+    if (la <= la1) parts[2 * L * L + la * M + m] = vr / ls[la * M + m];
+    if (lb <= lb1) parts[2 * L * L + L * M + lb * M + m] = -vc / ls[lb * M + m];
+  }
+}
+
+// out[z][v] = sum over tiles (fixed order) of parts[z][tile][v]
+__global__ void grad_finish_kernel(const double* __restrict__ parts, long ntiles, int nvals, double* __restrict__ out) {
+  __shared__ double red[32];
+  const int v = blockIdx.x, z = blockIdx.y;
+  double s = 0.0;
+  for (long t = threadIdx.x; t < ntiles; t += blockDim.x) s += parts[((long)z * ntiles + t) * nvals + v];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[(long)z * nvals + v] = s;
+}
+
+int grad_nvals(int L, int M) { return 2 * L * L + 2 * L * M; }
+
+static int grad_slots(int L, int N) { return min(L, GT / (N > 0 ? N : 1) + 2); }
+
+size_t grad_workspace_bytes(int n_pad, int L, int M, int batch) {
+  const long t = n_pad / GT;
+  return (size_t)batch * (size_t)(t * (t + 1) / 2) * grad_nvals(L, M) * sizeof(double);
+}
+
+int grad_reduce(GradArgs a, int n_pad, int batch, double* out, cudaStream_t st) {
+  RC_REQUIRE(n_pad % GT == 0, -2, "grad_reduce: n_pad must be a multiple of 64");
+  a.nvals = grad_nvals(a.L, a.M);
+  a.slots = grad_slots(a.L, a.N);
+  const long t = n_pad / GT, tiles = t * (t + 1) / 2;
+  const size_t smem = (size_t)(2 * GT * a.M + 2 * GT + 32 + 16 * a.slots * a.M) * sizeof(double) + 4 * GT * sizeof(int);
+  RC_REQUIRE(smem <= 48 * 1024, -2, "grad_reduce: M=%d / slots=%d need %zu bytes of shared memory (>48 KB)", a.M, a.slots, smem);
+  grad_reduce_kernel<<<dim3((unsigned)tiles, 1, batch), GTHREADS, smem, st>>>(a);
+  RC_LAUNCH_OK();
+  grad_finish_kernel<<<dim3(a.nvals, batch), 256, 0, st>>>(a.parts, tiles, a.nvals, out);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Predictive reductions: for A = L^-1 Kmn (n x c) and a = L^-1 y:  mean_c = sum_k A[k][c] a[k],  ss_c = sum_k A[k][c]^2.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int PR_SPLIT = 32;
+
+__global__ void predict_partial_kernel(const double* __restrict__ A, long lda, long strideA, const double* __restrict__ a, long stride_a, int n,
+                                       int c_pad, double* __restrict__ parts) {
+  const int z = blockIdx.z, split = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c_pad) return;
+  const int rows = (n + PR_SPLIT - 1) / PR_SPLIT;
+  const int k0 = split * rows, k1 = min(n, k0 + rows);
+  const double* Az = A + (long)z * strideA;
+  const double* az = a + (long)z * stride_a;
+  double m = 0.0, ss = 0.0;
+  for (int k = k0; k < k1; ++k) {
+    const double v = Az[(long)k * lda + c];
+    m = fma(v, az[k], m);
+    ss = fma(v, v, ss);
+  }
+  double* pz = parts + ((long)z * PR_SPLIT + split) * 2 * c_pad;
+  pz[c] = m;
+  pz[c_pad + c] = ss;
+}
+
+__global__ void predict_finish_kernel(const double* __restrict__ parts, int c_pad, double* __restrict__ mean, double* __restrict__ ss) {
+  const int z = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c_pad) return;
+  double m = 0.0, s = 0.0;
+  for (int sp = 0; sp < PR_SPLIT; ++sp) {
+    const double* pz = parts + ((long)z * PR_SPLIT + sp) * 2 * c_pad;
+    m += pz[c];
+    s += pz[c_pad + c];
+  }
+  mean[(long)z * c_pad + c] = m;
+  ss[(long)z * c_pad + c] = s;
+}
+
+size_t predict_workspace_bytes(int c_pad, int batch) { return (size_t)batch * PR_SPLIT * 2 * c_pad * sizeof(double); }
+
+int predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n, int c_pad, int batch, double* parts, double* mean,
+                   double* ss, cudaStream_t st) {
+  predict_partial_kernel<<<dim3((c_pad + 127) / 128, PR_SPLIT, batch), 128, 0, st>>>(A, lda, strideA, a, stride_a, n, c_pad, parts);
+  RC_LAUNCH_OK();
+  predict_finish_kernel<<<dim3((c_pad + 127) / 128, batch), 128, 0, st>>>(parts, c_pad, mean, ss);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace rc

@@ -1,0 +1,43 @@
+// Internal (C++) interface of the gram / gradient / prediction kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace rc {
+
+struct GramArgs {
+  const double* X;  int N;      // (N, M) row-major inputs of the rows
+  const double* X2; int N2;     // (N2, M) inputs of the columns (== X for the training gram)
+  int M, L;
+  const double* ls; long stride_ls;    // (L, M) lengthscales, batch stride
+  const double* F;  const double* E;   // (L, L) each or nullptr (F: unit variance, E: no noise); batch stride stride_FE
+  long stride_FE;
+  double* out; long ld_out; long stride_out;
+  int rows_pad, cols_pad;              // multiples of 64; indices >= L*N (L*N2) are padding
+  int lower_only;                      // only 64-tiles on or below the diagonal
+  int pad_identity;                    // padding gets the identity (square factorisation input) instead of zeros
+};
+int gram(const GramArgs& a, int batch, cudaStream_t st);
+
+int apply_variance_noise(const double* Ku, long ldu, const double* F, const double* E, int L, int N, int n_pad, double* out, long ldo,
+                         int lower_only, cudaStream_t st);
+
+struct GradArgs {
+  const double* X; int N, M, L;
+  const double* ls; long stride_ls;
+  const double* F;  long stride_FE;
+  const double* Kinv; long ldk; long stride_K;   // lower triangle of K^-1, padded storage
+  const double* alpha; long stride_alpha;        // K^-1 y, padded with zeros
+  double* parts;                                 // grad_workspace_bytes
+  int with_ls;
+  int nvals, slots;                              // filled in by grad_reduce
+};
+int grad_nvals(int L, int M);   // layout: SF (L*L), SE (L*L), dls row part (L*M), dls column part (L*M)
+size_t grad_workspace_bytes(int n_pad, int L, int M, int batch);
+int grad_reduce(GradArgs a, int n_pad, int batch, double* out, cudaStream_t st);
+
+size_t predict_workspace_bytes(int c_pad, int batch);
+int predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n, int c_pad, int batch, double* parts, double* mean,
+                   double* ss, cudaStream_t st);
+
+}  // namespace rc

@@ -1,0 +1,288 @@
+"""ctypes binding of ``librc_b200.so`` (include/romcomma_b200.h) with torch CUDA float64 tensors as the carrier.
+
+There is deliberately NO CPU fallback: if the shared library is missing, or a tensor is not a CUDA float64 tensor, the call
+raises.  Tensors handed back are ordinary ``torch`` CUDA tensors, so ``torch.utils.dlpack.to_dlpack`` gives the DLPack
+capsule a TensorFlow/GPflow caller would consume (``tf.experimental.dlpack.from_dlpack``) without leaving the device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+from typing import Optional, Sequence
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / 'librc_b200.so'
+_lib: Optional[ctypes.CDLL] = None
+
+c_double_p = ctypes.c_void_p
+RC_GRAD_NONE, RC_GRAD_VARIANCE, RC_GRAD_LENGTHSCALES = 0, 1, 2
+
+_SIGNATURES = {
+    'rc_version': (ctypes.c_int, []),
+    'rc_last_error': (ctypes.c_char_p, []),
+    'rc_padded': (ctypes.c_int, [ctypes.c_int]),
+    'rc_gram': (ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p, c_double_p,
+                               c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                               ctypes.c_void_p]),
+    'rc_apply_variance_noise': (ctypes.c_int, [c_double_p, ctypes.c_long, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p]),
+    'rc_potrf_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    'rc_potrf': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                ctypes.c_void_p]),
+    'rc_logdet': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_void_p]),
+    'rc_trsv': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_void_p, c_double_p, c_double_p,
+                               ctypes.c_long, ctypes.c_int, ctypes.c_void_p]),
+    'rc_trsm_fwd': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_void_p, c_double_p, ctypes.c_int,
+                                   ctypes.c_long, ctypes.c_long, ctypes.c_void_p]),
+    'rc_potri': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_void_p, c_double_p, ctypes.c_long,
+                                ctypes.c_long, ctypes.c_void_p]),
+    'rc_pad_identity': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_long, c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int,
+                                       ctypes.c_void_p]),
+    'rc_extract_lower': (ctypes.c_int, [c_double_p, ctypes.c_long, ctypes.c_long, c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_void_p]),
+    'rc_lml_grad_stride': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    'rc_lml_grad_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    'rc_lml_grad': (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
+                                   c_double_p, c_double_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, c_double_p, ctypes.c_void_p,
+                                   ctypes.c_void_p]),
+    'rc_predict_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    'rc_predict_reduce': (ctypes.c_int, [c_double_p, ctypes.c_long, ctypes.c_long, c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_void_p]),
+    'rc_sobol_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    'rc_sobol_prepare': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
+                                        c_double_p, c_double_p, c_double_p, ctypes.c_void_p]),
+    'rc_sobol_contract': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, c_double_p, ctypes.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class RomcommaB200Error(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+
+def library_path() -> Path:
+    return Path(os.environ.get('ROMCOMMA_B200_LIB', _LIB_PATH))
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not path.exists():
+            raise RomcommaB200Error(f'{path} is missing: build it with `make -C {path.parent}` - there is no CPU fallback.')
+        handle = ctypes.CDLL(str(path))
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise RomcommaB200Error(f'{what} failed with status {status}: {lib().rc_last_error().decode()}')
+
+
+def ptr(t: Optional[torch.Tensor]):
+    """Device pointer of a contiguous CUDA float64 tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise RomcommaB200Error(f'expected a contiguous CUDA float64 tensor, got {t.dtype} on {t.device} (contiguous={t.is_contiguous()})')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def raw_ptr(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RomcommaB200Error('expected a CUDA tensor')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def padded(n: int) -> int:
+    return int(lib().rc_padded(int(n)))
+
+
+def dev(a, device=None) -> torch.Tensor:
+    """Host array / tensor -> contiguous CUDA float64 tensor on the current (or given) device."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device or 'cuda', dtype=torch.float64).contiguous()
+    import numpy as np
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device or 'cuda')
+
+
+def workspace(nbytes: int, device=None) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=device or 'cuda')
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# thin, allocation-explicit wrappers (one per C entry point)
+# ------------------------------------------------------------------------------------------------------------------
+def gram(X, X2, ls, F=None, E=None, *, batch=1, lower_only=False, pad_to: Optional[int] = None, pad_identity=False, out=None) -> torch.Tensor:
+    """-> (batch, rows_pad, cols_pad) tensor; ls is (batch*L, M); F, E are (batch, L, L) or None."""
+    N, M = X.shape
+    N2 = N if X2 is None else X2.shape[0]
+    L = ls.shape[0] // batch
+    rows = L * N if pad_to is None else max(pad_to, L * N)
+    cols = L * N2 if pad_to is None else max(pad_to, L * N2)
+    rows_pad, cols_pad = (rows + 63) // 64 * 64, (cols + 63) // 64 * 64
+    if pad_to is not None:
+        rows_pad, cols_pad = padded(rows), padded(cols)
+    if out is None:
+        out = torch.empty((batch, rows_pad, cols_pad), dtype=torch.float64, device=X.device)
+    check(lib().rc_gram(ptr(X), N, ptr(X2), N2, M, ptr(ls), L, ptr(F), ptr(E), ptr(out), cols_pad, rows_pad * cols_pad, rows_pad, cols_pad,
+                        int(lower_only), int(pad_identity), batch, stream_ptr()), 'rc_gram')
+    return out
+
+
+class Factorization:
+    """Lower Cholesky factors of `batch` padded n_pad x n_pad matrices plus the workspace the solves need."""
+
+    def __init__(self, A: torch.Tensor):
+        assert A.dim() == 3 and A.shape[1] == A.shape[2]
+        self.A, self.batch, self.n_pad = A, A.shape[0], A.shape[1]
+        self.work = workspace(lib().rc_potrf_bufsize(self.n_pad, self.batch), A.device)
+        self.info = torch.zeros(self.batch, dtype=torch.int32, device=A.device)
+        check(lib().rc_potrf(ptr(A), self.n_pad, self.n_pad, self.n_pad * self.n_pad, self.batch, raw_ptr(self.work), raw_ptr(self.info),
+                             stream_ptr()), 'rc_potrf')
+
+    def raise_if_failed(self):
+        info = self.info.cpu()
+        if int(info.abs().max()) != 0:
+            raise RomcommaB200Error(f'Cholesky decomposition was not successful: first non-positive pivot at (1-based) {info.tolist()}. '
+                                    'The input might not be valid.')
+
+    def logdet_half(self) -> torch.Tensor:
+        out = torch.empty(self.batch, dtype=torch.float64, device=self.A.device)
+        check(lib().rc_logdet(raw_ptr(self.work), self.n_pad, self.batch, ptr(out), stream_ptr()), 'rc_logdet')
+        return out
+
+    def trsv(self, v: torch.Tensor, transpose=False) -> torch.Tensor:
+        """v: (batch, n_pad). Returns L^-1 v or L^-T v."""
+        w = v.clone().contiguous()
+        x = torch.empty_like(w)
+        check(lib().rc_trsv(ptr(self.A), self.n_pad, self.n_pad, self.n_pad * self.n_pad, self.batch, raw_ptr(self.work), ptr(w), ptr(x),
+                            self.n_pad, int(transpose), stream_ptr()), 'rc_trsv')
+        return x
+
+    def trsm_fwd_(self, B: torch.Tensor) -> torch.Tensor:
+        """B: (batch, n_pad, c_pad) with c_pad a multiple of 128; overwritten by L^-1 B."""
+        check(lib().rc_trsm_fwd(ptr(self.A), self.n_pad, self.n_pad, self.n_pad * self.n_pad, self.batch, raw_ptr(self.work), ptr(B), B.shape[2],
+                                B.shape[2], B.shape[1] * B.shape[2], stream_ptr()), 'rc_trsm_fwd')
+        return B
+
+    def inverse_(self) -> torch.Tensor:
+        """Overwrites the factor by L^-1 and returns K^-1 (lower 128-tiles valid)."""
+        Kinv = torch.empty_like(self.A)
+        check(lib().rc_potri(ptr(self.A), self.n_pad, self.n_pad, self.n_pad * self.n_pad, self.batch, raw_ptr(self.work), ptr(Kinv), self.n_pad,
+                             self.n_pad * self.n_pad, stream_ptr()), 'rc_potri')
+        return Kinv
+
+    def lower(self, n: int) -> torch.Tensor:
+        """(batch, n, n) dense lower-triangular factor (zeros above the diagonal)."""
+        return extract_lower(self.A, n)
+
+
+def pad_identity(K: torch.Tensor) -> torch.Tensor:
+    """(batch, n, n) -> (batch, n_pad, n_pad) with identity padding."""
+    K = K if K.dim() == 3 else K[None]
+    b, n, _ = K.shape
+    n_pad = padded(n)
+    out = torch.empty((b, n_pad, n_pad), dtype=torch.float64, device=K.device)
+    check(lib().rc_pad_identity(ptr(K.contiguous()), n, n * n, ptr(out), n_pad, n_pad, n_pad * n_pad, b, stream_ptr()), 'rc_pad_identity')
+    return out
+
+
+def extract_lower(A: torch.Tensor, n: int, symmetrize=False) -> torch.Tensor:
+    b, n_pad, _ = A.shape
+    out = torch.empty((b, n, n), dtype=torch.float64, device=A.device)
+    check(lib().rc_extract_lower(ptr(A), n_pad, n_pad * n_pad, ptr(out), n, n * n, b, int(symmetrize), stream_ptr()), 'rc_extract_lower')
+    return out
+
+
+def apply_variance_noise(Kunit: torch.Tensor, F: torch.Tensor, E: Optional[torch.Tensor], L: int, N: int, *, pad=False, lower_only=False):
+    n = L * N
+    n_pad = padded(n) if pad else n
+    out = torch.empty((n_pad, n_pad), dtype=torch.float64, device=Kunit.device)
+    check(lib().rc_apply_variance_noise(ptr(Kunit), Kunit.shape[-1], ptr(F), ptr(E), L, N, n_pad, ptr(out), n_pad, int(lower_only), stream_ptr()),
+          'rc_apply_variance_noise')
+    return out
+
+
+class LmlGradPlan:
+    """Pre-allocated workspace for repeated LML(+gradient) evaluations of one model shape (the optimiser's hot loop)."""
+
+    def __init__(self, X: torch.Tensor, Y: torch.Tensor, L: int, batch: int, flags: int):
+        self.X, self.Y = X.contiguous(), Y.contiguous()
+        self.N, self.M = X.shape
+        self.L, self.batch, self.flags = L, batch, flags
+        assert Y.shape == (self.N, L * batch)
+        self.stride = int(lib().rc_lml_grad_stride(L, self.M))
+        self.nbytes = int(lib().rc_lml_grad_bufsize(self.N, self.M, L, batch, flags))
+        self.work = workspace(self.nbytes, X.device)
+        self.out = torch.empty((batch, self.stride), dtype=torch.float64, device=X.device)
+        self.info = torch.zeros(batch, dtype=torch.int32, device=X.device)
+
+    def __call__(self, ls: torch.Tensor, F: torch.Tensor, E: torch.Tensor, Kunit: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ls (batch*L, M), F, E (batch, L, L) device tensors. Returns the device tensor (batch, 1 + 2 L^2 + L M)."""
+        check(lib().rc_lml_grad(ptr(self.X), ptr(self.Y), self.N, self.M, self.L, self.batch, ptr(ls), ptr(F), ptr(E), ptr(Kunit), self.flags,
+                                raw_ptr(self.work), self.nbytes, ptr(self.out), raw_ptr(self.info), stream_ptr()), 'rc_lml_grad')
+        return self.out
+
+    def unpack(self, out_host):
+        """host (batch, stride) array -> list of dicts(lml, dF, dE, dls)."""
+        L, M = self.L, self.M
+        res = []
+        for row in out_host:
+            res.append({'lml': float(row[0]), 'dF': row[1:1 + L * L].reshape(L, L), 'dE': row[1 + L * L:1 + 2 * L * L].reshape(L, L),
+                        'dls': row[1 + 2 * L * L:].reshape(L, M)})
+        return res
+
+
+def predict_reduce(A: torch.Tensor, a: torch.Tensor):
+    """A (batch, n_pad, c_pad) = L^-1 Kmn, a (batch, n_pad) = L^-1 y  ->  mean, ss each (batch, c_pad)."""
+    b, n_pad, c_pad = A.shape
+    parts = workspace(lib().rc_predict_bufsize(c_pad, b), A.device)
+    mean = torch.empty((b, c_pad), dtype=torch.float64, device=A.device)
+    ss = torch.empty_like(mean)
+    check(lib().rc_predict_reduce(ptr(A), c_pad, n_pad * c_pad, ptr(a), n_pad, n_pad, c_pad, b, raw_ptr(parts), ptr(mean), ptr(ss), stream_ptr()),
+          'rc_predict_reduce')
+    return mean, ss
+
+
+def sobol_prepare(X, Lam, F, KinvY, is_F_diagonal: bool):
+    N, M = X.shape
+    L = Lam.shape[0]
+    P = L if is_F_diagonal else L * L
+    Phi = torch.empty((P, M), dtype=torch.float64, device=X.device)
+    g0 = torch.empty((P, N), dtype=torch.float64, device=X.device)
+    g0KY = torch.empty_like(g0)
+    check(lib().rc_sobol_prepare(ptr(X), N, M, ptr(Lam), ptr(F), ptr(KinvY), L, int(is_F_diagonal), ptr(Phi), ptr(g0), ptr(g0KY), stream_ptr()),
+          'rc_sobol_prepare')
+    return Phi, g0, g0KY
+
+
+def slice_mask(m0: int, m1: int) -> int:
+    return ((1 << max(m1 - m0, 0)) - 1) << m0
+
+
+def sobol_contract(X, Phi, c, L: int, is_F_diagonal: bool, masks: Sequence[int], parts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """-> V (len(masks), L, L) on the device."""
+    N, M = X.shape
+    P = Phi.shape[0]
+    ns = len(masks)
+    if parts is None:
+        parts = workspace(lib().rc_sobol_bufsize(N, P, ns), X.device)
+    V = torch.empty((ns, L, L), dtype=torch.float64, device=X.device)
+    arr = (ctypes.c_ulonglong * ns)(*[int(m) for m in masks])
+    check(lib().rc_sobol_contract(ptr(X), N, M, ptr(Phi), ptr(c), L, int(is_F_diagonal), ctypes.cast(arr, ctypes.c_void_p), ns, raw_ptr(parts),
+                                  ptr(V), stream_ptr()), 'rc_sobol_contract')
+    return V
