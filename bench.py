@@ -1,0 +1,355 @@
+"""Benchmark of the B200-native rom-comma hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+
+Workload (BASELINE.json metric): cfg3 = synthetic MOGPR N=4096, M=8, L=4 (n = 16384, 2.1 GB FP64 gram).
+A "step" is ONE evaluation of the covariant MOGPR log-marginal-likelihood plus its analytic gradient with respect to the kernel
+variance F and the noise covariance E (the model's default trainables, romcomma/gpr/kernels.py:54-57, gpr/models.py:57-60):
+gram -> Cholesky -> solves -> explicit inverse -> gradient contractions, n^3 FP64 flops.  `value` is evaluations per second with
+all inputs resident in HBM; `e2e` is the same evaluation through the public API (romcomma.gpf.models.MOGPR) from pinned HOST
+buffers, copies inside the timed region.  The second headline quantity, closed-form Sobol index sweeps per second on the same
+configuration, is reported in the "sobol" object of the same JSON line.
+
+N > 1 (torchrun, one process per GPU): a single dense factorisation does not shard ("replicas only"), so every rank
+evaluates its own hyper-parameter point of the same shape (multi-start / fold-parallel fitting) - weak scaling, no data-path
+collective; the Sobol sweep is sharded by marginal subset and gathered with one NCCL all_gather.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / 'rom-comma_b200'):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+METRIC, UNIT = 'mogpr_lml_grad_evals_per_s', 'evals/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='cfg3')
+    ap.add_argument('--N', type=int, default=None, help='override the number of samples (debugging only; the JSON line names it)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample-N', type=int, default=None, help='rows used by the CPU baseline sample (default: all for cpu_baseline, 2048 for --impl reference)')
+    return ap.parse_args()
+
+
+def workload_description(w, L, M):
+    N = w.X.shape[0]
+    return (f'{w.name} synthetic MOGPR N={N} M={M} L={L} (n={L * N}, {8e-9 * (L * N) ** 2:.2f} GB FP64 gram): covariant LML + analytic '
+            f'gradient w.r.t. kernel variance F and noise covariance E (default trainables); Sobol: first-order + closed + total sweep over all m')
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.thread.join(timeout=5)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7), ('sw_power_cap', 8)):
+                if len(r) > col and r[col].lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port = the reference algorithm through LAPACK; the reference itself needs TensorFlow/GPflow, absent here)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_eval_seconds(w, L, rows, repeats=1):
+    from threadpoolctl import threadpool_limits
+    from oracle import gp
+    cores = os.cpu_count() or 1
+    X, Y = w.X[:rows], w.Y[:rows]
+    best = float('inf')
+    with threadpool_limits(limits=cores):
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            gp.lml_grad_mo_lapack(X, Y, w.lengthscales, w.F, w.E)
+            best = min(best, time.perf_counter() - t0)
+    return best, cores
+
+
+def cpu_sobol_seconds(w, L, rows, n_slices):
+    """A bounded sample of the sweep: `n_slices` closed slices on the first `rows` samples, all host threads (one (pair, slice) block per task)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import sobol
+    cores = os.cpu_count() or 1
+    X = w.X[:rows]
+    M = X.shape[1]
+    rng = np.random.default_rng(0)
+    KiY = rng.standard_normal((L, 1, rows))
+    cal = sobol.ClosedSobol(X[:64], w.lengthscales, np.diag(w.F), KiY[:, :, :64], True)      # tiny: only to get Phi / shapes
+    Phi = cal.Phi
+    c = rng.standard_normal((L, 1, rows))
+    slices = [(0, m + 1) for m in range(M)][:n_slices]
+
+    def task(args):
+        l, j, s = args
+        acc = 0.0
+        for r0 in range(0, rows, 512):
+            rr = slice(r0, min(rows, r0 + 512))
+            acc += c[l, 0, rr] @ (sobol.H_block(X, Phi[l, 0], Phi[j, 0], s[0], s[1], rr) @ c[j, 0])
+        return acc
+    tasks = [(l, j, s) for l in range(L) for j in range(L) for s in slices]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(task, tasks))
+    return time.perf_counter() - t0, cores
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm on the host cores.  Under torchrun only rank 0 works."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    from romcomma import synthetic
+    w = synthetic.config(args.workload, N=args.N)
+    N, M = w.X.shape
+    L = w.Y.shape[1]
+    rows = min(N, args.cpu_sample_N or 2048)
+    scale = (N / rows) ** 3
+    for _ in range(args.warmup):
+        cpu_eval_seconds(w, L, min(rows, 512))
+    times = [cpu_eval_seconds(w, L, rows)[0] for _ in range(args.steps)]
+    cores = os.cpu_count() or 1
+    per_step = float(np.mean(times)) * scale
+    value = 1.0 / per_step
+    sample = (f'{args.steps} evaluations at N={rows} (n={L * rows}) of the same workload through LAPACK dpotrf+dpotri (OpenBLAS, {cores} threads); '
+              f'time scaled by (N/N_sample)^3 = {scale:g} to the full-size unit (the n^3 factorisation+inverse dominates)')
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'impl': 'reference', 'config': {'workload': workload_description(w, L, M)},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    from romcomma import _capi as C, distributed, synthetic
+    from romcomma.gpf import kernels, models
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the host arm).')
+    distributed.init_from_env('nccl')
+    rank, world = distributed.rank(), distributed.world_size()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    C.lib()
+
+    w = synthetic.config(args.workload, N=args.N)
+    N, M = w.X.shape
+    L = w.Y.shape[1]
+    n = L * N
+    # every rank gets its own hyper-parameter point of the same shape (rank 0 = the canonical one)
+    rng = np.random.default_rng(1000 + rank)
+    ls = w.lengthscales if rank == 0 else rng.uniform(0.5, 3.0, (L, M))
+    Fm = w.F if rank == 0 else np.diag(rng.uniform(0.5, 2.0, L))
+    dX, dY, dls, dF, dE = C.dev(w.X), C.dev(w.Y), C.dev(ls), C.dev(Fm[None]), C.dev(w.E[None])
+    plan = C.LmlGradPlan(dX, dY, L, 1, C.RC_GRAD_VARIANCE)
+
+    def sync_all():
+        distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        plan(dls, dF, dE)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = C.launch_count()
+    with ClockSampler(local) as clocks:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            plan(dls, dF, dE)
+        e1.record()
+        sync_all()
+    launches = C.launch_count() - launches0
+    ms_total = distributed.all_reduce_max(e0.elapsed_time(e1))
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)
+    info = int(plan.info.cpu()[0])
+    lml = float(plan.out[0, 0].item())
+    assert info == 0 and np.isfinite(lml), f'evaluation failed: info={info}, lml={lml}'
+
+    # ---- stage breakdown (outside the timed region) ---------------------------------------------------------------------
+    def timed(fn, reps=2):
+        best = float('inf')
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best, out
+    stages = {}
+    if rank == 0:
+        t_gram, Kp = timed(lambda: C.gram(dX, None, dls, dF, dE, pad_to=n, pad_identity=True, lower_only=True))
+        t_potrf, fac = timed(lambda: C.Factorization(C.gram(dX, None, dls, dF, dE, pad_to=n, pad_identity=True, lower_only=True)))
+        t_potrf -= t_gram
+        t_potri, _ = timed(lambda: fac.inverse_(), reps=1)
+        stages = {'gram_ms': t_gram, 'potrf_ms': t_potrf, 'potrf_tflops': n ** 3 / 3 / t_potrf * 1e-9, 'potri_ms': t_potri,
+                  'potri_tflops': 2 * n ** 3 / 3 / t_potri * 1e-9}
+        del Kp, fac
+        torch.cuda.empty_cache()
+    peaks = C.measure_peaks()
+
+    # ---- end to end through the public API, host buffers ----------------------------------------------------------------
+    Xh, Yh = torch.as_tensor(w.X).pin_memory(), torch.as_tensor(w.Y).pin_memory()
+
+    def e2e_step():
+        model = models.MOGPR((Xh, Yh), kernels.RBF(Fm, ls), noise_variance=w.E)          # H2D of X, Y (+ hyper-parameters inside)
+        loss, grads = model._loss_and_grad(model.trainable_variables)                      # D2H of {lml, dF, dE, dls} + info
+        return loss, grads, model
+    h2d = w.X.nbytes + w.Y.nbytes + ls.nbytes + Fm.nbytes + w.E.nbytes
+    d2h = plan.stride * 8 + 4
+    del plan
+    torch.cuda.empty_cache()
+    for _ in range(2):
+        loss, grads, model = e2e_step()
+        del model
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss, grads, model = e2e_step()
+        del model
+    sync_all()
+    e2e_s = distributed.all_reduce_max(time.perf_counter() - t0)
+    e2e_value = world * args.steps / e2e_s
+    assert abs(-loss - lml) <= 1e-9 * abs(lml) + 1e-9, (loss, lml)
+    torch.cuda.empty_cache()
+
+    # ---- Sobol sweep: 3 kinds x M slices + the full model, sharded over ranks by slice ----------------------------------
+    slices = [(m, m + 1) for m in range(M)] + [(0, m + 1) for m in range(M)] + [(m + 1, M) for m in range(M)] + [(0, M)]
+    masks = [C.slice_mask(*s) for s in slices]
+    mine = distributed.shard(masks)
+    KiY = torch.randn(L, N, dtype=torch.float64, device='cuda', generator=torch.Generator('cuda').manual_seed(7)) * 0.1
+    dLam, dFdiag = C.dev(w.lengthscales), C.dev(np.diag(w.F).copy())
+    parts = C.workspace(C.lib().rc_sobol_bufsize(N, L, len(mine)))
+
+    def sweep():
+        Phi, g0, g0KY = C.sobol_prepare(dX, dLam, dFdiag, KiY, True)
+        return C.sobol_contract(dX, Phi, g0KY, L, True, mine, parts)
+    for _ in range(3):
+        V = sweep()
+    sync_all()
+    sweeps = max(3, args.steps)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(sweeps):
+        V = sweep()
+        if world > 1:
+            V = distributed.all_gather_rows(V.reshape(len(mine), -1).cpu().numpy(), len(masks))
+    s1.record()
+    sync_all()
+    sobol_ms = distributed.all_reduce_max(s0.elapsed_time(s1)) / sweeps
+    pairs = L * (L + 1) // 2                                   # diagonal F: P = L "rows", symmetric half of the (a,b) pairs
+    tiles_frac = 1.0                                           # a != b pairs are full; a == b pairs are half: counted below
+    exps = len(masks) * N * N * (L * (L - 1) / 2 + L / 2)      # exp evaluations actually needed with the symmetry
+    sobol = {'metric': 'sobol_sweeps_per_s', 'value': 1e3 / sobol_ms, 'unit': 'sweeps/s', 'ms_per_sweep': sobol_ms, 'slices': len(masks),
+             'scaling': 'strong (marginal subsets sharded over ranks, one all_gather)' if world > 1 else 'single GPU',
+             'roofline': {'bound': 'fp64 exp/ALU', 'achieved': exps / (sobol_ms * 1e-3) * 1e-9, 'peak': peaks['exp_gexps'], 'unit': 'Gexp/s',
+                          'frac': exps / (sobol_ms * 1e-3) * 1e-9 / peaks['exp_gexps'],
+                          'note': 'algorithmic exp count with the (a,N)<->(b,n) symmetry; peak = register-resident libm exp loop measured live'}}
+
+    # ---- CPU baseline on this box's host cores (rank 0, single-GPU runs only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows = min(N, args.cpu_sample_N or N)
+        secs, cores = cpu_eval_seconds(w, L, rows)
+        scale = (N / rows) ** 3
+        cpu = {'value': 1.0 / (secs * scale), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': f'1 evaluation at N={rows} (n={L * rows}) through LAPACK dpotrf+dpotri (OpenBLAS, {cores} threads), {secs:.1f} s'
+                         + (f', scaled by {scale:g}' if scale != 1 else ', full size, no scaling')}
+        srows, nsl = min(N, 2048), 4
+        ssecs, _ = cpu_sobol_seconds(w, L, srows, nsl)
+        full = ssecs * (N / srows) ** 2 * (len(masks) / nsl)
+        cpu['sobol'] = {'value': 1.0 / full, 'unit': 'sweeps/s',
+                        'sample': f'{nsl} closed slices x {L * L} output pairs on N={srows} rows, blocked numpy exp+dgemm on {cores} threads, {ssecs:.1f} s; '
+                                  f'scaled by (N/N_s)^2 x slices = {(N / srows) ** 2 * len(masks) / nsl:g}'}
+
+    if rank == 0:
+        flops = float(n) ** 3
+        achieved = flops / (ms_per_step * 1e-3) * 1e-12
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+                'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': workload_description(w, L, M), 'parallelism': f'replicas x{world} (one hyper-parameter point per GPU)',
+                           'l2': 'inputs larger than L2: each step rewrites and re-reads 2.1 GB matrices (126 MB L2), no explicit flush needed'},
+                'roofline': {'bound': 'tensor', 'kernel': 'gemm_dmma_kernel (FP64 DMMA.8x8x4 tiles: Cholesky trailing update, TRSM, triangular inverse, LAUUM)',
+                             'achieved': achieved, 'peak': peaks['dmma_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['dmma_tflops'],
+                             'traffic': None,
+                             'note': 'achieved = algorithmic n^3 flops (n^3/3 potrf + 2n^3/3 inverse) / whole-step time, so it also carries the gram, '
+                                     'panel, solve and reduction kernels; peak = FP64 tensor peak measured live by a register-resident DMMA loop '
+                                     '(MEASURED_PEAKS.json has no FP64 entry)', 'stages': stages},
+                'cpu_baseline': cpu,
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                        'ms_per_step': 1e3 * e2e_s / args.steps,
+                        'path': 'romcomma.gpf.models.MOGPR(data=(pinned host X, Y), ...)._loss_and_grad: H2D of X, Y and hyper-parameters, D2H of LML+gradient'},
+                'gpu_launches': int(launches), 'sobol': sobol, 'clocks': clocks.summary(), 'lml': lml}
+        print(json.dumps(line), flush=True)
+    distributed.barrier()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

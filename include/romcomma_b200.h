@@ -29,6 +29,12 @@ typedef void* rc_stream_t;
 int rc_version(void);
 const char* rc_last_error(void);
 int rc_padded(int n);
+/* Number of CUDA kernels this library has launched in this process (bench.py's "gpu_launches"). */
+long rc_launch_count(void);
+/* Roofline denominators measured on the current device with register-resident loops (host-blocking, default stream):
+ * FP64 tensor-core (DMMA.8x8x4) TFLOP/s and FP64 exp() evaluations per second (in 1e9/s). scratch: >= 8 bytes of device memory. */
+int rc_measure_dmma_tflops(double* scratch, double* tflops_host);
+int rc_measure_exp_gexps(double* scratch, double* gexps_host);
 
 /* ---- gram ---------------------------------------------------------------------------------------------------------
  * out[(l,n),(l',n')] = F[l,l'] * exp(-1/2 sum_m (X[n,m]/ls[l,m] - X2[n',m]/ls[l',m])^2) + E[l,l'] * [n == n']
@@ -91,12 +97,14 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
                 const double* Kunit, int flags, void* work, size_t work_bytes, double* out, int* info, rc_stream_t stream);
 
 /* ---- prediction reductions -----------------------------------------------------------------------------------------
- * With A = L^-1 Kmn (n_pad x c_pad, from rc_trsm_fwd) and a = L^-1 y: mean[c] = sum_k A[k][c] a[k], ss[c] = sum_k A[k][c]^2,
- * i.e. fmean and the diagonal of A^T A of gpflow base_conditional (romcomma/gpf/models.py:97-109) without forming the full
- * (L n*)^2 covariance.  parts: rc_predict_bufsize bytes. */
+ * With A = L^-1 Kmn (n_pad x c_pad, from rc_trsm_fwd; column c = l*nstar + i) and a = L^-1 y:
+ *   mean[z][i][l] = sum_k A[k][c] a[k],   var[z][i][l] = kdiag[z][l] - sum_k A[k][c]^2 (+ noise[z][l] if noise != NULL)
+ * i.e. fmean and diag(Knn - A^T A) of gpflow base_conditional as used by MOGPR.predict_f (romcomma/gpf/models.py:97-111), plus
+ * the diag(E) of MOGaussian._predict_mean_and_var (romcomma/gpf/likelihoods.py:85-89), in the (n*, L) layout predict_f returns,
+ * without forming the full (L n*)^2 covariance.  kdiag = diag F (L per problem).  parts: rc_predict_bufsize bytes. */
 size_t rc_predict_bufsize(int c_pad, int batch);
-int rc_predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n_pad, int c_pad, int batch, void* parts,
-                      double* mean, double* ss, rc_stream_t stream);
+int rc_predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n_pad, int c_pad, int batch, int L, int nstar,
+                      const double* kdiag, const double* noise, void* parts, double* mean, double* var, rc_stream_t stream);
 
 /* ---- Sobol ---------------------------------------------------------------------------------------------------------
  * rc_sobol_prepare: Phi, g0, g0KY (mean-centred) of ClosedSobol._calibrate / _Lambda2 (romcomma/gsa/calibrators.py:82-92,99-109,

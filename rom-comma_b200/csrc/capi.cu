@@ -4,12 +4,15 @@
 #include "common.cuh"
 #include "gp_ops.h"
 #include "sobol.h"
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
 
 namespace rc {
 static thread_local char g_err[512] = "";
+static std::atomic<long> g_launches{0};
+void count_launches(long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -75,6 +78,7 @@ using namespace rc;
 extern "C" {
 
 int rc_version(void) { return 100; }
+long rc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* rc_last_error(void) { return g_err; }
 int rc_padded(int n) { return round_up(n, TILE); }
 
@@ -229,10 +233,11 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
 
 size_t rc_predict_bufsize(int c_pad, int batch) { return align256(predict_workspace_bytes(c_pad, batch)); }
 
-int rc_predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n_pad, int c_pad, int batch, void* parts,
-                      double* mean, double* ss, rc_stream_t stream) {
-  RC_REQUIRE(A && a && parts && mean && ss, -2, "rc_predict_reduce: null pointer");
-  return predict_reduce(A, lda, strideA, a, stride_a, n_pad, c_pad, batch, static_cast<double*>(parts), mean, ss, (cudaStream_t)stream);
+int rc_predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n_pad, int c_pad, int batch, int L, int nstar,
+                      const double* kdiag, const double* noise, void* parts, double* mean, double* var, rc_stream_t stream) {
+  RC_REQUIRE(A && a && kdiag && parts && mean && var, -2, "rc_predict_reduce: null pointer");
+  return predict_reduce(A, lda, strideA, a, stride_a, n_pad, c_pad, batch, L, nstar, kdiag, noise, static_cast<double*>(parts), mean, var,
+                        (cudaStream_t)stream);
 }
 
 size_t rc_sobol_bufsize(int N, int P, int nslices) { return align256(sobol_workspace_bytes(N, P, nslices)); }

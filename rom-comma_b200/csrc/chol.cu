@@ -233,11 +233,13 @@ int trsv_lower(const double* A, int n, long ld, long strideA, int batch, const d
       dim3 grid(nblk - k, batch);
       trsv_fwd_step_kernel<<<grid, 256, 0, st>>>(A, ld, strideA, dinv, strideD, w, x, strideV, k);
     }
+    count_launches(nblk - 1);
   } else {
     for (int k = nblk - 1; k >= 0; --k) {
       dim3 grid(k + 1, batch);
       trsv_bwd_step_kernel<<<grid, 256, 0, st>>>(A, ld, strideA, dinv, strideD, w, x, strideV, k);
     }
+    count_launches(nblk - 1);
   }
   RC_LAUNCH_OK();
   return 0;

@@ -10,6 +10,8 @@ constexpr int TILE = 128;   // every factorisation matrix is padded to a multipl
 
 // Thread-local last error text for the C ABI (rc_last_error).
 void set_error(const char* fmt, ...);
+// Kernel-launch counter behind rc_launch_count(): bench.py's "gpu_launches" claim is counted here, not estimated.
+void count_launches(long n);
 
 #define RC_CUDA_OK(expr)                                                                          \
   do {                                                                                            \
@@ -20,7 +22,11 @@ void set_error(const char* fmt, ...);
     }                                                                                             \
   } while (0)
 
-#define RC_LAUNCH_OK() RC_CUDA_OK(cudaGetLastError())
+#define RC_LAUNCH_OK()                \
+  do {                                 \
+    rc::count_launches(1);             \
+    RC_CUDA_OK(cudaGetLastError());    \
+  } while (0)
 
 #define RC_REQUIRE(cond, code, ...) \
   do {                              \

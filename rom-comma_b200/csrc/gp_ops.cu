@@ -371,27 +371,32 @@ __global__ void predict_partial_kernel(const double* __restrict__ A, long lda, l
   pz[c_pad + c] = ss;
 }
 
-__global__ void predict_finish_kernel(const double* __restrict__ parts, int c_pad, double* __restrict__ mean, double* __restrict__ ss) {
+// mean[z][i][l] = sum of partials,  var[z][i][l] = kdiag[z][l] - sum of squares (+ noise[z][l]);  column c = l*nstar + i
+__global__ void predict_finish_kernel(const double* __restrict__ parts, int c_pad, int L, int nstar, const double* __restrict__ kdiag,
+                                      const double* __restrict__ noise, double* __restrict__ mean, double* __restrict__ var) {
   const int z = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= c_pad) return;
+  if (c >= L * nstar) return;
   double m = 0.0, s = 0.0;
   for (int sp = 0; sp < PR_SPLIT; ++sp) {
     const double* pz = parts + ((long)z * PR_SPLIT + sp) * 2 * c_pad;
     m += pz[c];
     s += pz[c_pad + c];
   }
-  mean[(long)z * c_pad + c] = m;
-  ss[(long)z * c_pad + c] = s;
+  const int l = c / nstar, i = c - l * nstar;
+  const long o = ((long)z * nstar + i) * L + l;
+  mean[o] = m;
+  var[o] = kdiag[(long)z * L + l] - s + (noise ? noise[(long)z * L + l] : 0.0);
 }
 
 size_t predict_workspace_bytes(int c_pad, int batch) { return (size_t)batch * PR_SPLIT * 2 * c_pad * sizeof(double); }
 
-int predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n, int c_pad, int batch, double* parts, double* mean,
-                   double* ss, cudaStream_t st) {
+int predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n, int c_pad, int batch, int L, int nstar,
+                   const double* kdiag, const double* noise, double* parts, double* mean, double* var, cudaStream_t st) {
+  RC_REQUIRE(L * nstar <= c_pad, -2, "predict_reduce: L*nstar=%d exceeds c_pad=%d", L * nstar, c_pad);
   predict_partial_kernel<<<dim3((c_pad + 127) / 128, PR_SPLIT, batch), 128, 0, st>>>(A, lda, strideA, a, stride_a, n, c_pad, parts);
   RC_LAUNCH_OK();
-  predict_finish_kernel<<<dim3((c_pad + 127) / 128, batch), 128, 0, st>>>(parts, c_pad, mean, ss);
+  predict_finish_kernel<<<dim3((c_pad + 127) / 128, batch), 128, 0, st>>>(parts, c_pad, L, nstar, kdiag, noise, mean, var);
   RC_LAUNCH_OK();
   return 0;
 }

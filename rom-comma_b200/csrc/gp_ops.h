@@ -37,7 +37,7 @@ size_t grad_workspace_bytes(int n_pad, int L, int M, int batch);
 int grad_reduce(GradArgs a, int n_pad, int batch, double* out, cudaStream_t st);
 
 size_t predict_workspace_bytes(int c_pad, int batch);
-int predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n, int c_pad, int batch, double* parts, double* mean,
-                   double* ss, cudaStream_t st);
+int predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n, int c_pad, int batch, int L, int nstar,
+                   const double* kdiag, const double* noise, double* parts, double* mean, double* var, cudaStream_t st);
 
 }  // namespace rc

@@ -1,0 +1,92 @@
+// Live roofline denominators: register-resident DMMA.8x8x4 and FP64 exp loops (no memory traffic).  MEASURED_PEAKS.json has no
+// FP64 entry, so bench.py measures these on the box it runs on and says so next to every fraction.
+#include "../../include/romcomma_b200.h"
+#include "common.cuh"
+
+namespace rc {
+
+__global__ void dmma_peak_kernel(double* out, int iters) {
+  double c[8][2];
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
+__global__ void exp_peak_kernel(double* out, int iters) {
+  double x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = -1e-3 * (threadIdx.x + i + 1);
+  double s = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s += exp(x[i]);
+      x[i] *= 1.0000001;
+    }
+  }
+  if (s == 123.456) out[0] = s;
+}
+
+template <typename Launch>
+static int time_best(Launch launch, int reps, float* best_ms) {
+  cudaEvent_t e0, e1;
+  RC_CUDA_OK(cudaEventCreate(&e0));
+  RC_CUDA_OK(cudaEventCreate(&e1));
+  launch();
+  RC_CUDA_OK(cudaDeviceSynchronize());
+  *best_ms = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    RC_CUDA_OK(cudaEventRecord(e0));
+    launch();
+    RC_CUDA_OK(cudaEventRecord(e1));
+    RC_CUDA_OK(cudaEventSynchronize(e1));
+    float ms;
+    RC_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < *best_ms) *best_ms = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+
+}  // namespace rc
+
+using namespace rc;
+
+extern "C" {
+
+int rc_measure_dmma_tflops(double* scratch, double* tflops) {
+  RC_REQUIRE(scratch && tflops, -2, "rc_measure_dmma_tflops: null pointer");
+  int dev, sms;
+  RC_CUDA_OK(cudaGetDevice(&dev));
+  RC_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int iters = 20000, threads = 512;
+  float ms;
+  int rc = time_best([&] { dmma_peak_kernel<<<sms, threads>>>(scratch, iters); }, 5, &ms);
+  if (rc) return rc;
+  *tflops = (double)sms * (threads / 32) * iters * 8.0 * (8 * 8 * 4 * 2) / ms * 1e-9;
+  return 0;
+}
+
+int rc_measure_exp_gexps(double* scratch, double* gexps) {
+  RC_REQUIRE(scratch && gexps, -2, "rc_measure_exp_gexps: null pointer");
+  int dev, sms;
+  RC_CUDA_OK(cudaGetDevice(&dev));
+  RC_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int iters = 2000, threads = 1024;
+  float ms;
+  int rc = time_best([&] { exp_peak_kernel<<<sms * 2, threads>>>(scratch, iters); }, 5, &ms);
+  if (rc) return rc;
+  *gexps = (double)sms * 2 * threads * iters * 4.0 / ms * 1e-6;
+  return 0;
+}
+
+}  // extern "C"

@@ -23,6 +23,9 @@ _SIGNATURES = {
     'rc_version': (ctypes.c_int, []),
     'rc_last_error': (ctypes.c_char_p, []),
     'rc_padded': (ctypes.c_int, [ctypes.c_int]),
+    'rc_launch_count': (ctypes.c_long, []),
+    'rc_measure_dmma_tflops': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
+    'rc_measure_exp_gexps': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
     'rc_gram': (ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p, c_double_p,
                                c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                ctypes.c_void_p]),
@@ -49,7 +52,8 @@ _SIGNATURES = {
                                    ctypes.c_void_p]),
     'rc_predict_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     'rc_predict_reduce': (ctypes.c_int, [c_double_p, ctypes.c_long, ctypes.c_long, c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
-                                         ctypes.c_int, ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_void_p]),
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_void_p, c_double_p, c_double_p,
+                                         ctypes.c_void_p]),
     'rc_sobol_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'rc_sobol_prepare': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
                                         c_double_p, c_double_p, c_double_p, ctypes.c_void_p]),
@@ -105,6 +109,20 @@ def raw_ptr(t: torch.Tensor):
 
 def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(lib().rc_launch_count())
+
+
+def measure_peaks() -> dict:
+    """Live FP64 roofline denominators of the current device: DMMA TFLOP/s and exp evaluations (1e9/s)."""
+    scratch = torch.zeros(8, dtype=torch.float64, device='cuda')
+    tf, ge = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    torch.cuda.synchronize()
+    check(lib().rc_measure_dmma_tflops(ptr(scratch), ctypes.byref(tf)), 'rc_measure_dmma_tflops')
+    check(lib().rc_measure_exp_gexps(ptr(scratch), ctypes.byref(ge)), 'rc_measure_exp_gexps')
+    return {'dmma_tflops': tf.value, 'exp_gexps': ge.value}
 
 
 def padded(n: int) -> int:
@@ -247,15 +265,15 @@ class LmlGradPlan:
         return res
 
 
-def predict_reduce(A: torch.Tensor, a: torch.Tensor):
-    """A (batch, n_pad, c_pad) = L^-1 Kmn, a (batch, n_pad) = L^-1 y  ->  mean, ss each (batch, c_pad)."""
+def predict_reduce(A: torch.Tensor, a: torch.Tensor, L: int, nstar: int, kdiag: torch.Tensor, noise: Optional[torch.Tensor]):
+    """A (batch, n_pad, c_pad) = L^-1 Kmn, a (batch, n_pad) = L^-1 y, kdiag/noise (batch, L)  ->  mean, var each (batch, nstar, L)."""
     b, n_pad, c_pad = A.shape
     parts = workspace(lib().rc_predict_bufsize(c_pad, b), A.device)
-    mean = torch.empty((b, c_pad), dtype=torch.float64, device=A.device)
-    ss = torch.empty_like(mean)
-    check(lib().rc_predict_reduce(ptr(A), c_pad, n_pad * c_pad, ptr(a), n_pad, n_pad, c_pad, b, raw_ptr(parts), ptr(mean), ptr(ss), stream_ptr()),
-          'rc_predict_reduce')
-    return mean, ss
+    mean = torch.empty((b, nstar, L), dtype=torch.float64, device=A.device)
+    var = torch.empty_like(mean)
+    check(lib().rc_predict_reduce(ptr(A), c_pad, n_pad * c_pad, ptr(a), n_pad, n_pad, c_pad, b, L, nstar, ptr(kdiag), ptr(noise), raw_ptr(parts),
+                                  ptr(mean), ptr(var), stream_ptr()), 'rc_predict_reduce')
+    return mean, var
 
 
 def sobol_prepare(X, Lam, F, KinvY, is_F_diagonal: bool):

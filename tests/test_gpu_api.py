@@ -1,0 +1,183 @@
+"""GPU: the drop-in Python API (romcomma.gpf / gpr / gsa / user.run) end to end against the oracle."""
+import random
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from conftest import assert_close, random_problem
+from oracle import gp, sobol
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpf_mogpr_lml_predict_and_dlpack(golden):
+    from romcomma.gpf import kernels, models
+    g = golden['rand_a']
+    X, Y, ls, F, E = g['X'], g['Y'], g['ls'], g['F'], g['E']
+    Ed = np.diag(np.diag(E))                                                  # constructor keeps the diagonal only (quirk Q1)
+    model = models.MOGPR((X, Y), kernels.RBF(F, ls), noise_variance=E)
+    assert (model.L, model.M) == (3, 5)
+    assert_close(model.likelihood.variance.value.numpy(), Ed, rtol=1e-12, what='noise re-diagonalised')
+    assert_close(model.log_marginal_likelihood().numpy(), gp.lml_mo(X, Y, ls, F, Ed), what='lml')
+    assert_close(model.training_loss().numpy(), -gp.lml_mo(X, Y, ls, F, Ed), what='training loss')
+    assert_close(model.KXX.numpy(), gp.gram_mo(X, None, ls, F), what='KXX (cached unit gram branch)')
+    K4 = model.kernel.K_unit_variance(X)
+    assert tuple(K4.shape) == (3, 17, 3, 17)
+    assert_close(model.likelihood.add_to(model.KXX).numpy(), gp.add_noise_mo(gp.gram_mo(X, None, ls, F), Ed), what='add_to')
+    mean, var = model.predict_f(g['Xs'])
+    rm, rv = gp.predict_mo(X, Y, ls, F, Ed, g['Xs'], y_instead_of_f=False)
+    assert tuple(mean.shape) == (6, 3)
+    assert_close(mean.numpy(), rm, what='f mean')
+    assert_close(var.numpy(), rv, what='f var')
+    ym, yv = model.predict_y(g['Xs'])
+    assert_close(yv.numpy(), rv + np.diag(Ed)[None, :], what='y var')
+    # results stay on the device and travel by DLPack
+    assert mean.is_cuda
+    back = torch.utils.dlpack.from_dlpack(mean.to_dlpack())
+    assert back.data_ptr() == mean.data_ptr()
+    # the K_d family on the materialised scaled difference (API parity, small inputs)
+    d = (torch.as_tensor(X)[None, :, :] / torch.as_tensor(ls)[:, None, :])
+    d = d[:, :, None, None, :] - d[None, None, :, :, :]
+    assert_close(model.kernel.K_d(d).numpy(), gp.gram_mo(X, None, ls, F), what='K_d')
+
+
+def test_gpf_training_reaches_the_oracle_optimum():
+    """L-BFGS-B on the device LML+gradient: the optimum satisfies the oracle's first-order condition and beats the start."""
+    from romcomma import gf_compat as gf
+    from romcomma.gpf import kernels, models
+    X, Y, ls, F, E = random_problem(60, 2, 2, seed=4, full_E=False)
+    model = models.MOGPR((X, Y), kernels.RBF(F, ls), noise_variance=E)
+    gf.set_trainable(model.kernel.lengthscales, True)
+    start = float(model.log_marginal_likelihood())
+    names = [v.name for v in model.trainable_variables]
+    assert names == ['KernelLengthscales', 'KernelVariance.cholesky_diagonal', 'KernelVariance.cholesky_lower_triangle',
+                     'LikelihoodVariance.cholesky_diagonal', 'LikelihoodVariance.cholesky_lower_triangle']
+    # analytic gradient w.r.t. the unconstrained variables == oracle chain rule
+    loss, grads = model._loss_and_grad(model.trainable_variables)
+    r = gp.lml_grad_mo(X, Y, ls, F, E)
+    uF, lowF = gp.variance_pack(F)
+    uE, lowE = gp.variance_pack(E)
+    dFd, dFl = gp.chain_variance(r['dF'], uF, lowF)
+    dEd, dEl = gp.chain_variance(r['dE'], uE, lowE)
+    ref = [-(r['dls'] * gp.sigmoid(gp.softplus_inverse(ls))).reshape(2, 1, 2), -dFd, -dFl, -dEd, -dEl]
+    for a, b, nm in zip(grads, ref, names):
+        assert_close(a, b, atol=1e-8, what=nm)
+    res = gf.optimizers.Scipy().minimize(model.training_loss, model.trainable_variables, method='L-BFGS-B', options={'maxiter': 200, 'gtol': 1e-10})
+    end = float(model.log_marginal_likelihood())
+    assert end > start + 1.0 and res.nit > 3
+    lsn, Fn, En = model.kernel.lengthscales_neat.numpy(), model.kernel.variance.value.numpy(), model.likelihood.variance.value.numpy()
+    assert_close(end, gp.lml_mo(X, Y, lsn, Fn, En), what='LML at the optimum')
+    g = gp.lml_grad_mo(X, Y, lsn, Fn, En)
+    assert np.abs(g['dls']).max() < 1e-3 * max(1.0, abs(end))
+
+
+@pytest.fixture()
+def small_repo(tmp_path):
+    from romcomma.user import functions, sample
+    np.random.seed(1)
+    random.seed(1)
+    fn = sample.Function(tmp_path, sample.DOE.latin_hypercube, functions.ISHIGAMI.subVector('ish', ['standard', 'balanced']), N=120, M=3,
+                         noise_variance=sample.GaussianNoise.Variance(2, 0.04, False, False), overwrite_existing=True)
+    return fn.repo.into_K_folds(2)
+
+
+def test_user_run_gpr_and_gsa_layout_and_values(small_repo):
+    """user.run.gpr / gsa over folds: variant then covariant model, files in the reference layout, values equal to the oracle
+    evaluated at the fitted hyper-parameters read back from the csv files."""
+    from romcomma.data.storage import Fold
+    from romcomma.gpr.models import MOGP
+    from romcomma.gsa.models import GSA
+    from romcomma.user import run
+    repo = small_repo
+    names = run.gpr('gpr', repo, is_read=None, is_covariant=None, is_isotropic=False, maxiter=40)
+    assert names == ['gpr.v.a', 'gpr.c.a']
+    gsa_names = run.gsa('gpr', repo, is_covariant=None, is_isotropic=False)
+    assert [str(p) for p in gsa_names] == ['gpr.v.a/gsa/first_order', 'gpr.v.a/gsa/closed', 'gpr.v.a/gsa/total',
+                                           'gpr.c.a/gsa/first_order', 'gpr.c.a/gsa/closed', 'gpr.c.a/gsa/total']
+    for k in repo.folds:
+        fold = Fold(repo, k)
+        for name, cov in (('gpr.v.a', False), ('gpr.c.a', True)):
+            folder = fold.folder / name
+            for f in ('kernel.csv', 'meta.json', 'kernel/variance.csv', 'kernel/lengthscales.csv', 'likelihood/variance.csv',
+                      'likelihood/log_marginal.csv', 'test.csv', 'test_summary.csv', 'gsa/closed/S.csv', 'gsa/total/V.csv', 'gsa/first_order/meta.json'):
+                assert (folder / f).exists(), (k, name, f)
+            var = pd.read_csv(folder / 'kernel/variance.csv', index_col=0).values
+            assert var.shape == ((2, 2) if cov else (1, 2))
+            assert pd.read_csv(folder / 'kernel/lengthscales.csv', index_col=0).values.shape == (2, 3)
+    for f in ('gpr.v.a/test.csv', 'gpr.c.a/likelihood/variance.csv', 'gpr.v.a/gsa/closed/S.csv', 'gpr.c.a/gsa/total/meta.json'):
+        assert (repo.folder / f).exists(), f
+    # values: re-read the fitted variant GP of fold 0 and compare every device result with the oracle at the same hyper-parameters
+    fold = Fold(repo, 0)
+    gpv = MOGP('gpr.v.a', fold, is_read=True, is_covariant=False, is_isotropic=False)
+    X, Y = fold.X.values, fold.Y.values
+    ls = gpv.kernel.data.frames.lengthscales.np
+    var = gpv.kernel.data.frames.variance.np[0]
+    noise = gpv.likelihood.data.frames.variance.np[0]
+    lml_csv = gpv.likelihood.data.frames.log_marginal.np[0]
+    for l in range(2):
+        assert_close(lml_csv[l], gp.lml_rbf(X, Y[:, l], ls[l], var[l], noise[l]), rtol=1e-8, what=f'log_marginal.csv[{l}]')
+    xs = fold.test_x.values[:7]
+    mean, std = gpv.predict(xs)
+    for l in range(2):
+        rm, rv = gp.predict_rbf(X, Y[:, l], ls[l], var[l], noise[l], xs)
+        assert_close(mean[:, l], rm, what='variant mean')
+        assert_close(std[:, l], np.sqrt(rv), what='variant std (quirk Q6: predict returns the standard deviation)')
+    assert_close(gpv.K_cho.numpy(), gp.k_cho_rbf(X, ls, var, noise), what='K_cho (L,N,N)')
+    KiY = gpv.K_inv_Y.numpy()
+    assert KiY.shape == (2, 1, X.shape[0])
+    assert_close(KiY, gp.k_inv_y_rbf(X, Y, ls, var, noise), rtol=1e-7, atol=1e-8, what='K_inv_Y')
+    assert np.all(gpv.check_K_inv_Y(xs) < 1e-9)
+    ref = sobol.sweep(X, ls, var, gp.k_inv_y_rbf(X, Y, ls, var, noise), True)
+    for kind in GSA.ALL_KINDS:
+        S = pd.read_csv(fold.folder / 'gpr.v.a' / 'gsa' / kind.name.lower() / 'S.csv', index_col=[0, 1]).values.reshape(2, 2, 4)
+        assert_close(S, ref[int(kind)]['S'], rtol=0, atol=6e-7, what=f'S.csv {kind.name} (csv holds 6 decimals)')
+    # covariant GP of fold 1
+    fold1 = Fold(repo, 1)
+    gpc = MOGP('gpr.c.a', fold1, is_read=True, is_covariant=True, is_isotropic=False)
+    X, Y = fold1.X.values, fold1.Y.values
+    ls, F, E = gpc.kernel.data.frames.lengthscales.np, gpc.kernel.data.frames.variance.np, gpc.likelihood.data.frames.variance.np
+    assert np.count_nonzero(E - np.diag(np.diag(E))) == 0, 'stored likelihood variance is re-diagonalised on read (quirk Q1)'
+    mean, std = gpc.predict(xs)
+    rm, rv = gp.predict_mo(X, Y, ls, F, E, xs)
+    assert_close(mean, rm, what='covariant mean')
+    assert_close(std, np.sqrt(rv), what='covariant std')
+    assert_close(gpc.K_cho.numpy(), gp.k_cho_mo(X, ls, F, E), what='K_cho (LN,LN)')
+    assert_close(gpc.K_inv_Y.numpy(), gp.k_inv_y_mo(X, Y, ls, F, E), rtol=1e-7, atol=1e-8, what='covariant K_inv_Y')
+    assert np.all(gpc.check_K_inv_Y(xs) < 1e-9)
+
+
+def test_closed_sobol_calibrator_attributes(small_repo):
+    from romcomma.data.storage import Fold
+    from romcomma.gpr.models import MOGP
+    from romcomma.gsa.calibrators import ClosedSobol
+    fold = Fold(small_repo, 2)
+    gpm = MOGP('gp', fold, is_read=False, is_covariant=True, is_isotropic=False,
+               likelihood_variance=np.array([[0.02, 0.0], [0.0, 0.03]]))
+    gpm.kernel.data.replace(variance=np.array([[1.5, 0.3], [0.3, 0.8]]), lengthscales=np.array([[1.0, 2.0, 0.7], [0.5, 1.5, 2.5]]))
+    gpm = MOGP('gp', fold, is_read=True, is_covariant=True, is_isotropic=False)
+    X, Y = fold.X.values, fold.Y.values
+    ls, F, E = gpm.kernel.data.frames.lengthscales.np, gpm.kernel.data.frames.variance.np, gpm.likelihood.data.frames.variance.np
+    KiY = gp.k_inv_y_mo(X, Y, ls, F, E)
+    for diag in (True, False):
+        cal = ClosedSobol(gpm, is_F_diagonal=diag)
+        ref = sobol.ClosedSobol(X, ls, F, KiY, diag)
+        assert cal.is_F_diagonal == diag
+        for j in range(3):
+            assert_close(cal.Lambda2[1][j].numpy(), ref.Lambda2[1][j], what='Lambda2')
+            assert_close(cal.Lambda2[-1][j].numpy(), ref.Lambda2[-1][j], what='Lambda2^-1')
+        assert_close(cal.Phi.numpy(), ref.Phi, what='Phi')
+        assert_close(cal.g0.numpy(), ref.g0, what='g0')
+        assert_close(cal.g0KY.numpy(), ref.g0KY, rtol=1e-7, atol=1e-9, what='g0KY')
+        assert_close(cal.G.numpy(), ref.G, what='G')
+        for j in range(3):
+            assert_close(cal.V[j].numpy(), ref.V[j], rtol=1e-7, atol=1e-9, what=f'V[{j}]')
+        assert_close(cal.S.numpy(), ref.S, rtol=1e-7, atol=1e-9, what='S')
+        out = cal.marginalize((1, 3))
+        assert_close(out['V'].numpy(), ref.marginalize((1, 3))['V'], rtol=1e-7, atol=1e-9, what='marginalize V')
+        assert_close(out['S'].numpy(), ref.marginalize((1, 3))['S'], rtol=1e-7, atol=1e-9, what='marginalize S')
+        subs = cal.marginalize_subsets([[0, 2], [1]])
+        assert_close(subs[0]['V'].numpy(), sobol.subset_V(X, ls, F, KiY, [0, 2], diag)['V'], rtol=1e-7, atol=1e-9, what='subset {0,2}')
+    # default is_F_diagonal: True unless the GP's meta says the kernel covariance was trained (quirk Q3)
+    assert ClosedSobol(gpm).is_F_diagonal is True

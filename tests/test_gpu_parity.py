@@ -1,0 +1,241 @@
+"""GPU: the CUDA path, called through the C ABI (romcomma._capi -> librc_b200.so), against the CPU oracle on identical seeded
+inputs; golden vectors; and size-independent properties at the full benchmark size.  Tolerance: rtol 1e-8 / atol 1e-10
+(BASELINE.json north_star) unless a test states why it differs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, random_problem
+from oracle import gp, sobol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def C():
+    assert torch.cuda.is_available(), 'these tests need a GPU'
+    from romcomma import _capi
+    _capi.lib()
+    return _capi
+
+
+def _dense_K(X, ls, F, E):
+    return gp.add_noise_mo(gp.gram_mo(X, None, ls, F), E)
+
+
+# ---- gram -------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('N,M,L,full_F', [(50, 3, 2, True), (64, 1, 1, False), (130, 5, 3, False), (7, 2, 4, True), (257, 20, 2, True)])
+def test_gram_matches_oracle(C, N, M, L, full_F):
+    X, Y, ls, F, E = random_problem(N, M, L, seed=N, full_F=full_F)
+    dX, dls = C.dev(X), C.dev(ls)
+    n = L * N
+    K = C.gram(dX, None, dls, C.dev(F[None]), C.dev(E[None]))[0, :n, :n].cpu().numpy()
+    assert_close(K, _dense_K(X, ls, F, E), what='K')
+    Ku = C.gram(dX, None, dls, None, None)[0, :n, :n].cpu().numpy()
+    assert_close(Ku.reshape(L, N, L, N), gp.gram_mo_unit(X, None, ls), what='K_unit')
+    X2 = np.random.default_rng(1).normal(size=(11, M))
+    Kx = C.gram(dX, C.dev(X2), dls, C.dev(F[None]), None)[0, :n, :L * 11].cpu().numpy()
+    assert_close(Kx, gp.gram_mo(X, X2, ls, F), what='K(X, X2)')
+    # cached-unit-gram branch of MOGPR.KXX
+    Kc = C.apply_variance_noise(C.dev(Ku), C.dev(F), C.dev(E), L, N).cpu().numpy()
+    assert_close(Kc, _dense_K(X, ls, F, E), what='apply_variance_noise')
+
+
+def test_gram_variant_batch_matches_gpflow_form(C):
+    """Variant path: per-output gpflow kernels.RBF.  The device uses the difference form of r^2, gpflow the expanded
+    -2XX^T+|x|^2+|x'|^2 form; they agree to rounding of r^2 (|dK| <~ 1e-15 here)."""
+    X, Y, ls, F, E = random_problem(90, 4, 3, seed=3, full_E=False)
+    var, noise = np.diag(F).copy(), np.diag(E).copy()
+    K = C.gram(C.dev(X), None, C.dev(ls), C.dev(var.reshape(3, 1, 1)), C.dev(noise.reshape(3, 1, 1)), batch=3)[:, :90, :90].cpu().numpy()
+    for l in range(3):
+        ref = gp.gram_rbf(X, None, ls[l], var[l])
+        ref[np.diag_indices(90)] += noise[l]
+        assert_close(K[l], ref, what=f'variant K[{l}]')
+
+
+# ---- factorisation ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', [5, 128, 200, 384, 700])
+def test_potrf_solves_and_inverse(C, n):
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(n, n))
+    K = A @ A.T / n + np.eye(n)
+    Kp = C.pad_identity(C.dev(K))
+    fac = C.Factorization(Kp)
+    fac.raise_if_failed()
+    Lc = np.linalg.cholesky(K)
+    assert_close(fac.lower(n)[0].cpu().numpy(), Lc, rtol=1e-8, atol=1e-10, what='L')
+    assert_close(fac.logdet_half().cpu().numpy()[0], np.log(np.diag(Lc)).sum(), what='sum log L_ii')
+    y = rng.normal(size=n)
+    yp = torch.zeros((1, fac.n_pad), dtype=torch.float64, device='cuda')
+    yp[0, :n] = C.dev(y)
+    a = fac.trsv(yp)
+    assert_close(a[0, :n].cpu().numpy(), np.linalg.solve(Lc, y), rtol=1e-8, atol=1e-10, what='L^-1 y')
+    assert_close(fac.trsv(a, transpose=True)[0, :n].cpu().numpy(), np.linalg.solve(K, y), rtol=1e-8, atol=1e-10, what='K^-1 y')
+    B = rng.normal(size=(n, 37))
+    Bp = torch.zeros((1, fac.n_pad, C.padded(37)), dtype=torch.float64, device='cuda')
+    Bp[0, :n, :37] = C.dev(B)
+    fac.trsm_fwd_(Bp)
+    assert_close(Bp[0, :n, :37].cpu().numpy(), np.linalg.solve(Lc, B), rtol=1e-8, atol=1e-10, what='L^-1 B')
+    Kinv = C.extract_lower(fac.inverse_(), n, symmetrize=True)[0].cpu().numpy()
+    assert_close(Kinv, np.linalg.inv(K), rtol=1e-8, atol=1e-10, what='K^-1')
+
+
+def test_potrf_batched(C):
+    rng = np.random.default_rng(0)
+    Ks = []
+    for z in range(3):
+        A = rng.normal(size=(150, 150))
+        Ks.append(A @ A.T / 150 + (z + 1) * np.eye(150))
+    fac = C.Factorization(C.pad_identity(C.dev(np.stack(Ks))))
+    fac.raise_if_failed()
+    Ls = fac.lower(150).cpu().numpy()
+    for z in range(3):
+        assert_close(Ls[z], np.linalg.cholesky(Ks[z]), what=f'L[{z}]')
+    Kinv = C.extract_lower(fac.inverse_(), 150, symmetrize=True).cpu().numpy()
+    for z in range(3):
+        assert_close(Kinv[z], np.linalg.inv(Ks[z]), what=f'Kinv[{z}]')
+
+
+def test_potrf_reports_first_bad_pivot(C):
+    """A matrix that is not positive definite: the reference raises tf InvalidArgumentError; here info = 1-based pivot index."""
+    K = np.eye(300)
+    K[200, 200] = -1.0
+    fac = C.Factorization(C.pad_identity(C.dev(K)))
+    assert int(fac.info.cpu()[0]) == 201
+    with pytest.raises(C.RomcommaB200Error):
+        fac.raise_if_failed()
+
+
+# ---- LML + gradient ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('N,M,L,full_F', [(50, 3, 2, True), (200, 5, 3, False), (300, 4, 1, False), (33, 2, 4, True), (129, 8, 2, False)])
+def test_lml_grad_covariant(C, N, M, L, full_F):
+    X, Y, ls, F, E = random_problem(N, M, L, seed=N + 1, full_F=full_F)
+    plan = C.LmlGradPlan(C.dev(X), C.dev(Y), L, 1, C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES)
+    res = plan.unpack(plan(C.dev(ls), C.dev(F[None]), C.dev(E[None])).cpu().numpy())[0]
+    assert plan.info.cpu().tolist() == [0]
+    ref = gp.lml_grad_mo(X, Y, ls, F, E)
+    assert_close(res['lml'], ref['lml'], what='lml')
+    # gradients are sums of O(n^2) terms of either sign: atol is scaled to the size of the terms (1e-10 * n)
+    for k in ('dF', 'dE', 'dls'):
+        assert_close(res[k], ref[k], atol=1e-10 * L * N, what=k)
+    # value-only call, and the cached-unit-gram branch
+    plan0 = C.LmlGradPlan(C.dev(X), C.dev(Y), L, 1, C.RC_GRAD_NONE)
+    Ku = C.gram(C.dev(X), None, C.dev(ls), None, None)[0, :L * N, :L * N].contiguous()
+    v0 = plan0(C.dev(ls), C.dev(F[None]), C.dev(E[None])).cpu().numpy()[0, 0]
+    v1 = plan0(C.dev(ls), C.dev(F[None]), C.dev(E[None]), Ku).cpu().numpy()[0, 0]
+    assert_close(v0, ref['lml'], what='lml (value only)')
+    assert_close(v1, ref['lml'], what='lml (cached K_unit)')
+
+
+def test_lml_grad_variant_batch(C):
+    X, Y, ls, F, E = random_problem(180, 6, 3, seed=21, full_E=False)
+    var, noise = np.diag(F).copy(), np.diag(E).copy()
+    plan = C.LmlGradPlan(C.dev(X), C.dev(Y), 1, 3, C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES)
+    res = plan.unpack(plan(C.dev(ls), C.dev(var.reshape(3, 1, 1)), C.dev(noise.reshape(3, 1, 1))).cpu().numpy())
+    for l in range(3):
+        ref = gp.lml_grad_rbf(X, Y[:, l], ls[l], var[l], noise[l])
+        assert_close(res[l]['lml'], ref['lml'], what=f'lml[{l}]')
+        assert_close(res[l]['dF'][0, 0], ref['dvariance'], atol=1e-8, what=f'dvariance[{l}]')
+        assert_close(res[l]['dE'][0, 0], ref['dnoise'], atol=1e-8, what=f'dnoise[{l}]')
+        assert_close(res[l]['dls'][0], ref['dls'], atol=1e-8, what=f'dls[{l}]')
+
+
+def test_lml_grad_golden(C, golden):
+    for name, g in golden.items():
+        X, Y, ls, F, E = g['X'], g['Y'], g['ls'], g['F'], g['E']
+        L = Y.shape[1]
+        plan = C.LmlGradPlan(C.dev(X), C.dev(Y), L, 1, C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES)
+        res = plan.unpack(plan(C.dev(ls), C.dev(F[None]), C.dev(E[None])).cpu().numpy())[0]
+        assert_close(res['lml'], g['lml'], what=f'{name} lml')
+        scale = 1e-10 * max(1.0, np.abs(g['dF']).max(), np.abs(g['dE']).max())
+        assert_close(res['dF'], np.tril(g['dF']) + np.tril(g['dF'], -1).T, rtol=1e-7, atol=max(1e-9, scale), what=f'{name} dF')
+        assert_close(res['dE'], np.tril(g['dE']) + np.tril(g['dE'], -1).T, rtol=1e-7, atol=max(1e-9, scale), what=f'{name} dE')
+        assert_close(res['dls'], g['dls'], rtol=1e-7, atol=max(1e-9, 1e-10 * np.abs(g['dls']).max()), what=f'{name} dls')
+
+
+def test_lml_not_positive_definite_sets_info(C):
+    X, Y, ls, F, E = random_problem(60, 2, 2, seed=2)
+    plan = C.LmlGradPlan(C.dev(X), C.dev(Y), 2, 1, C.RC_GRAD_NONE)
+    plan(C.dev(ls), C.dev(-F[None]), C.dev(E[None]))
+    assert int(plan.info.cpu()[0]) > 0
+
+
+# ---- Sobol ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('N,M,L,full_F', [(50, 3, 2, True), (200, 5, 3, False), (64, 4, 1, False), (65, 2, 2, True), (10, 6, 2, False)])
+def test_sobol_matches_oracle(C, N, M, L, full_F):
+    X, Y, ls, F, E = random_problem(N, M, L, seed=N + 5, full_F=full_F, full_E=False)
+    KiY = gp.k_inv_y_mo(X, Y, ls, F, E)
+    dX, dls = C.dev(X), C.dev(ls)
+    for diag in (True, False):
+        cal = sobol.ClosedSobol(X, ls, F, KiY, diag)
+        Fin = np.diag(F).copy() if diag else F
+        Phi, g0, g0KY = C.sobol_prepare(dX, dls, C.dev(Fin), C.dev(KiY.reshape(L, N)), diag)
+        assert_close(Phi.cpu().numpy().reshape(cal.Phi.shape), cal.Phi, what='Phi')
+        assert_close(g0.cpu().numpy().reshape(cal.g0.shape), cal.g0, what='g0')
+        assert_close(g0KY.cpu().numpy().reshape(cal.g0KY.shape), cal.g0KY, what='g0KY')
+        slices = [(0, M), (0, 1), (M - 1, M), (0, 2), (1, M), (M, M)] + [(m, m + 1) for m in range(M)]
+        V = C.sobol_contract(dX, Phi, g0KY, L, diag, [C.slice_mask(*s) for s in slices]).cpu().numpy()
+        for i, s in enumerate(slices):
+            assert_close(V[i], cal._V(*s), what=f'V{s} diag={diag}')
+        assert_close(V[i], V[i].T, atol=1e-14, what='V symmetric')
+
+
+def test_sobol_noncontiguous_subsets_and_long_lists(C):
+    """Arbitrary subsets (bit masks) and more than 64 subsets per call (chunked launches)."""
+    X, Y, ls, F, E = random_problem(70, 7, 2, seed=8, full_E=False)
+    KiY = gp.k_inv_y_mo(X, Y, ls, F, E)
+    Phi, g0, g0KY = C.sobol_prepare(C.dev(X), C.dev(ls), C.dev(np.diag(F).copy()), C.dev(KiY.reshape(2, 70)), True)
+    masks = list(range(1, 128))                     # all 127 non-empty subsets of 7 inputs
+    V = C.sobol_contract(C.dev(X), Phi, g0KY, 2, True, masks).cpu().numpy()
+    for mask in (0b0000101, 0b1010010, 0b1111111, 0b0100000):
+        subset = [m for m in range(7) if (mask >> m) & 1]
+        assert_close(V[mask - 1], sobol.subset_V(X, ls, F, KiY, subset)['V'], what=f'subset {subset}')
+
+
+def test_sobol_golden(C, golden):
+    for name, g in golden.items():
+        if 'V_diag' not in g:
+            continue
+        X, ls, F, KiY = g['X'], g['ls'], g['F'], g['KiY']
+        L, N = KiY.shape[0], X.shape[0]
+        for tag, diag in (('diag', True), ('full', False)):
+            Fin = np.diag(F).copy() if diag else F
+            Phi, g0, g0KY = C.sobol_prepare(C.dev(X), C.dev(ls), C.dev(Fin), C.dev(KiY.reshape(L, N)), diag)
+            V = C.sobol_contract(C.dev(X), Phi, g0KY, L, diag, [C.slice_mask(int(a), int(b)) for a, b in g['slices']]).cpu().numpy()
+            assert_close(V, g[f'V_{tag}'], what=f'{name} V {tag}')
+
+
+# ---- properties at benchmark scale (oracle too slow / too large there) ---------------------------------------------------
+def test_full_size_properties_cfg3(C):
+    """n = 16384 (cfg3): K K^-1 v = v, L L^T v = K v, symmetric V, bitwise run-to-run reproducibility."""
+    from romcomma import synthetic
+    w = synthetic.config('cfg3')
+    N, M, L = 4096, 8, 4
+    n = N * L
+    dX, dY, dls, dF, dE = C.dev(w.X), C.dev(w.Y), C.dev(w.lengthscales), C.dev(w.F[None]), C.dev(w.E[None])
+    K = C.gram(dX, None, dls, dF, dE)[0]
+    assert_close((K - K.T).abs().max().item(), 0.0, atol=0.0, what='gram exactly symmetric')
+    fac = C.Factorization(C.gram(dX, None, dls, dF, dE, pad_to=n, pad_identity=True, lower_only=True))
+    fac.raise_if_failed()
+    v = torch.randn(1, n, dtype=torch.float64, device='cuda', generator=torch.Generator('cuda').manual_seed(0))
+    x = fac.trsv(fac.trsv(v), transpose=True)                         # K^-1 v
+    resid = (K @ x[0] - v[0]).abs().max().item()
+    assert resid < 1e-9, resid
+    Lc = fac.lower(n)[0]
+    assert ((Lc @ (Lc.T @ v[0])) - K @ v[0]).abs().max().item() < 1e-9
+    Kinv = C.extract_lower(fac.inverse_(), n, symmetrize=True)[0]
+    assert ((Kinv @ v[0]) - x[0]).abs().max().item() < 1e-8 * x.abs().max().item()
+    plan = C.LmlGradPlan(dX, dY, L, 1, C.RC_GRAD_VARIANCE)
+    a = plan(dls, dF, dE).clone()
+    b = plan(dls, dF, dE).clone()
+    assert torch.equal(a, b), 'LML+grad is not bitwise reproducible'
+    logdet = Lc.diagonal().log().sum().item()
+    alpha = fac  # noqa: F841  (factor has been overwritten by its inverse; recompute the quadratic form from K^-1 v identity instead)
+    y = dY.T.reshape(-1)
+    quad = (y @ (Kinv @ y)).item()
+    assert_close(a[0, 0].item(), -0.5 * quad - 0.5 * n * np.log(2 * np.pi) - logdet, rtol=1e-10, what='LML identity')
+    # gradient identity: dLML/dE[l,l] = 1/2 (|a_l|^2 - tr Kinv_ll)
+    ky = Kinv @ y
+    for l in range(L):
+        ref = 0.5 * ((ky[l * N:(l + 1) * N] ** 2).sum() - Kinv[l * N:(l + 1) * N, l * N:(l + 1) * N].diagonal().sum()).item()
+        assert_close(a[0, 1 + L * L + l * L + l].item(), ref, rtol=1e-8, atol=1e-6, what=f'dE[{l},{l}]')

@@ -1,0 +1,220 @@
+"""CPU: host-side logic of the drop-in API - parameter transforms, Variance chain rule, optimizer packing order, storage layout,
+test functions, synthetic workloads, slice lists, and the world_size-2 sharding/gather helpers on gloo."""
+import json
+import os
+import random
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import assert_close, ROOT
+from oracle import gp as ogp, sobol as osobol
+
+
+def test_transforms_match_oracle():
+    from romcomma import gf_compat as gf
+    u = np.linspace(-30, 30, 13)
+    t = gf.positive(lower=1e-3)
+    assert_close(t.forward(u), ogp.softplus(u) + 1e-3)
+    v = u[u > -6]                                 # below that softplus(u) << the 1e-3 shift and the round trip is ill-conditioned
+    assert_close(t.inverse(t.forward(v)), v, rtol=1e-9, atol=1e-9)
+    assert_close(t.dforward(u), ogp.sigmoid(u))
+    p = gf.Parameter([0.5, 2.0], transform=gf.positive())
+    assert_close(p.numpy(), [0.5, 2.0])
+    with pytest.raises(ValueError):
+        gf.Parameter([0.0], transform=gf.positive())
+
+
+def test_variance_parametrisation_and_chain_rule():
+    from romcomma.gpf.base import Variance
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(3, 3))
+    V = A @ A.T + np.eye(3)
+    var = Variance(V)
+    assert var.shape == (3, 3)
+    assert_close(var.value.numpy(), V, rtol=1e-12)
+    assert_close(var.cholesky.numpy(), np.linalg.cholesky(V), rtol=1e-12)
+    assert var.value_to_broadcast.shape == (3, 1, 3, 1)
+    u, low = ogp.variance_pack(V)
+    assert_close(var._cholesky_diagonal.unconstrained_variable, u, rtol=1e-12)
+    assert_close(var._cholesky_lower_triangle.numpy(), low, rtol=1e-12)       # row-major strict lower triangle (base.py:93 mask)
+    dV = rng.normal(size=(3, 3))
+    gd, gl = var._chain(dV)
+    rd, rl = ogp.chain_variance(dV, u, low)
+    assert_close(gd, rd)
+    assert_close(gl, rl)
+    with pytest.raises(ValueError):
+        Variance(np.diag([1e-7, 1.0]))          # Cholesky diagonal below the 1e-3 bound (base.py:88-89)
+    with pytest.raises(ValueError):
+        Variance(np.ones((2, 3)))
+
+
+def test_trainable_variable_order_follows_tf_module():
+    """tf.Module flattens attributes in sorted-name order: kernel.lengthscales, kernel.variance.{_cholesky_diagonal,_cholesky_lower_triangle},
+    likelihood.variance.{...}; the variant model gives kernel.lengthscales, kernel.variance, likelihood.variance."""
+    from romcomma import gf_compat as gf
+    from romcomma.gpf.kernels import RBF
+
+    class Holder(gf.Module):
+        def __init__(self):
+            super().__init__()
+            self.kernel = RBF(np.eye(2) * 0.5, np.ones((2, 3)))
+            self.likelihood = gf.Module('lik')
+            self.likelihood.variance = __import__('romcomma.gpf.base', fromlist=['Variance']).Variance(np.eye(2) * 0.1)
+    h = Holder()
+    assert [p.name for p in h.trainable_variables] == ['KernelVariance.cholesky_diagonal', 'KernelVariance.cholesky_lower_triangle',
+                                                       'Variance.cholesky_diagonal', 'Variance.cholesky_lower_triangle']
+    gf.set_trainable(h.kernel.lengthscales, True)
+    assert h.trainable_variables[0].name == 'KernelLengthscales'
+    k = gf.kernels.RBF(variance=2.0, lengthscales=[1.0, 2.0])
+    assert [p.name for p in k.trainable_variables] == ['lengthscales', 'variance']
+
+
+def test_kernel_lengthscale_broadcast_shapes():
+    from romcomma.gpf.kernels import RBF
+    k = RBF(np.eye(2), 0.7)
+    assert (k.L, k.M) == (2, 1) and k.lengthscales.shape == (2, 1, 1) and not k.lengthscales.trainable
+    k = RBF(np.eye(2), [[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])
+    assert (k.L, k.M) == (2, 3)
+    assert_close(k.lengthscales_neat.numpy(), [[1, 2, 3], [4, 5, 6]])
+
+
+def test_test_functions_closed_forms():
+    from romcomma.user import functions
+    U = np.random.default_rng(0).random((11, 7))
+    x = -np.pi + 2 * np.pi * U[:, :3]
+    assert_close(functions.ISHIGAMI['standard'](U)[:, 0], np.sin(x[:, 0]) + 7 * np.sin(x[:, 1]) ** 2 + 0.1 * x[:, 2] ** 4 * np.sin(x[:, 0]))
+    a = np.array([3, 6, 9, 18, 27.0])
+    assert_close(functions.SOBOL_G['weak5_2'](U)[:, 0], np.prod((3 * np.abs(2 * U[:, :5] - 1) ** 2 + a) / (1 + a), axis=1))
+    z = -1 + 2 * U
+    assert_close(functions.OAKLEY2004['lin7'](U)[:, 0], z @ np.linspace(7, 3.5, 7))
+    assert functions.ALL(U).shape == (11, 9)
+
+
+def test_slice_lists_and_masks():
+    from romcomma import _capi
+    assert _capi.slice_mask(0, 3) == 0b111 and _capi.slice_mask(2, 3) == 0b100 and _capi.slice_mask(3, 3) == 0 and _capi.slice_mask(1, 4) == 0b1110
+    assert osobol.m_slices(osobol.FIRST_ORDER, 3) == [(0, 1), (1, 2), (2, 3)]
+    assert osobol.m_slices(osobol.CLOSED, 3) == [(0, 1), (0, 2), (0, 3)]
+    assert osobol.m_slices(osobol.TOTAL, 3) == [(1, 3), (2, 3), (3, 3)]
+
+
+def test_synthetic_workloads_are_deterministic_and_normalised():
+    from romcomma import synthetic
+    a, b = synthetic.config('cfg3', N=200), synthetic.config('cfg3', N=200)
+    assert np.array_equal(a.X, b.X) and np.array_equal(a.Y, b.Y) and np.array_equal(a.lengthscales, b.lengthscales)
+    assert a.X.shape == (200, 8) and a.Y.shape == (200, 4) and a.F.shape == (4, 4)
+    assert_close(a.Y.mean(0), np.zeros(4), atol=1e-12)
+    assert_close(a.Y.std(0, ddof=1), np.ones(4), rtol=1e-12)
+    assert np.abs(a.X).max() < 7.1 and abs(a.X.mean()) < 1e-8
+    assert ogp.lml_mo(a.X, a.Y, a.lengthscales, a.F, a.E) < 0
+
+
+def test_repository_fold_layout_and_normalisation(tmp_path):
+    from romcomma.data.storage import Repository, Fold, Normalization
+    from romcomma.user import functions, sample
+    np.random.seed(0)
+    random.seed(3)
+    fn = sample.Function(tmp_path, sample.DOE.latin_hypercube, functions.ISHIGAMI.subVector('ish', ['standard', 'sin']), N=40, M=3,
+                         noise_variance=sample.GaussianNoise.Variance(2, 0.04, False, False), overwrite_existing=True)
+    repo = fn.repo
+    assert repo.folder.name == 'ish.M.3.u.v.4.00.N.40' and (repo.N, repo.M, repo.L) == (40, 3, 2)
+    repo.into_K_folds(4)
+    assert list(repo.folds) == [0, 1, 2, 3, 4] and repo.meta['has_improper_fold'] and repo.K == 4
+    for k in repo.folds:
+        folder = repo.fold_folder(k)
+        for f in ('data.csv', 'test.csv', 'meta.json', 'normalization.csv'):
+            assert (folder / f).exists(), (k, f)
+    fold = Fold(repo, 1)
+    assert (fold.N, fold.M, fold.L) == (30, 3, 2) and fold.meta['k'] == 1 and fold.test_x.shape == (10, 3)
+    improper = Fold(repo, 4)
+    assert improper.N == 40 and improper.test_data.df.shape[0] == 40
+    # normalization.csv: rows mean,std,rng,min,max computed on ALL data and copied into every fold (storage.py:187,432-433)
+    norm = pd.read_csv(repo.folder / 'normalization.csv', header=[0, 1], index_col=0)
+    assert list(norm.index) == ['mean', 'std', 'rng', 'min', 'max']
+    assert_close(norm.loc['rng'].values, 2 * np.sqrt(3) * norm.loc['std'].values, rtol=1e-12)
+    assert (repo.fold_folder(0) / 'normalization.csv').read_text() == (repo.folder / 'normalization.csv').read_text()
+    # the improper fold is normalised with statistics of all rows: X ~ N(0,1)-ish, Y standardised
+    assert_close(improper.Y.values.mean(0), np.zeros(2), atol=1e-12)
+    assert_close(improper.Y.values.std(0, ddof=1), np.ones(2), rtol=1e-10)
+    raw = repo.data.df
+    back = improper.normalization.undo_from(improper.data.df)
+    assert_close(back.values, raw.values, rtol=1e-8, atol=1e-8)
+    meta = json.loads((repo.folder / 'meta.json').read_text())
+    assert meta['K'] == 4 and meta['data'] == {'X_heading': 'X', 'Y_heading': 'Y', 'N': 40, 'M': 3, 'L': 2}
+
+
+def test_model_data_frames_roundtrip(tmp_path):
+    from romcomma.gpr.kernels import Kernel, RBF
+    data = RBF.Data(tmp_path / 'kernel', variance=np.array([[1.0, 2.0]]), lengthscales=np.array([[0.5]]))
+    assert (tmp_path / 'kernel' / 'variance.csv').exists() and (tmp_path / 'kernel' / 'lengthscales.csv').exists()
+    again = RBF.Data.read(tmp_path / 'kernel')
+    assert_close(again.frames.variance.np, [[1.0, 2.0]])
+    again.frames.lengthscales.broadcast_value((2, 3), is_diagonal=False)
+    assert again.frames.lengthscales.np.shape == (2, 3)
+    again.frames.variance.broadcast_value((2, 2), is_diagonal=True)
+    assert_close(again.frames.variance.np, [[1.0, 0.0], [0.0, 2.0]])
+    with pytest.raises(IndexError):
+        again.frames.variance.broadcast_value((1, 3))
+    assert RBF.TYPE_IDENTIFIER == 'kernels.RBF' and Kernel.TypeFromIdentifier('kernels.RBF') is RBF
+    assert Kernel.META == {'variance': True, 'covariance': False, 'lengthscales': {'variant': True, 'covariant': False}}
+
+
+def test_gsa_columns_index_and_post_processing():
+    from romcomma.gsa.models import GSA, Sobol
+    assert list(GSA._columns(3, 4, [0, 1, 2])) == [0, 1, 2, 3]
+    assert list(GSA._index([2, 2, 4]).names) == ['l.0', 'l.1'] and len(GSA._index([2, 2, 4])) == 4
+    assert [k.name for k in GSA.ALL_KINDS] == ['FIRST_ORDER', 'CLOSED', 'TOTAL'] and int(GSA.Kind.FIRST_ORDER) == 1
+    assert Sobol.META == {'is_T_partial': True}
+
+    class Cal:
+        V = {0: np.full((2, 2), 4.0)}
+        S = np.full((2, 2), 0.9)
+    fake = Sobol.__new__(Sobol)
+    fake.kind = GSA.Kind.TOTAL
+    out = fake._post_calibrate(Cal, {'V': np.ones((2, 2, 3)), 'S': np.full((2, 2, 3), 0.25)})
+    assert out['V'].shape == (2, 2, 4) and np.all(out['V'][..., -1] == 4.0)
+    assert_close(out['S'][..., :3], np.full((2, 2, 3), 0.65))
+    assert_close(out['S'][..., 3], np.full((2, 2), 0.9))
+
+
+def test_shard_round_robin():
+    from romcomma import distributed
+    items = list(range(11))
+    shards = [distributed.shard(items, r, 4) for r in range(4)]
+    assert sorted(sum(shards, [])) == items and shards[1] == [1, 5, 9]
+    assert distributed.shard(items) == items and distributed.world_size() == 1
+
+
+WORKER = textwrap.dedent('''
+    import sys, numpy as np
+    sys.path.insert(0, sys.argv[1])
+    from romcomma import distributed
+    distributed.init_from_env('gloo')
+    r, w = distributed.rank(), distributed.world_size()
+    assert w == 2
+    total = 7
+    rows = distributed.shard(list(range(total)))
+    local = np.array([[10.0 * i, i + 0.5] for i in rows])
+    full = distributed.all_gather_rows(local, total)
+    assert full.shape == (7, 2) and np.array_equal(full[:, 0], 10.0 * np.arange(7)), full
+    assert distributed.all_reduce_max(float(r)) == 1.0 and distributed.all_reduce_sum(1.0) == 2.0
+    distributed.barrier()
+    print('rank', r, 'ok')
+''')
+
+
+def test_world_size_2_gloo_gather(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29531', WORLD_SIZE='2', OMP_NUM_THREADS='1')
+    procs = [subprocess.Popen([sys.executable, str(script), str(ROOT / 'rom-comma_b200')], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert 'rank 0 ok' in outs[0] and 'rank 1 ok' in outs[1]
