@@ -200,7 +200,7 @@ def run_b200(args):
     ls = w.lengthscales if rank == 0 else rng.uniform(0.5, 3.0, (L, M))
     Fm = w.F if rank == 0 else np.diag(rng.uniform(0.5, 2.0, L))
     dX, dY, dls, dF, dE = C.dev(w.X), C.dev(w.Y), C.dev(ls), C.dev(Fm[None]), C.dev(w.E[None])
-    plan = C.LmlGradPlan(dX, dY, L, 1, C.RC_GRAD_VARIANCE)
+    plan = C.LmlGradPlan(dX, dY, L, 1, C.RC_GRAD_VARIANCE | C.RC_GRAD_F_DIAGONAL)
 
     def sync_all():
         distributed.barrier()

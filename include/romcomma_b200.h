@@ -91,6 +91,10 @@ int rc_extract_lower(const double* src, long ld, long stride_src, double* dst, i
 #define RC_GRAD_NONE 0
 #define RC_GRAD_VARIANCE 1
 #define RC_GRAD_LENGTHSCALES 2
+/* Hint: dF is only wanted on its diagonal (kernel 'covariance' not trainable, romcomma/gpr/kernels.py:54-57 default).  Without
+ * RC_GRAD_LENGTHSCALES and for L > 1, batch == 1 this lets K^-1 be formed on the diagonal (l,l) blocks only ("selected" LAUUM);
+ * the off-diagonal entries of dF are then returned as zero.  dE is always complete. */
+#define RC_GRAD_F_DIAGONAL 4
 int rc_lml_grad_stride(int L, int M);
 size_t rc_lml_grad_bufsize(int N, int M, int L, int batch, int flags);
 int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch, const double* ls, const double* F, const double* E,

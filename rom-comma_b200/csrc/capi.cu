@@ -71,6 +71,19 @@ __global__ void lml_finalize_kernel(const double* __restrict__ logdet, const dou
     o[e] = v;
   }
 }
+
+// SE[l][l'] (l > l') = sum_i (a[l*N+i] a[l'*N+i] - Kinv[(l,i),(l',i)]),  a = K^-1 y, dots[pair][i] = Kinv[(l,i),(l',i)]
+__global__ void offdiag_noise_sums_kernel(const double* __restrict__ a, const double* __restrict__ dots, int N, int L, double* __restrict__ SE) {
+  __shared__ double red[32];
+  const int pair = blockIdx.x;
+  int l = 1;
+  while ((l + 1) * l / 2 <= pair) ++l;
+  const int lp = pair - l * (l - 1) / 2;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += a[(long)l * N + i] * a[(long)lp * N + i] - dots[(long)pair * N + i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) SE[l * L + lp] = s;
+}
 }  // namespace rc
 
 using namespace rc;
@@ -133,7 +146,7 @@ int rc_potri(double* A, int n_pad, long ld, long strideA, int batch, const void*
   PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, batch);
   int rc = trtri_lower(A, n_pad, ld, strideA, batch, w.dinv, Kinv, strideK, (cudaStream_t)stream);
   if (rc) return rc;
-  return lauum_lower(A, n_pad, ld, strideA, batch, Kinv, ldk, strideK, (cudaStream_t)stream);
+  return lauum_lower(A, n_pad, ld, strideA, batch, Kinv, ldk, strideK, 0, (cudaStream_t)stream);
 }
 
 int rc_pad_identity(const double* src, int n, long stride_src, double* dst, int n_pad, long ld, long stride_dst, int batch, rc_stream_t stream) {
@@ -148,8 +161,13 @@ int rc_extract_lower(const double* src, long ld, long stride_src, double* dst, i
 int rc_lml_grad_stride(int L, int M) { return 1 + 2 * L * L + L * M; }
 
 namespace {
+// "Selected inversion": when dF is only wanted on its diagonal and no lengthscale gradient is requested, the gradient needs just
+// the diagonal (l,l) blocks of K^-1 and the diagonals of its off-diagonal blocks, so LAUUM is restricted to those tiles.
+bool lml_selected(int L, int batch, int flags) {
+  return (flags & RC_GRAD_F_DIAGONAL) && (flags & RC_GRAD_VARIANCE) && !(flags & RC_GRAD_LENGTHSCALES) && L > 1 && batch == 1;
+}
 struct LmlLayout {
-  size_t A, Kinv, potrf, vec, scal, gparts, graw, total;
+  size_t A, Kinv, potrf, vec, scal, gparts, graw, dots, total;
   int n_pad;
 };
 LmlLayout lml_layout(int N, int M, int L, int batch, int flags) {
@@ -164,6 +182,7 @@ LmlLayout lml_layout(int N, int M, int L, int batch, int flags) {
   o.scal = off; off += align256((size_t)2 * batch * sizeof(double));
   o.gparts = off; off += (flags != RC_GRAD_NONE) ? align256(grad_workspace_bytes(o.n_pad, L, M, batch)) : 0;
   o.graw = off; off += align256((size_t)batch * grad_nvals(L, M) * sizeof(double));
+  o.dots = off; off += lml_selected(L, batch, flags) ? align256(block_diag_dots_workspace_bytes(N, L) + (size_t)(L * (L - 1) / 2) * N * sizeof(double)) : 0;
   o.total = off;
   return o;
 }
@@ -218,13 +237,22 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
     RC_CUDA_OK(cudaMemcpyAsync(wv, alpha, (size_t)batch * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if ((rc = trsv_lower(A, n_pad, n_pad, mat, batch, pw.dinv, wv, kinvy, n_pad, 1, st))) return rc;
     if ((rc = trtri_lower(A, n_pad, n_pad, mat, batch, pw.dinv, Kinv, mat, st))) return rc;
-    if ((rc = lauum_lower(A, n_pad, n_pad, mat, batch, Kinv, n_pad, mat, st))) return rc;
+    const bool selected = lml_selected(L, batch, flags);
+    if ((rc = lauum_lower(A, n_pad, n_pad, mat, batch, Kinv, n_pad, mat, selected ? N : 0, st))) return rc;
     // 5. contractions
     GradArgs ga{};
     ga.X = X; ga.N = N; ga.M = M; ga.L = L; ga.ls = ls; ga.stride_ls = (long)L * M; ga.F = F; ga.stride_FE = (long)L * L;
     ga.Kinv = Kinv; ga.ldk = n_pad; ga.stride_K = mat; ga.alpha = kinvy; ga.stride_alpha = n_pad; ga.parts = gparts;
     ga.with_ls = (flags & RC_GRAD_LENGTHSCALES) ? 1 : 0;
+    ga.diag_blocks_only = selected ? 1 : 0;
     if ((rc = grad_reduce(ga, n_pad, batch, graw, st))) return rc;
+    if (selected) {   // dE off-diagonal entries from the diagonals of the off-diagonal blocks of K^-1 = Z^T Z (A holds Z = L^-1 now)
+      double* dparts = reinterpret_cast<double*>(base + lay.dots);
+      double* dots = dparts + block_diag_dots_workspace_bytes(N, L) / sizeof(double);
+      if ((rc = block_diag_dots(A, n_pad, n_pad, N, L, dparts, dots, st))) return rc;
+      offdiag_noise_sums_kernel<<<L * (L - 1) / 2, 256, 0, st>>>(kinvy, dots, N, L, graw + (size_t)L * L);
+      RC_LAUNCH_OK();
+    }
   }
   lml_finalize_kernel<<<batch, 128, 0, st>>>(logdet, quad, graw, L, M, n, flags, out);
   RC_LAUNCH_OK();

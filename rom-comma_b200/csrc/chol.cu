@@ -17,75 +17,197 @@ namespace rc {
 constexpr int DB = 128;
 constexpr int DB_LD = DB + 1;
 constexpr int DB_THREADS = 256;
-constexpr size_t DB_SMEM = (size_t)(DB * DB_LD + 2 * DB + 32) * sizeof(double);
+constexpr size_t DB_SMEM = (size_t)(DB * DB_LD + 5 * DB + 32) * sizeof(double);
+
+// One CTA per diagonal block, 16 x 16 threads; thread (ty,tx) owns the elements (ty + 16a, tx + 16b), a >= b, of the lower triangle in
+// REGISTERS.  Phase 1 is a right-looking rank-1 Cholesky with ONE barrier per column: every thread tracks the running diagonal of its
+// rows and columns redundantly, so the owners of column j+1 can scale and publish it (double-buffered `colbuf`) in the same step that
+// applies column j.  Phase 2 builds L^-1 the same way (apply E_j^-1 to the identity, one barrier per row, L read from shared memory).
+// The pivot loop is unrolled over the eight 16-column blocks (template parameter JB) so that every register index is static and the
+// blocks that are already finished are skipped at compile time.
+struct DiagCtx {
+  double* colbuf; double* rowbuf; double* rinvs; const double* S;
+  int ty, tx; int* info; int info_base;
+};
+
+// publish column jn = 16*NB + (jn & 15):  colbuf[jn&1][r] = L[r][jn] (r > jn), 0 for the other rows of blocks >= NB
+template <int NB>
+__device__ __forceinline__ void diag_produce_col(double (&a)[8][8], const double (&dc)[8], const DiagCtx& c, int jn) {
+  if (c.tx != (jn & 15)) return;
+  const double d = dc[NB];
+  const double rinv = rsqrt(d);
+  double* cb = c.colbuf + (jn & 1) * DB;
+#pragma unroll
+  for (int ia = NB; ia < 8; ++ia) {
+    const int r = c.ty + 16 * ia;
+    double v = 0.0;
+    if (r > jn) {
+      v = a[ia][NB] * rinv;
+      a[ia][NB] = v;
+    } else if (ia == NB && r == jn) {
+      a[ia][NB] = d * rinv;       // L_jj = sqrt(d)
+      c.rinvs[jn] = rinv;
+      if (!(d > 0.0)) atomicCAS(c.info, 0, c.info_base + jn + 1);
+    }
+    cb[r] = v;
+  }
+}
+
+template <int JB>
+__device__ __forceinline__ void diag_potrf_block(double (&a)[8][8], double (&dr)[8], double (&dc)[8], const DiagCtx& c) {
+  for (int jj = 0; jj < 16; ++jj) {
+    const int j = 16 * JB + jj;
+    __syncthreads();
+    const double* cb = c.colbuf + (j & 1) * DB;
+    double lr[8], lc[8];
+#pragma unroll
+    for (int i = JB; i < 8; ++i) {
+      lr[i] = cb[c.ty + 16 * i];
+      lc[i] = cb[c.tx + 16 * i];
+      dr[i] = fma(-lr[i], lr[i], dr[i]);
+      dc[i] = fma(-lc[i], lc[i], dc[i]);
+    }
+    // the two column blocks that can hold the next pivot first, then publish it, then the rest
+#pragma unroll
+    for (int ib = JB; ib < 8 && ib <= JB + 1; ++ib)
+#pragma unroll
+      for (int ia = ib; ia < 8; ++ia) a[ia][ib] = fma(-lr[ia], lc[ib], a[ia][ib]);
+    if (jj < 15) diag_produce_col<JB>(a, dc, c, j + 1);
+    else if (JB < 7) diag_produce_col<(JB < 7 ? JB + 1 : 7)>(a, dc, c, j + 1);
+#pragma unroll
+    for (int ib = JB + 2; ib < 8; ++ib)
+#pragma unroll
+      for (int ia = ib; ia < 8; ++ia) a[ia][ib] = fma(-lr[ia], lc[ib], a[ia][ib]);
+  }
+}
+
+// publish row jn of Z:  rowbuf[jn&1][col] = Z[jn][col] / L_jj for col <= jn, 0 for the other columns of blocks <= AN
+template <int AN>
+__device__ __forceinline__ void diag_produce_row(double (&zz)[8][8], const DiagCtx& c, int jn) {
+  if (c.ty != (jn & 15)) return;
+  const double rinv = c.rinvs[jn];
+  double* rb = c.rowbuf + (jn & 1) * DB;
+#pragma unroll
+  for (int ib = 0; ib <= AN; ++ib) {
+    const int col = c.tx + 16 * ib;
+    double v = 0.0;
+    if (col <= jn) {
+      v = zz[AN][ib] * rinv;
+      zz[AN][ib] = v;
+    }
+    rb[col] = v;
+  }
+}
+
+template <int JB>
+__device__ __forceinline__ void diag_trtri_block(double (&zz)[8][8], const DiagCtx& c) {
+  for (int jj = 0; jj < 16; ++jj) {
+    const int j = 16 * JB + jj;
+    __syncthreads();
+    const double* rb = c.rowbuf + (j & 1) * DB;
+    double lr[8], zr[8];
+#pragma unroll
+    for (int i = JB; i < 8; ++i) {
+      const int r = c.ty + 16 * i;
+      lr[i] = (i > JB || c.ty > jj) ? c.S[r * DB_LD + j] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i <= JB; ++i) zr[i] = rb[c.tx + 16 * i];
+#pragma unroll
+    for (int ia = JB; ia < 8 && ia <= JB + 1; ++ia)
+#pragma unroll
+      for (int ib = 0; ib <= JB; ++ib) zz[ia][ib] = fma(-lr[ia], zr[ib], zz[ia][ib]);
+    if (jj < 15) diag_produce_row<JB>(zz, c, j + 1);
+    else if (JB < 7) diag_produce_row<(JB < 7 ? JB + 1 : 7)>(zz, c, j + 1);
+#pragma unroll
+    for (int ia = JB + 2; ia < 8; ++ia)
+#pragma unroll
+      for (int ib = 0; ib <= JB; ++ib) zz[ia][ib] = fma(-lr[ia], zr[ib], zz[ia][ib]);
+  }
+}
 
 __global__ void __launch_bounds__(DB_THREADS, 1)
 diag_potrf_inv_kernel(double* __restrict__ A, long ld, long strideA, double* __restrict__ dinv, long strideD, int blk,
                       double* __restrict__ logdet_parts, int nblk, int* __restrict__ info) {
   extern __shared__ __align__(16) double sm[];
-  double* S = sm;
-  double* part = sm + DB * DB_LD;      // [2][DB]
-  double* red = part + 2 * DB;
+  double* S = sm;                       // [128][129]  L, for phase 2
+  double* red = sm + DB * DB_LD + 5 * DB;
   const int tid = threadIdx.x, z = blockIdx.x;
+  DiagCtx c;
+  c.colbuf = sm + DB * DB_LD;           // [2][128]
+  c.rowbuf = c.colbuf + 2 * DB;         // [2][128]
+  c.rinvs = c.rowbuf + 2 * DB;          // [128]  1 / L_jj
+  c.S = S;
+  c.ty = tid >> 4;
+  c.tx = tid & 15;
+  c.info = info + z;
+  c.info_base = blk * DB;
+  const int ty = c.ty, tx = c.tx;
   double* Ab = A + (long)z * strideA + (long)blk * DB * (ld + 1);
   double* Db = dinv + (long)z * strideD + (long)blk * DB * DB;
 
-  for (int idx = tid; idx < DB * DB; idx += DB_THREADS) {
-    const int i = idx >> 7, j = idx & 127;
-    S[i * DB_LD + j] = (j <= i) ? Ab[(long)i * ld + j] : 0.0;
-  }
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int j = 0; j < DB; ++j) {
-    __syncthreads();
-    const double d = S[j * DB_LD + j];
-    if (!(d > 0.0)) {
-      if (tid == 0) atomicCAS(info + z, 0, blk * DB + j + 1);
-    }
-    const double ljj = sqrt(d);
-    const double rinv = 1.0 / ljj;
-    for (int i = j + 1 + tid; i < DB; i += DB_THREADS) S[i * DB_LD + j] *= rinv;
-    __syncthreads();
-    if (tid == 0) S[j * DB_LD + j] = ljj;
-    for (int i = j + 1 + ty; i < DB; i += 16) {
-      const double li = S[i * DB_LD + j];
-      for (int c = j + 1 + tx; c <= i; c += 16) S[i * DB_LD + c] -= li * S[c * DB_LD + j];
+  double a[8][8], dr[8], dc[8];
+#pragma unroll
+  for (int ia = 0; ia < 8; ++ia) {
+    const int r = ty + 16 * ia;
+    dr[ia] = Ab[(long)r * ld + r];
+    dc[ia] = Ab[(long)(tx + 16 * ia) * ld + tx + 16 * ia];
+#pragma unroll
+    for (int ib = 0; ib < 8; ++ib) {
+      const int col = tx + 16 * ib;
+      a[ia][ib] = (ib <= ia && col <= r) ? Ab[(long)r * ld + col] : 0.0;
     }
   }
-  __syncthreads();
-  for (int idx = tid; idx < DB * DB; idx += DB_THREADS) {
-    const int i = idx >> 7, j = idx & 127;
-    if (j <= i) Ab[(long)i * ld + j] = S[i * DB_LD + j];
-  }
-  {
-    double v = (tid < DB) ? log(S[tid * DB_LD + tid]) : 0.0;
-    v = block_sum(v, red);
-    if (tid == 0) logdet_parts[(long)z * nblk + blk] = v;
-  }
-  // In-place inverse, row by row: X[i][j] = -(1/L_ii) sum_{k<i} L[i][k] X[k][j]  (X upper triangle is zero, so k starts at 0).
-  const int j = tid & (DB - 1), half = tid >> 7;
-  for (int i = 0; i < DB; ++i) {
-    __syncthreads();
-    const int kmid = i >> 1;
-    const int kb = half ? kmid : 0, ke = half ? i : kmid;
-    double s0 = 0.0, s1 = 0.0;
-    int k = kb;
-    for (; k + 1 < ke; k += 2) {
-      s0 = fma(S[i * DB_LD + k], S[k * DB_LD + j], s0);
-      s1 = fma(S[i * DB_LD + k + 1], S[(k + 1) * DB_LD + j], s1);
-    }
-    if (k < ke) s0 = fma(S[i * DB_LD + k], S[k * DB_LD + j], s0);
-    part[half * DB + j] = s0 + s1;
-    const double inv_ii = 1.0 / S[i * DB_LD + i];
-    __syncthreads();
-    if (half == 0) {
-      if (j < i) S[i * DB_LD + j] = -(part[j] + part[DB + j]) * inv_ii;
-      else if (j == i) S[i * DB_LD + i] = inv_ii;
+  diag_produce_col<0>(a, dc, c, 0);
+  diag_potrf_block<0>(a, dr, dc, c);
+  diag_potrf_block<1>(a, dr, dc, c);
+  diag_potrf_block<2>(a, dr, dc, c);
+  diag_potrf_block<3>(a, dr, dc, c);
+  diag_potrf_block<4>(a, dr, dc, c);
+  diag_potrf_block<5>(a, dr, dc, c);
+  diag_potrf_block<6>(a, dr, dc, c);
+  diag_potrf_block<7>(a, dr, dc, c);
+
+  // L -> global (lower part) and shared memory; log-determinant part
+  double logsum = 0.0;
+#pragma unroll
+  for (int ia = 0; ia < 8; ++ia) {
+    const int r = ty + 16 * ia;
+#pragma unroll
+    for (int ib = 0; ib <= ia; ++ib) {
+      const int col = tx + 16 * ib;
+      if (col <= r) {
+        Ab[(long)r * ld + col] = a[ia][ib];
+        S[r * DB_LD + col] = a[ia][ib];
+        if (col == r) logsum += log(a[ia][ib]);
+      }
     }
   }
-  __syncthreads();
-  for (int idx = tid; idx < DB * DB; idx += DB_THREADS) {
-    const int i = idx >> 7, jj = idx & 127;
-    Db[idx] = (jj <= i) ? S[i * DB_LD + jj] : 0.0;
+  logsum = block_sum(logsum, red);               // contains the barriers that publish S and rinvs
+  if (tid == 0) logdet_parts[(long)z * nblk + blk] = logsum;
+
+  // Phase 2: Z = L^-1.  Start from the identity and apply E_j^-1 for j = 0..127: row j <- row j / L_jj, rows i > j -= L[i][j] * row j.
+#pragma unroll
+  for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+    for (int ib = 0; ib < 8; ++ib) a[ia][ib] = (ty + 16 * ia == tx + 16 * ib) ? 1.0 : 0.0;
+  diag_produce_row<0>(a, c, 0);
+  diag_trtri_block<0>(a, c);
+  diag_trtri_block<1>(a, c);
+  diag_trtri_block<2>(a, c);
+  diag_trtri_block<3>(a, c);
+  diag_trtri_block<4>(a, c);
+  diag_trtri_block<5>(a, c);
+  diag_trtri_block<6>(a, c);
+  diag_trtri_block<7>(a, c);
+#pragma unroll
+  for (int ia = 0; ia < 8; ++ia) {
+    const int r = ty + 16 * ia;
+#pragma unroll
+    for (int ib = 0; ib < 8; ++ib) {
+      const int col = tx + 16 * ib;
+      Db[r * DB + col] = (ib <= ia && col <= r) ? a[ia][ib] : 0.0;
+    }
   }
 }
 
@@ -324,13 +446,57 @@ int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double
 }
 
 // Kinv (lower tiles) = Z^T Z with Z = L^-1 lower (diagonal 128-blocks carry explicit zeros above the diagonal).
-int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double* Kinv, long ldk, long strideK, cudaStream_t st) {
+// sel_block > 0: only the tiles that intersect the diagonal blocks of that size (all the gradient of a diagonal F needs).
+int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double* Kinv, long ldk, long strideK, int sel_block, cudaStream_t st) {
   GemmArgs g{};
+  g.sel_block = sel_block;
   g.A = Z; g.lda = ld; g.strideA = strideZ;
   g.B = Z; g.ldb = ld; g.strideB = strideZ;
   g.C = Kinv; g.ldc = ldk; g.strideC = strideK;
   g.M = g.N = g.K = n; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 1; g.kmode = K_GE_M0;
   return launch_gemm<true, true>(g, batch, st);
+}
+
+// dots[pair(l > l')][i] = sum_{k >= l*N+i} Z[k][l*N+i] * Z[k][l'*N+i] = K^-1[(l,i),(l',i)]: the diagonals of the off-diagonal
+// (l,l') blocks of K^-1 = Z^T Z, which is all of those blocks that dLML/dE needs.  Row-split partial sums, fixed-order finish.
+constexpr int BD_SPLIT = 16;
+
+__global__ void __launch_bounds__(128) block_diag_dots_partial_kernel(const double* __restrict__ Z, long ld, int n, int N, int L, double* __restrict__ parts) {
+  const int pair = blockIdx.y, split = blockIdx.z;
+  int l = (int)((sqrt(8.0 * pair + 1.0) + 1.0) * 0.5);
+  while (l * (l - 1) / 2 > pair) --l;
+  while ((l + 1) * l / 2 <= pair) ++l;
+  const int lp = pair - l * (l - 1) / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const long c1 = (long)l * N + i, c2 = (long)lp * N + i;
+  // rows k in [l*N + chunk start, ...) restricted to k >= c1; the split is over the rows of the whole matrix
+  const long rows = (n + BD_SPLIT - 1) / BD_SPLIT;
+  const long k0 = max((long)split * rows, c1), k1 = min((long)n, (long)(split + 1) * rows);
+  double s = 0.0;
+  for (long k = k0; k < k1; ++k) s = fma(Z[k * ld + c1], Z[k * ld + c2], s);
+  parts[((long)pair * BD_SPLIT + split) * N + i] = s;
+}
+
+__global__ void block_diag_dots_finish_kernel(const double* __restrict__ parts, int N, double* __restrict__ dots) {
+  const int pair = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double s = 0.0;
+  for (int sp = 0; sp < BD_SPLIT; ++sp) s += parts[((long)pair * BD_SPLIT + sp) * N + i];
+  dots[(long)pair * N + i] = s;
+}
+
+size_t block_diag_dots_workspace_bytes(int N, int L) { return (size_t)(L * (L - 1) / 2) * BD_SPLIT * N * sizeof(double); }
+
+int block_diag_dots(const double* Z, long ld, int n, int N, int L, double* parts, double* dots, cudaStream_t st) {
+  const int pairs = L * (L - 1) / 2;
+  if (pairs == 0) return 0;
+  block_diag_dots_partial_kernel<<<dim3((N + 127) / 128, pairs, BD_SPLIT), 128, 0, st>>>(Z, ld, n, N, L, parts);
+  RC_LAUNCH_OK();
+  block_diag_dots_finish_kernel<<<dim3((N + 127) / 128, pairs), 128, 0, st>>>(parts, N, dots);
+  RC_LAUNCH_OK();
+  return 0;
 }
 
 // ----------------------------------------------------------------------------------------------------------------

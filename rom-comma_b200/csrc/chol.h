@@ -23,8 +23,12 @@ int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, con
 // A (holding L) <- L^-1 in place; tmp needs n*n/4 doubles per matrix.
 int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double* dinv, double* tmp, long strideT, cudaStream_t st);
 
-// Kinv(lower 128-tiles) = Z^T Z.
-int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double* Kinv, long ldk, long strideK, cudaStream_t st);
+// Kinv(lower 128-tiles) = Z^T Z; sel_block > 0 restricts it to the tiles that intersect the diagonal blocks of that size.
+int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double* Kinv, long ldk, long strideK, int sel_block, cudaStream_t st);
+
+// dots[pair(l > l')][i] = K^-1[(l,i),(l',i)] from Z = L^-1 (pair index l*(l-1)/2 + l').
+size_t block_diag_dots_workspace_bytes(int N, int L);
+int block_diag_dots(const double* Z, long ld, int n, int N, int L, double* parts, double* dots, cudaStream_t st);
 
 int sum_parts(const double* parts, int count, int batch, double* out, double scale, cudaStream_t st);
 int dot_batched(const double* a, const double* b, long n, long stride, int batch, double* out, cudaStream_t st);

@@ -4,7 +4,8 @@
 //   Aop[m][k] = TA ? A[k*lda + m] : A[m*lda + k]        (row-major storage everywhere)
 //   Bop[n][k] = TB ? B[k*ldb + n] : B[n*ldb + k]
 //
-// CTA tile 128x128x16, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA tiles, 4-stage cp.async pipeline (160 KB smem, 1 CTA/SM).
+// CTA tile 128x128x16, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA tiles, 4-stage cp.async pipeline (160 KB smem, 1 CTA/SM),
+// persistent over the tile list (grid = number of SMs).
 // Shared-memory rows are padded by 4 doubles so that every half-warp fragment read (4 rows x 4 consecutive doubles, or its
 // transpose) hits 16 distinct 8-byte banks.  M, N are multiples of 128 and K of 16 (callers pad matrices with identity).
 // Triangular structure is exploited at tile granularity through `kmode` (per-tile K range) and `lower_only` (tile list);
@@ -30,6 +31,7 @@ struct GemmArgs {
   double alpha, beta;
   int lower_only;   // 1: only tiles with tile_m >= tile_n (requires M == N)
   int kmode;
+  int sel_block;    // > 0 (with lower_only): compute only tiles that intersect the diagonal blocks of size sel_block ("selected" LAUUM)
 };
 
 constexpr int G_BM = 128, G_BN = 128, G_BK = 16, G_STAGES = 4, G_PAD = 4, G_THREADS = 256;
@@ -57,8 +59,50 @@ __device__ __forceinline__ void gemm_load_operand(double* __restrict__ dst, cons
   }
 }
 
+struct GemmTile {
+  int m0, n0, kb, nk;   // nk == 0: nothing to do for this tile (skipped by sel_block)
+  const double* A; const double* B; double* C;
+};
+
+// tile index (over all matrices of the batch) -> coordinates, K range and base pointers
+__device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p, long tile, long tiles_per_matrix) {
+  const int z = (int)(tile / tiles_per_matrix);
+  const long idx = tile - (long)z * tiles_per_matrix;
+  int tm, tn;
+  if (p.lower_only) {
+    tm = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while ((long)(tm + 1) * (tm + 2) / 2 <= idx) ++tm;
+    while ((long)tm * (tm + 1) / 2 > idx) --tm;
+    tn = (int)(idx - (long)tm * (tm + 1) / 2);
+  } else {
+    const int tiles_m = p.M / G_BM;
+    tm = (int)(idx % tiles_m);
+    tn = (int)(idx / tiles_m);
+    if (p.kmode == K_LT_M1) tm = tiles_m - 1 - tm;   // longest K ranges first
+    if (p.kmode == K_LE_N1) tn = p.N / G_BN - 1 - tn;
+  }
+  GemmTile t;
+  t.m0 = tm * G_BM;
+  t.n0 = tn * G_BN;
+  int kb = 0, ke = p.K;
+  if (p.kmode == K_GE_N0) kb = t.n0;
+  else if (p.kmode == K_LT_M1) ke = min(p.K, t.m0 + G_BM);
+  else if (p.kmode == K_GE_M0) kb = t.m0;
+  else if (p.kmode == K_LE_N1) ke = min(p.K, t.n0 + G_BN);
+  t.kb = kb;
+  t.nk = (ke - kb) / G_BK;
+  if (p.sel_block > 0 && t.m0 / p.sel_block > (t.n0 + G_BN - 1) / p.sel_block) t.nk = -1;   // row blocks all above the column blocks
+  t.A = p.A + (long)z * p.strideA;
+  t.B = p.B + (long)z * p.strideB;
+  t.C = p.C + (long)z * p.strideC;
+  return t;
+}
+
+// Persistent kernel: one CTA per SM walks the tile list with stride gridDim.x.  The cp.async pipeline runs ACROSS tiles: the first
+// stages of the next tile are requested before the epilogue of the current one, and the C tile is prefetched into L2 while the
+// main loop runs, so the read-modify-write epilogue overlaps the next tile's loads instead of draining the SM.
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(GemmArgs p) {
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(GemmArgs p, long tiles_per_matrix, long total_tiles) {
   extern __shared__ __align__(16) double smem[];
   using S = GemmSmem<TA, TB>;
   double* As = smem;
@@ -68,99 +112,103 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(GemmArgs p) {
   const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
   const int g = lane >> 2, t = lane & 3;
 
-  int tm, tn;
-  if (p.lower_only) {
-    const int idx = blockIdx.x;
-    tm = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
-    while ((long)(tm + 1) * (tm + 2) / 2 <= idx) ++tm;
-    while ((long)tm * (tm + 1) / 2 > idx) --tm;
-    tn = idx - tm * (tm + 1) / 2;
-  } else {
-    const int tiles_m = p.M / G_BM;
-    tm = blockIdx.x % tiles_m;
-    tn = blockIdx.x / tiles_m;
-    if (p.kmode == K_LT_M1) tm = tiles_m - 1 - tm;   // longest K ranges first
-    if (p.kmode == K_LE_N1) tn = p.N / G_BN - 1 - tn;
-  }
-  const int m0 = tm * G_BM, n0 = tn * G_BN;
-  int kb = 0, ke = p.K;
-  if (p.kmode == K_GE_N0) kb = n0;
-  else if (p.kmode == K_LT_M1) ke = min(p.K, m0 + G_BM);
-  else if (p.kmode == K_GE_M0) kb = m0;
-  else if (p.kmode == K_LE_N1) ke = min(p.K, n0 + G_BN);
-  const int nk = (ke - kb) / G_BK;
-
-  const double* A = p.A + (long)blockIdx.z * p.strideA;
-  const double* B = p.B + (long)blockIdx.z * p.strideB;
-  double* C = p.C + (long)blockIdx.z * p.strideC;
-
-  double acc[8][4][2];
+  auto prologue = [&](const GemmTile& T) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-#pragma unroll
-  for (int s = 0; s < G_STAGES - 1; ++s) {
-    if (s < nk) {
-      gemm_load_operand<TA>(As + s * S::A_STAGE, A, p.lda, m0, kb + s * G_BK, tid);
-      gemm_load_operand<TB>(Bs + s * S::B_STAGE, B, p.ldb, n0, kb + s * G_BK, tid);
-    }
-    cp_async_commit();
-  }
-
-  for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<G_STAGES - 2>();
-    __syncthreads();
-    {
-      const int nxt = kt + G_STAGES - 1;
-      if (nxt < nk) {
-        const int s = nxt % G_STAGES;
-        gemm_load_operand<TA>(As + s * S::A_STAGE, A, p.lda, m0, kb + nxt * G_BK, tid);
-        gemm_load_operand<TB>(Bs + s * S::B_STAGE, B, p.ldb, n0, kb + nxt * G_BK, tid);
+    for (int s = 0; s < G_STAGES - 1; ++s) {
+      if (s < T.nk) {
+        gemm_load_operand<TA>(As + s * S::A_STAGE, T.A, p.lda, T.m0, T.kb + s * G_BK, tid);
+        gemm_load_operand<TB>(Bs + s * S::B_STAGE, T.B, p.ldb, T.n0, T.kb + s * G_BK, tid);
       }
       cp_async_commit();
     }
-    const double* as = As + (kt % G_STAGES) * S::A_STAGE;
-    const double* bs = Bs + (kt % G_STAGES) * S::B_STAGE;
-#pragma unroll
-    for (int kk = 0; kk < G_BK / 4; ++kk) {
-      double a[8], b[4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        a[i] = TA ? as[(kk * 4 + t) * (G_BM + G_PAD) + wm * 64 + i * 8 + g] : as[(wm * 64 + i * 8 + g) * (G_BK + G_PAD) + kk * 4 + t];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        b[j] = TB ? bs[(kk * 4 + t) * (G_BN + G_PAD) + wn * 32 + j * 8 + g] : bs[(wn * 32 + j * 8 + g) * (G_BK + G_PAD) + kk * 4 + t];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-  }
-  // All operand reads are complete before any store: makes tile-exclusive in-place updates (C aliasing A or B) safe.
-  cp_async_wait<0>();
-  __syncthreads();
+  };
 
-  const double alpha = p.alpha, beta = p.beta;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const long row = m0 + wm * 64 + i * 8 + g;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = n0 + wn * 32 + j * 8 + t * 2;
-      double2* cp = reinterpret_cast<double2*>(C + row * p.ldc + col);
-      double2 v;
-      if (beta == 0.0) {
-        v.x = alpha * acc[i][j][0];
-        v.y = alpha * acc[i][j][1];
-      } else {
-        const double2 o = *cp;
-        v.x = fma(alpha, acc[i][j][0], beta * o.x);
-        v.y = fma(alpha, acc[i][j][1], beta * o.y);
-      }
-      *cp = v;
+  long tile = blockIdx.x;
+  GemmTile T;
+  auto next_tile = [&]() -> bool {        // advance `tile` to the next one that has work; false when the list is exhausted
+    for (; tile < total_tiles; tile += gridDim.x) {
+      T = gemm_decode_tile(p, tile, tiles_per_matrix);
+      if (T.nk >= 0) return true;
     }
+    return false;
+  };
+  if (!next_tile()) return;
+  prologue(T);
+
+  for (;;) {
+    if (p.beta != 0.0) {   // pull the C tile (128 rows x 1 KB) into L2 while the main loop runs
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int line = tid + r * G_THREADS;           // 1024 lines of 128 B
+        const double* addr = T.C + (long)(T.m0 + (line >> 3)) * p.ldc + T.n0 + (line & 7) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+      }
+    }
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < T.nk; ++kt) {
+      cp_async_wait<G_STAGES - 2>();
+      __syncthreads();
+      {
+        const int nxt = kt + G_STAGES - 1;
+        if (nxt < T.nk) {
+          const int s = nxt % G_STAGES;
+          gemm_load_operand<TA>(As + s * S::A_STAGE, T.A, p.lda, T.m0, T.kb + nxt * G_BK, tid);
+          gemm_load_operand<TB>(Bs + s * S::B_STAGE, T.B, p.ldb, T.n0, T.kb + nxt * G_BK, tid);
+        }
+        cp_async_commit();
+      }
+      const double* as = As + (kt % G_STAGES) * S::A_STAGE;
+      const double* bs = Bs + (kt % G_STAGES) * S::B_STAGE;
+#pragma unroll
+      for (int kk = 0; kk < G_BK / 4; ++kk) {
+        double a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          a[i] = TA ? as[(kk * 4 + t) * (G_BM + G_PAD) + wm * 64 + i * 8 + g] : as[(wm * 64 + i * 8 + g) * (G_BK + G_PAD) + kk * 4 + t];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          b[j] = TB ? bs[(kk * 4 + t) * (G_BN + G_PAD) + wn * 32 + j * 8 + g] : bs[(wn * 32 + j * 8 + g) * (G_BK + G_PAD) + kk * 4 + t];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    }
+    // All operand reads of this tile are complete before any of its stores: tile-exclusive in-place updates (C aliasing A or B) are safe.
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const GemmTile done = T;
+    tile += gridDim.x;
+    const bool more = next_tile();
+    if (more) prologue(T);                           // overlaps the epilogue below
+
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long row = done.m0 + wm * 64 + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = done.n0 + wn * 32 + j * 8 + t * 2;
+        double2* cp = reinterpret_cast<double2*>(done.C + row * p.ldc + col);
+        double2 v;
+        if (beta == 0.0) {
+          v.x = alpha * acc[i][j][0];
+          v.y = alpha * acc[i][j][1];
+        } else {
+          const double2 o = *cp;
+          v.x = fma(alpha, acc[i][j][0], beta * o.x);
+          v.y = fma(alpha, acc[i][j][1], beta * o.y);
+        }
+        *cp = v;
+      }
+    }
+    if (!more) break;
   }
 }
 
@@ -168,16 +216,21 @@ template <bool TA, bool TB>
 inline int launch_gemm(const GemmArgs& a, int batch, cudaStream_t stream) {
   using S = GemmSmem<TA, TB>;
   static bool configured = false;   // per instantiation; benign race (idempotent attribute set)
+  static int num_sms = 0;
   if (!configured) {
     RC_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
+    int dev = 0;
+    RC_CUDA_OK(cudaGetDevice(&dev));
+    RC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
   if (a.M <= 0 || a.N <= 0 || batch <= 0) return 0;
   RC_REQUIRE(a.M % G_BM == 0 && a.N % G_BN == 0 && a.K % G_BK == 0, -2, "gemm_dmma: M,N must be multiples of 128 and K of 16 (got %d,%d,%d)", a.M, a.N, a.K);
   const long tm = a.M / G_BM, tn = a.N / G_BN;
   const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
-  dim3 grid((unsigned)tiles, 1, (unsigned)batch);
-  gemm_dmma_kernel<TA, TB><<<grid, G_THREADS, S::BYTES, stream>>>(a);
+  const long total = tiles * batch;
+  const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);   // persistent: one CTA per SM (160 KB smem each)
+  gemm_dmma_kernel<TA, TB><<<grid, G_THREADS, S::BYTES, stream>>>(a, tiles, total);
   RC_LAUNCH_OK();
   return 0;
 }

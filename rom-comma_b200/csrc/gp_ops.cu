@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(GTHREADS) grad_reduce_kernel(GradArgs p) {
     ac[r] = alpha[(long)tj * GT + r];
   }
   for (int e = threadIdx.x; e < p.nvals; e += GTHREADS) parts[e] = 0.0;
+  if (p.diag_blocks_only && ((long)ti * GT) / p.N > ((long)tj * GT + GT - 1) / p.N) return;   // tile lies wholly in off-diagonal blocks
   __syncthreads();
 
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(GTHREADS) grad_reduce_kernel(GradArgs p) {
     for (int v = 0; v < 4; ++v) {
       const int c = tx * 4 + v;
       const long gj = (long)tj * GT + c;
-      const bool valid = li[r] >= 0 && lj[c] >= 0 && gj <= gi;
+      const bool valid = li[r] >= 0 && lj[c] >= 0 && gj <= gi && (!p.diag_blocks_only || li[r] == lj[c]);
       const double wgt = (gj < gi && li[r] == lj[c]) ? 2.0 : 1.0;   // diagonal (l,l) blocks are symmetric: count the mirror
       const double W = valid ? (ar[r] * ac[c] - kv[v]) : 0.0;
       const double U = exp(-0.5 * d2[u][v]);

@@ -30,6 +30,7 @@ struct GradArgs {
   const double* alpha; long stride_alpha;        // K^-1 y, padded with zeros
   double* parts;                                 // grad_workspace_bytes
   int with_ls;
+  int diag_blocks_only;                          // Kinv holds only the tiles that intersect the diagonal (l,l) blocks: restrict the sums to l_i == l_j
   int nvals, slots;                              // filled in by grad_reduce
 };
 int grad_nvals(int L, int M);   // layout: SF (L*L), SE (L*L), dls row part (L*M), dls column part (L*M)

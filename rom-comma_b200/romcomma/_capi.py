@@ -17,7 +17,7 @@ _LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / 'librc_b200.so'
 _lib: Optional[ctypes.CDLL] = None
 
 c_double_p = ctypes.c_void_p
-RC_GRAD_NONE, RC_GRAD_VARIANCE, RC_GRAD_LENGTHSCALES = 0, 1, 2
+RC_GRAD_NONE, RC_GRAD_VARIANCE, RC_GRAD_LENGTHSCALES, RC_GRAD_F_DIAGONAL = 0, 1, 2, 4
 
 _SIGNATURES = {
     'rc_version': (ctypes.c_int, []),
@@ -134,7 +134,7 @@ def dev(a, device=None) -> torch.Tensor:
     if isinstance(a, torch.Tensor):
         return a.to(device=device or 'cuda', dtype=torch.float64).contiguous()
     import numpy as np
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device or 'cuda')
+    return torch.as_tensor(np.require(a, dtype=np.float64, requirements=['C', 'W'])).to(device or 'cuda')
 
 
 def workspace(nbytes: int, device=None) -> torch.Tensor:

@@ -39,4 +39,4 @@ def as_device(a, device=None) -> torch.Tensor:
         return a.as_subclass(torch.Tensor).to(device=device or 'cuda', dtype=torch.float64).contiguous()
     if hasattr(a, 'numpy') and not isinstance(a, np.ndarray):
         a = a.numpy()
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device or 'cuda')
+    return torch.as_tensor(np.require(a, dtype=np.float64, requirements=['C', 'W'])).to(device or 'cuda')

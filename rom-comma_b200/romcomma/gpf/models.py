@@ -108,7 +108,11 @@ class MOGPR(gf.Module):
         """(-LML, gradients w.r.t. the unconstrained ``variables``): what tf.GradientTape gives gpflow's Scipy in the reference."""
         kv, lv = self.kernel.variance, self.likelihood.variance
         want_ls = any(v is self.kernel.lengthscales for v in variables)
-        res = self._evaluate(_capi.RC_GRAD_VARIANCE | (_capi.RC_GRAD_LENGTHSCALES if want_ls else 0))
+        flags = _capi.RC_GRAD_VARIANCE | (_capi.RC_GRAD_LENGTHSCALES if want_ls else 0)
+        F = kv.value.numpy()
+        if not any(v is kv._cholesky_lower_triangle for v in variables) and not np.any(F - np.diag(np.diag(F))):
+            flags |= _capi.RC_GRAD_F_DIAGONAL     # default trainables (gpr/kernels.py:54-57): only diag(F) is trained and F is diagonal
+        res = self._evaluate(flags)
         dFd, dFl = kv._chain(res['dF'])
         dEd, dEl = lv._chain(res['dE'])
         grads = []

@@ -180,14 +180,12 @@ class GPR(Model):
         mean, std = self.predict(self._fold.test_x.values)
 
         def block(values, label):
-            out = truth.copy().rename(columns={Y_heading: label}, level=0)
-            out.iloc[:] = values
-            return out
+            return pd.DataFrame(np.asarray(values), index=truth.index, columns=truth.rename(columns={Y_heading: label}, level=0).columns)
 
         error = truth.to_numpy(dtype=float) - mean
         z_score = error / std
         is_outlier = (z_score ** 2 > 4.0)
-        outliers = block(is_outlier, 'Outlier').astype(bool)
+        outliers = block(is_outlier, 'Outlier')
         both = pd.DataFrame(np.column_stack((is_outlier.any(axis=1), is_outlier.all(axis=1))), index=outliers.index,
                             columns=pd.MultiIndex.from_tuples([('Outlier', 'Any Output'), ('Outlier', 'All Outputs')]))
         outliers = outliers.join(both)

@@ -127,6 +127,21 @@ def test_lml_grad_covariant(C, N, M, L, full_F):
     assert_close(v1, ref['lml'], what='lml (cached K_unit)')
 
 
+@pytest.mark.parametrize('N,M,L', [(200, 5, 3), (128, 3, 4), (131, 4, 2), (50, 2, 4), (300, 6, 1)])
+def test_lml_grad_selected_inverse(C, N, M, L):
+    """RC_GRAD_F_DIAGONAL (default trainables, diagonal F): K^-1 is only formed on its diagonal (l,l) blocks; diag(dF) and the whole
+    of dE must still match the oracle, the off-diagonal entries of dF are returned as zero."""
+    X, Y, ls, F, E = random_problem(N, M, L, seed=N + 7, full_F=False)
+    plan = C.LmlGradPlan(C.dev(X), C.dev(Y), L, 1, C.RC_GRAD_VARIANCE | C.RC_GRAD_F_DIAGONAL)
+    res = plan.unpack(plan(C.dev(ls), C.dev(F[None]), C.dev(E[None])).cpu().numpy())[0]
+    ref = gp.lml_grad_mo(X, Y, ls, F, E)
+    assert_close(res['lml'], ref['lml'], what='lml')
+    assert_close(np.diag(res['dF']), np.diag(ref['dF']), atol=1e-10 * L * N, what='diag dF')
+    assert_close(res['dE'], ref['dE'], atol=1e-10 * L * N, what='dE')
+    assert np.all(res['dF'][~np.eye(L, dtype=bool)] == 0.0)
+    assert np.all(res['dls'] == 0.0)
+
+
 def test_lml_grad_variant_batch(C):
     X, Y, ls, F, E = random_problem(180, 6, 3, seed=21, full_E=False)
     var, noise = np.diag(F).copy(), np.diag(E).copy()
@@ -214,7 +229,7 @@ def test_full_size_properties_cfg3(C):
     n = N * L
     dX, dY, dls, dF, dE = C.dev(w.X), C.dev(w.Y), C.dev(w.lengthscales), C.dev(w.F[None]), C.dev(w.E[None])
     K = C.gram(dX, None, dls, dF, dE)[0]
-    assert_close((K - K.T).abs().max().item(), 0.0, atol=0.0, what='gram exactly symmetric')
+    assert (K - K.T).abs().max().item() == 0.0, 'gram is not exactly symmetric'
     fac = C.Factorization(C.gram(dX, None, dls, dF, dE, pad_to=n, pad_identity=True, lower_only=True))
     fac.raise_if_failed()
     v = torch.randn(1, n, dtype=torch.float64, device='cuda', generator=torch.Generator('cuda').manual_seed(0))
