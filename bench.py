@@ -34,6 +34,9 @@ for p in (ROOT, ROOT / 'rom-comma_b200'):
         sys.path.insert(0, str(p))
 
 METRIC, UNIT = 'mogpr_lml_grad_evals_per_s', 'evals/s'
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` captures (profiles/r01_ncu_syrk.md:
+# first rank-256 trailing update, 2.25 GB; profiles/r01_ncu_lauum.md: full LAUUM, 41.3 GB), per launch.  None until captured.
+NCU_TRAFFIC = {'syrk_rank256_first_launch_bytes': 2.254e9, 'lauum_full_launch_bytes': 41.29e9, 'source': 'profiles/r01_ncu_syrk.md, profiles/r01_ncu_lauum.md'}
 
 
 def parse():
@@ -227,29 +230,43 @@ def run_b200(args):
     lml = float(plan.out[0, 0].item())
     assert info == 0 and np.isfinite(lml), f'evaluation failed: info={info}, lml={lml}'
 
-    # ---- stage breakdown (outside the timed region) ---------------------------------------------------------------------
+    # ---- dominant-kernel profile + stage breakdown (outside the timed region) ---------------------------------------------
+    # One more evaluation with every gemm_dmma_kernel launch bracketed by CUDA events on its own stream (rc_profile_begin/end):
+    # roofline.achieved = flops those launches executed / their summed durations.
+    peaks = C.measure_peaks()
+    with C.gemm_profile() as prof:
+        plan(dls, dF, dE)
+        torch.cuda.synchronize()
+
     def timed(fn, reps=2):
         best = float('inf')
         for _ in range(reps):
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            out = fn()
+            fn()
             b.record()
             torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b))
-        return best, out
+        return best
     stages = {}
     if rank == 0:
-        t_gram, Kp = timed(lambda: C.gram(dX, None, dls, dF, dE, pad_to=n, pad_identity=True, lower_only=True))
-        t_potrf, fac = timed(lambda: C.Factorization(C.gram(dX, None, dls, dF, dE, pad_to=n, pad_identity=True, lower_only=True)))
-        t_potrf -= t_gram
-        t_potri, _ = timed(lambda: fac.inverse_(), reps=1)
-        stages = {'gram_ms': t_gram, 'potrf_ms': t_potrf, 'potrf_tflops': n ** 3 / 3 / t_potrf * 1e-9, 'potri_ms': t_potri,
-                  'potri_tflops': 2 * n ** 3 / 3 / t_potri * 1e-9}
-        del Kp, fac
+        lib = C.lib()
+        Kp = torch.empty((1, n, n), dtype=torch.float64, device='cuda')
+        Kinv = torch.empty_like(Kp)
+        work = C.workspace(lib.rc_potrf_bufsize(n, 1))
+        info_t = torch.zeros(1, dtype=torch.int32, device='cuda')
+        t_gram = timed(lambda: C.gram(dX, None, dls, dF, dE, pad_to=n, pad_identity=True, lower_only=True, out=Kp))
+
+        def potrf():
+            C.check(lib.rc_potrf(C.ptr(Kp), n, n, n * n, 1, C.raw_ptr(work), C.raw_ptr(info_t), C.stream_ptr()), 'rc_potrf')
+        t_potrf = timed(potrf, reps=1)              # in place: one shot per gram
+        t_potri = timed(lambda: C.check(lib.rc_potri(C.ptr(Kp), n, n, n * n, 1, C.raw_ptr(work), C.ptr(Kinv), n, n * n, C.stream_ptr()), 'rc_potri'),
+                        reps=1)
+        stages = {'gram_ms': t_gram, 'gram_gbs': 8e-9 * n * (n + 128) / 2 / (t_gram * 1e-3), 'potrf_ms': t_potrf,
+                  'potrf_tflops': n ** 3 / 3 / t_potrf * 1e-9, 'potri_full_ms': t_potri, 'potri_full_tflops': 2 * n ** 3 / 3 / t_potri * 1e-9}
+        del Kp, Kinv, work
         torch.cuda.empty_cache()
-    peaks = C.measure_peaks()
 
     # ---- end to end through the public API, host buffers ----------------------------------------------------------------
     Xh, Yh = torch.as_tensor(w.X).pin_memory(), torch.as_tensor(w.Y).pin_memory()
@@ -326,18 +343,24 @@ def run_b200(args):
                                   f'scaled by (N/N_s)^2 x slices = {(N / srows) ** 2 * len(masks) / nsl:g}'}
 
     if rank == 0:
-        flops = float(n) ** 3
-        achieved = flops / (ms_per_step * 1e-3) * 1e-12
+        achieved = prof.tflops
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
                 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': workload_description(w, L, M), 'parallelism': f'replicas x{world} (one hyper-parameter point per GPU)',
                            'l2': 'inputs larger than L2: each step rewrites and re-reads 2.1 GB matrices (126 MB L2), no explicit flush needed'},
                 'roofline': {'bound': 'tensor', 'kernel': 'gemm_dmma_kernel (FP64 DMMA.8x8x4 tiles: Cholesky trailing update, TRSM, triangular inverse, LAUUM)',
                              'achieved': achieved, 'peak': peaks['dmma_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['dmma_tflops'],
-                             'traffic': None,
-                             'note': 'achieved = algorithmic n^3 flops (n^3/3 potrf + 2n^3/3 inverse) / whole-step time, so it also carries the gram, '
-                                     'panel, solve and reduction kernels; peak = FP64 tensor peak measured live by a register-resident DMMA loop '
-                                     '(MEASURED_PEAKS.json has no FP64 entry)', 'stages': stages},
+                             'traffic': NCU_TRAFFIC['lauum_full_launch_bytes'], 'traffic_detail': NCU_TRAFFIC,
+                             'launches_per_step': prof.launches, 'kernel_ms_per_step': prof.ms, 'kernel_share_of_step': prof.ms / ms_per_step,
+                             'flops_per_step': prof.flops, 'reference_flops_per_step': float(n) ** 3,
+                             'step_tflops_on_executed_flops': prof.flops / (ms_per_step * 1e-3) * 1e-12,
+                             'note': 'achieved = flops executed by the tile lists of the gemm_dmma_kernel launches of one evaluation / the sum of their '
+                                     'CUDA-event durations (events on the launching stream, rc_profile_begin/end); flops_per_step is below the textbook '
+                                     'n^3 (n^3/3 potrf + n^3/3 trtri + n^3/3 lauum) because, with the default trainables and a diagonal F, K^-1 is only '
+                                     'formed on its diagonal (l,l) blocks (RC_GRAD_F_DIAGONAL); peak = FP64 tensor peak measured live by a '
+                                     'register-resident DMMA loop (MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 is ~37-40 TFLOP/s); '
+                                     'traffic = ncu dram bytes (read+write) per launch averaged over the launches of profiles/r01_ncu_*.md',
+                             'stages': stages},
                 'cpu_baseline': cpu,
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                         'ms_per_step': 1e3 * e2e_s / args.steps,

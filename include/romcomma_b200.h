@@ -36,6 +36,13 @@ long rc_launch_count(void);
 int rc_measure_dmma_tflops(double* scratch, double* tflops_host);
 int rc_measure_exp_gexps(double* scratch, double* gexps_host);
 
+/* Per-launch profile of the dominant kernel (gemm_dmma_kernel: FP64 DMMA tiles behind potrf / trtri / lauum / trsm), for bench.py's
+ * roofline: between rc_profile_begin() and rc_profile_end() every GEMM launch is bracketed by CUDA events on its own stream.
+ * rc_profile_end synchronises on them and returns the summed launch durations (ms), the flops those launches executed
+ * (2*128*128*K per tile actually computed) and their count.  Diagnostic, process-global, not thread-safe. */
+int rc_profile_begin(void);
+int rc_profile_end(double* gemm_ms_host, double* gemm_flops_host, long* gemm_launches_host);
+
 /* ---- gram ---------------------------------------------------------------------------------------------------------
  * out[(l,n),(l',n')] = F[l,l'] * exp(-1/2 sum_m (X[n,m]/ls[l,m] - X2[n',m]/ls[l',m])^2) + E[l,l'] * [n == n']
  * Replaces MOStationary.K_unit_variance / K_d_apply_variance / K_d / __call__ (romcomma/gpf/kernels.py:74-116,153-154),

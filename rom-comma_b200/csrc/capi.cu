@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <vector>
 
 namespace rc {
 static thread_local char g_err[512] = "";
@@ -18,6 +19,30 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- optional GEMM launch profile --------------------------------------------------------------------------------
+namespace {
+struct GemmProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;   // events are created once and re-used
+  size_t used = 0;
+  std::vector<double> flops;
+} g_prof;
+cudaEvent_t prof_event() {
+  if (g_prof.used == g_prof.pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof.pool.push_back(e);
+  }
+  return g_prof.pool[g_prof.used++];
+}
+}  // namespace
+bool profile_enabled() { return g_prof.on; }
+void profile_gemm_begin(cudaStream_t st) { cudaEventRecord(prof_event(), st); }
+void profile_gemm_end(cudaStream_t st, double flops) {
+  cudaEventRecord(prof_event(), st);
+  g_prof.flops.push_back(flops);
 }
 
 static inline size_t align256(size_t b) { return (b + 255) / 256 * 256; }
@@ -95,6 +120,29 @@ long rc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); 
 const char* rc_last_error(void) { return g_err; }
 int rc_padded(int n) { return round_up(n, TILE); }
 
+int rc_profile_begin(void) {
+  g_prof.on = true;
+  g_prof.used = 0;
+  g_prof.flops.clear();
+  return 0;
+}
+
+int rc_profile_end(double* gemm_ms_host, double* gemm_flops_host, long* gemm_launches_host) {
+  g_prof.on = false;
+  double ms = 0.0, fl = 0.0;
+  for (size_t i = 0; i < g_prof.flops.size(); ++i) {
+    RC_CUDA_OK(cudaEventSynchronize(g_prof.pool[2 * i + 1]));
+    float t = 0.f;
+    RC_CUDA_OK(cudaEventElapsedTime(&t, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]));
+    ms += t;
+    fl += g_prof.flops[i];
+  }
+  if (gemm_ms_host) *gemm_ms_host = ms;
+  if (gemm_flops_host) *gemm_flops_host = fl;
+  if (gemm_launches_host) *gemm_launches_host = (long)g_prof.flops.size();
+  return 0;
+}
+
 int rc_gram(const double* X, int N, const double* X2, int N2, int M, const double* ls, int L, const double* F, const double* E, double* out,
             long ld_out, long stride_out, int rows_pad, int cols_pad, int lower_only, int pad_identity, int batch, rc_stream_t stream) {
   RC_REQUIRE(X && ls && out && N > 0 && M > 0 && L > 0 && batch > 0, -2, "rc_gram: null pointer or non-positive size");
@@ -167,7 +215,7 @@ bool lml_selected(int L, int batch, int flags) {
   return (flags & RC_GRAD_F_DIAGONAL) && (flags & RC_GRAD_VARIANCE) && !(flags & RC_GRAD_LENGTHSCALES) && L > 1 && batch == 1;
 }
 struct LmlLayout {
-  size_t A, Kinv, potrf, vec, scal, gparts, graw, dots, total;
+  size_t A, Kinv, potrf, vec, scal, gparts, graw, dots, tg, total;
   int n_pad;
 };
 LmlLayout lml_layout(int N, int M, int L, int batch, int flags) {
@@ -183,6 +231,7 @@ LmlLayout lml_layout(int N, int M, int L, int batch, int flags) {
   o.gparts = off; off += (flags != RC_GRAD_NONE) ? align256(grad_workspace_bytes(o.n_pad, L, M, batch)) : 0;
   o.graw = off; off += align256((size_t)batch * grad_nvals(L, M) * sizeof(double));
   o.dots = off; off += lml_selected(L, batch, flags) ? align256(block_diag_dots_workspace_bytes(N, L) + (size_t)(L * (L - 1) / 2) * N * sizeof(double)) : 0;
+  o.tg = off; off += (flags != RC_GRAD_NONE) ? align256(tri_gemv_workspace_bytes(o.n_pad, batch)) : 0;
   o.total = off;
   return o;
 }
@@ -229,14 +278,18 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
   // 3. alpha = L^-1 y, quad = alpha^T alpha
   pack_y_kernel<<<dim3((n_pad + 255) / 256, batch), 256, 0, st>>>(Y, N, L, batch, n_pad, yv);
   RC_LAUNCH_OK();
-  if ((rc = trsv_lower(A, n_pad, n_pad, mat, batch, pw.dinv, yv, alpha, n_pad, 0, st))) return rc;
-  if ((rc = dot_batched(alpha, alpha, n_pad, n_pad, batch, quad, st))) return rc;
   RC_CUDA_OK(cudaMemsetAsync(graw, 0, (size_t)batch * grad_nvals(L, M) * sizeof(double), st));
-  if (flags != RC_GRAD_NONE) {
-    // 4. K^-1 y = L^-T alpha ; K^-1 = L^-T L^-1
-    RC_CUDA_OK(cudaMemcpyAsync(wv, alpha, (size_t)batch * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    if ((rc = trsv_lower(A, n_pad, n_pad, mat, batch, pw.dinv, wv, kinvy, n_pad, 1, st))) return rc;
+  if (flags == RC_GRAD_NONE) {
+    if ((rc = trsv_lower(A, n_pad, n_pad, mat, batch, pw.dinv, yv, alpha, n_pad, 0, st))) return rc;
+    if ((rc = dot_batched(alpha, alpha, n_pad, n_pad, batch, quad, st))) return rc;
+  } else {
+    // 4. Z = L^-1 in place first: alpha = Z y and K^-1 y = Z^T alpha are then two passes over the triangle instead of
+    //    2 x n/128 dependent substitution steps; K^-1 = Z^T Z.
+    double* tg = reinterpret_cast<double*>(base + lay.tg);
     if ((rc = trtri_lower(A, n_pad, n_pad, mat, batch, pw.dinv, Kinv, mat, st))) return rc;
+    if ((rc = tri_gemv_lower(A, n_pad, n_pad, mat, batch, yv, alpha, n_pad, 0, tg, st))) return rc;
+    if ((rc = dot_batched(alpha, alpha, n_pad, n_pad, batch, quad, st))) return rc;
+    if ((rc = tri_gemv_lower(A, n_pad, n_pad, mat, batch, alpha, kinvy, n_pad, 1, tg, st))) return rc;
     const bool selected = lml_selected(L, batch, flags);
     if ((rc = lauum_lower(A, n_pad, n_pad, mat, batch, Kinv, n_pad, mat, selected ? N : 0, st))) return rc;
     // 5. contractions

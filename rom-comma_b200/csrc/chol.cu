@@ -500,6 +500,75 @@ int block_diag_dots(const double* Z, long ld, int n, int N, int L, double* parts
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// Triangular matrix-vector products with Z = L^-1 (lower, row-major):  out = Z v  or  out = Z^T v.
+// Once Z exists (gradient path) these replace the two block-sequential substitutions: one pass over the triangle (HBM bound)
+// instead of 2 x n/128 dependent launches.  Fixed reduction order: bitwise reproducible.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tri_gemv_n_kernel(const double* __restrict__ Z, long ld, long strideZ, const double* __restrict__ v,
+                                                         double* __restrict__ out, long strideV, int n) {
+  const int lane = threadIdx.x & 31, z = blockIdx.y;
+  const long i = (long)blockIdx.x * 8 + (threadIdx.x >> 5);   // one warp per row
+  if (i >= n) return;
+  const double* row = Z + (long)z * strideZ + i * ld;
+  const double* vz = v + (long)z * strideV;
+  double s0 = 0.0, s1 = 0.0;
+  // columns 0..i in double2 steps; the element right of the diagonal (if any) is an explicit zero of the diagonal block or masked here
+  for (long j = 2 * lane; j <= i; j += 64) {
+    const double2 a = *reinterpret_cast<const double2*>(row + j);
+    const double2 b = *reinterpret_cast<const double2*>(vz + j);
+    s0 = fma(a.x, b.x, s0);
+    if (j + 1 <= i) s1 = fma(a.y, b.y, s1);
+  }
+  const double s = warp_sum(s0 + s1);
+  if (lane == 0) out[(long)z * strideV + i] = s;
+}
+
+constexpr int TG_SPLIT = 32;
+
+__global__ void __launch_bounds__(128) tri_gemv_t_partial_kernel(const double* __restrict__ Z, long ld, long strideZ, const double* __restrict__ v,
+                                                                 long strideV, int n, double* __restrict__ parts) {
+  const int z = blockIdx.z, split = blockIdx.y;
+  const long j = (long)blockIdx.x * 128 + threadIdx.x;
+  const long rows = ((long)n + TG_SPLIT - 1) / TG_SPLIT;
+  const long i1 = min((long)n, (long)(split + 1) * rows);
+  const long i0 = max((long)split * rows, (long)blockIdx.x * 128);   // no row above this column block contributes
+  double s = 0.0;
+  if (j < n) {
+    const double* Zz = Z + (long)z * strideZ;
+    const double* vz = v + (long)z * strideV;
+    for (long i = i0; i < i1; ++i)
+      if (i >= j) s = fma(Zz[i * ld + j], vz[i], s);
+  }
+  if (j < n) parts[((long)z * TG_SPLIT + split) * n + j] = s;
+}
+
+__global__ void tri_gemv_t_finish_kernel(const double* __restrict__ parts, int n, double* __restrict__ out, long strideV) {
+  const int z = blockIdx.y;
+  const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s = 0.0;
+  for (int sp = 0; sp < TG_SPLIT; ++sp) s += parts[((long)z * TG_SPLIT + sp) * n + j];
+  out[(long)z * strideV + j] = s;
+}
+
+size_t tri_gemv_workspace_bytes(int n, int batch) { return (size_t)batch * TG_SPLIT * n * sizeof(double); }
+
+int tri_gemv_lower(const double* Z, int n, long ld, long strideZ, int batch, const double* v, double* out, long strideV, int transpose,
+                   double* parts, cudaStream_t st) {
+  RC_REQUIRE(ld % 2 == 0, -2, "tri_gemv_lower: ld=%ld must be even", ld);
+  if (!transpose) {
+    tri_gemv_n_kernel<<<dim3((n + 7) / 8, batch), 256, 0, st>>>(Z, ld, strideZ, v, out, strideV, n);
+    RC_LAUNCH_OK();
+  } else {
+    tri_gemv_t_partial_kernel<<<dim3((n + 127) / 128, TG_SPLIT, batch), 128, 0, st>>>(Z, ld, strideZ, v, strideV, n, parts);
+    RC_LAUNCH_OK();
+    tri_gemv_t_finish_kernel<<<dim3((n + 127) / 128, batch), 128, 0, st>>>(parts, n, out, strideV);
+    RC_LAUNCH_OK();
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // small utilities
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void sum_parts_kernel(const double* __restrict__ parts, int count, double* __restrict__ out, double scale) {

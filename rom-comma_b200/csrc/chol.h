@@ -30,6 +30,11 @@ int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double
 size_t block_diag_dots_workspace_bytes(int N, int L);
 int block_diag_dots(const double* Z, long ld, int n, int N, int L, double* parts, double* dots, cudaStream_t st);
 
+// out = Z v (transpose = 0) or Z^T v (transpose = 1) for lower-triangular Z (only i >= j is read); parts: tri_gemv_workspace_bytes.
+size_t tri_gemv_workspace_bytes(int n, int batch);
+int tri_gemv_lower(const double* Z, int n, long ld, long strideZ, int batch, const double* v, double* out, long strideV, int transpose,
+                   double* parts, cudaStream_t st);
+
 int sum_parts(const double* parts, int count, int batch, double* out, double scale, cudaStream_t st);
 int dot_batched(const double* a, const double* b, long n, long stride, int batch, double* out, cudaStream_t st);
 int extract_lower(const double* src, long lds, long strideS, double* dst, int n, long strideDst, int batch, int symmetrize, cudaStream_t st);

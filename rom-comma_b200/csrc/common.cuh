@@ -13,6 +13,12 @@ void set_error(const char* fmt, ...);
 // Kernel-launch counter behind rc_launch_count(): bench.py's "gpu_launches" claim is counted here, not estimated.
 void count_launches(long n);
 
+// Optional per-launch timing of the DMMA GEMM (rc_profile_begin / rc_profile_end): CUDA events on the launching stream around every
+// gemm_dmma_kernel launch plus the flops its tile list executes.  Off by default; a diagnostic, not thread-safe.
+bool profile_enabled();
+void profile_gemm_begin(cudaStream_t st);
+void profile_gemm_end(cudaStream_t st, double flops);
+
 #define RC_CUDA_OK(expr)                                                                          \
   do {                                                                                            \
     cudaError_t _e = (expr);                                                                      \

@@ -212,6 +212,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(GemmArgs p, lon
   }
 }
 
+// flops the tile list of one launch executes (2 * 128 * 128 * K-range per tile): host mirror of gemm_decode_tile, profiling only
+inline double gemm_tile_flops(const GemmArgs& p, int batch) {
+  const long tm_n = p.M / G_BM, tn_n = p.N / G_BN;
+  double ksum = 0.0;
+  for (long tm = 0; tm < tm_n; ++tm)
+    for (long tn = 0; tn < (p.lower_only ? tm + 1 : tn_n); ++tn) {
+      const long m0 = tm * G_BM, n0 = tn * G_BN;
+      long kb = 0, ke = p.K;
+      if (p.kmode == K_GE_N0) kb = n0;
+      else if (p.kmode == K_LT_M1) ke = (p.K < m0 + G_BM) ? p.K : m0 + G_BM;
+      else if (p.kmode == K_GE_M0) kb = m0;
+      else if (p.kmode == K_LE_N1) ke = (p.K < n0 + G_BN) ? p.K : n0 + G_BN;
+      if (p.sel_block > 0 && m0 / p.sel_block > (n0 + G_BN - 1) / p.sel_block) continue;
+      if (ke > kb) ksum += (double)(ke - kb);
+    }
+  return 2.0 * G_BM * G_BN * ksum * batch;
+}
+
 template <bool TA, bool TB>
 inline int launch_gemm(const GemmArgs& a, int batch, cudaStream_t stream) {
   using S = GemmSmem<TA, TB>;
@@ -230,7 +248,10 @@ inline int launch_gemm(const GemmArgs& a, int batch, cudaStream_t stream) {
   const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   const long total = tiles * batch;
   const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);   // persistent: one CTA per SM (160 KB smem each)
+  const bool prof = profile_enabled();
+  if (prof) profile_gemm_begin(stream);
   gemm_dmma_kernel<TA, TB><<<grid, G_THREADS, S::BYTES, stream>>>(a, tiles, total);
+  if (prof) profile_gemm_end(stream, gemm_tile_flops(a, batch));
   RC_LAUNCH_OK();
   return 0;
 }

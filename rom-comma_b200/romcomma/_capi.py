@@ -26,6 +26,8 @@ _SIGNATURES = {
     'rc_launch_count': (ctypes.c_long, []),
     'rc_measure_dmma_tflops': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
     'rc_measure_exp_gexps': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
+    'rc_profile_begin': (ctypes.c_int, []),
+    'rc_profile_end': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'rc_gram': (ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p, c_double_p,
                                c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                ctypes.c_void_p]),
@@ -123,6 +125,21 @@ def measure_peaks() -> dict:
     check(lib().rc_measure_dmma_tflops(ptr(scratch), ctypes.byref(tf)), 'rc_measure_dmma_tflops')
     check(lib().rc_measure_exp_gexps(ptr(scratch), ctypes.byref(ge)), 'rc_measure_exp_gexps')
     return {'dmma_tflops': tf.value, 'exp_gexps': ge.value}
+
+
+class gemm_profile:
+    """Context manager around rc_profile_begin/end: ``with gemm_profile() as p: ...`` then p.ms, p.flops, p.launches, p.tflops."""
+
+    def __enter__(self):
+        check(lib().rc_profile_begin(), 'rc_profile_begin')
+        return self
+
+    def __exit__(self, *exc):
+        ms, fl, cnt = ctypes.c_double(0.0), ctypes.c_double(0.0), ctypes.c_long(0)
+        check(lib().rc_profile_end(ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(cnt)), 'rc_profile_end')
+        self.ms, self.flops, self.launches = ms.value, fl.value, cnt.value
+        self.tflops = fl.value / (ms.value * 1e-3) * 1e-12 if ms.value > 0 else 0.0
+        return False
 
 
 def padded(n: int) -> int:
