@@ -44,9 +44,10 @@ def eye(num_rows, num_columns=None, dtype=float64):
 
 
 def fill(dims, value):
+    """Differentiable in ``value`` (gpflow's add_noise_cov fills the likelihood variance, a trainable parameter)."""
     value = _t(value)
-    return Tensor.wrap(_torch.full(tuple(int(d) for d in _t(dims).tolist()) if not isinstance(dims, (tuple, list)) else tuple(int(d) for d in dims),
-                                   value.item(), dtype=value.dtype))
+    dims = tuple(int(d) for d in (_t(dims).tolist() if not isinstance(dims, (tuple, list)) else dims))
+    return Tensor.wrap(value.reshape(()) * _torch.ones(dims, dtype=value.dtype))
 
 
 def zeros(shape, dtype=float64):

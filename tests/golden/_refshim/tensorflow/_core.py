@@ -87,6 +87,23 @@ class Tensor(_torch.Tensor):
     def __bool__(self):
         return bool(self.detach().as_subclass(_torch.Tensor).item())
 
+    # tf.Tensor is an immutable value: ``a += b`` rebinds ``a`` to a new tensor (torch would mutate in place and alias), and a
+    # deep copy may share storage.
+    def __iadd__(self, other):
+        return self + other
+
+    def __isub__(self, other):
+        return self - other
+
+    def __imul__(self, other):
+        return self * other
+
+    def __itruediv__(self, other):
+        return self / other
+
+    def __deepcopy__(self, memo):
+        return self
+
 
 def as_t(x, dtype=None) -> Tensor:
     """Anything tensor-like (incl. gpflow-shim Parameters, numpy arrays, python scalars/sequences, TensorShapes) -> Tensor."""

