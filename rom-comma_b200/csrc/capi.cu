@@ -335,4 +335,21 @@ int rc_sobol_contract(const double* X, int N, int M, const double* Phi, const do
   return sobol_contract(X, N, M, Phi, c, L, is_F_diagonal ? 1 : L, masks_host, nslices, static_cast<double*>(parts), V, (cudaStream_t)stream);
 }
 
+size_t rc_sobol_error_bufsize(int N, int M, int L, int nslices, int n_pad, int chol_batch) {
+  return align256(sobol_error_workspace_bytes(N, M, L, nslices, n_pad, chol_batch));
+}
+
+int rc_sobol_error(const double* X, int N, int M, const double* Lam, const double* F, const double* Phi, const double* g0, const double* g0KY,
+                   int L, const double* Achol, int n_pad, long ld, long strideA, int chol_batch, const void* potrf_work,
+                   const unsigned long long* masks_host, int nslices, void* work, size_t work_bytes, double* V, double* W, rc_stream_t stream) {
+  RC_REQUIRE(X && Lam && F && Phi && g0 && g0KY && Achol && potrf_work && masks_host && work && V && W && nslices > 0, -2,
+             "rc_sobol_error: null pointer or empty subset list");
+  RC_REQUIRE(chol_batch == 1 || chol_batch == L, -2, "rc_sobol_error: chol_batch must be 1 (covariant) or L (variant)");
+  RC_REQUIRE(n_pad % TILE == 0, -2, "rc_sobol_error: n_pad must be a multiple of 128");
+  RC_REQUIRE(work_bytes >= sobol_error_workspace_bytes(N, M, L, nslices, n_pad, chol_batch), -2, "rc_sobol_error: workspace too small");
+  PotrfWork w = split_potrf_work(const_cast<void*>(potrf_work), n_pad, chol_batch);
+  return sobol_error(X, N, M, Lam, F, Phi, g0, g0KY, L, Achol, n_pad, ld, strideA, chol_batch, w.dinv, masks_host, nslices, work, V, W,
+                     (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -1,0 +1,335 @@
+// Standard errors of the closed Sobol indices (FP64, sm_100a): ClosedSobolWithError.marginalize / _calibrate with diagonal F and
+// is_T_partial (romcomma/gsa/calibrators.py:146-402).
+//
+// With the size-one axes of a diagonal F removed, the reference's rank-8 Gaussian chains collapse to two families of pairwise
+// kernels over the (N, n) sample pairs, both of the form
+//     K[N,n] = exp( sum_{m in s} ( cA_m x_Nm^2 + cB_m x_nm^2 + cC_m x_Nm x_nm + cK_m ) )
+// job (kind 0; l,i):  H_li - the kernel of ClosedSobol._V - from which  u_li[n] = sum_N c_l[N] H_li[N,n]   (_psi_factor, :290-309)
+// job (kind 1; l,i):  Q_li - the Omega/Upsilon/G Gaussian ratio of _mu_phi_mu (:259-288)               w_li[n] = sum_N c_l[N] Q_li[N,n]
+// Then  V[l,i] = c_i . u_li,   psi_li = L_chol^-1 (g0_i * u_li)  (block i of an LN-vector for a covariant GP),
+//       W_raw[l,i] = ( pre_i * c_l . w_li  -  |psi_li|^2 ) * (1 + [l == i]),   W = W_raw + W_raw^T.
+// The coefficient algebra is derived in oracle/sobol_error.py (checked against vectors produced by running the reference's file).
+// One fused mat-vec kernel evaluates every (job, subset) pair; nothing of size N^2 is ever stored.  Partial sums are combined in
+// a fixed order: bitwise reproducible, no atomics.
+#include "sobol.h"
+#include "chol.h"
+#include "common.cuh"
+
+namespace rc {
+
+constexpr int EC = 64;          // columns (n) per CTA
+constexpr int ETHREADS = 256;   // 16 x 16 threads, 4 x 4 pairs each per 64 x 64 sub-tile
+
+// ---- per-job coefficients ------------------------------------------------------------------------------------------
+// coef layout: [4][J][M] = { cA, cB, cC, cK }, J = 2*L*L, job = kind*L*L + l*L + i.  pre[i] = F_i sqrt(prod_m Lam2/(Lam2+2)).
+__global__ void sobol_error_coeff_kernel(const double* __restrict__ Phi, const double* __restrict__ Lam, const double* __restrict__ F, int L, int M,
+                                         double* __restrict__ coef, double* __restrict__ pre) {
+  const int J = 2 * L * L;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < J * M; e += gridDim.x * blockDim.x) {
+    const int job = e / M, m = e - job * M;
+    const int kind = job / (L * L), li = job - kind * L * L, l = li / L, i = li - l * L;
+    const double pl = Phi[l * M + m], pi = Phi[i * M + m];
+    double A, B, C, K;
+    if (kind == 0) {
+      const double psi = 1.0 - pl * pi, g = pl * pi / psi;
+      A = g * pl; B = g * pi; C = g; K = -0.5 * log(psi);
+    } else {
+      const double lam2 = Lam[i * M + m] * Lam[i * M + m];
+      const double ups = 1.0 / (lam2 + 2.0);
+      const double gl = 1.0 - pl, gi = 1.0 - pi;
+      const double r = (1.0 - ups) / (1.0 - pl * ups);
+      const double a = pi * pl * pl * r;
+      const double v = gl * pl + pl * pl * gi + pi * pi * pl * pl * r * gl;
+      const double b = ups * pl * pl / (1.0 - ups * pl);
+      A = a * a / v + b; B = pl * pl / v - pl; C = a * pl / v; K = -0.5 * log(v * (1.0 - ups * pl) / pl);
+    }
+    coef[(0L * J + job) * M + m] = -0.5 * A;
+    coef[(1L * J + job) * M + m] = -0.5 * B;
+    coef[(2L * J + job) * M + m] = C;
+    coef[(3L * J + job) * M + m] = K;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < L) {
+    const int i = threadIdx.x;
+    double prod = 1.0;
+    for (int m = 0; m < M; ++m) {
+      const double lam2 = Lam[i * M + m] * Lam[i * M + m];
+      prod *= lam2 / (lam2 + 2.0);
+    }
+    pre[i] = sqrt(prod) * F[i];
+  }
+}
+
+// ---- fused pairwise kernel + mat-vec -----------------------------------------------------------------------------------
+struct ErrMatvecArgs {
+  const double* X; int N, M;
+  const double* coef;     // [4][J][M]
+  const double* c;        // [L][N] left weights g0KY; job (kind,l,i) uses row l
+  int L, J, T, RC, RCH;   // T column tiles of 64, RC row chunks of RCH rows
+  int ns;
+  double* parts;          // [J][RC][ns][T*64]
+  unsigned long long masks[SOBOL_MAX_SLICES];
+};
+
+__global__ void __launch_bounds__(ETHREADS) sobol_error_matvec_kernel(ErrMatvecArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int M = p.M, RCH = p.RCH;
+  double* cA = sm;                  // [M]
+  double* cB = cA + M;
+  double* cC = cB + M;
+  double* cK = cC + M;
+  double* xs = cK + M;              // [M][RCH]   x of this row chunk
+  double* wl = xs + (long)M * RCH;  // [RCH]      left weights
+  double* yc = wl + RCH;            // [M][64]    cC_m * y
+  double* y2 = yc + M * EC;         // [M][64]    cB_m * y^2
+  double* su = y2 + M * EC;         // [RCH]
+  double* sv = su + RCH;            // [64]
+  double* red = sv + EC;            // [16][64]
+
+  const int job = blockIdx.y, J = p.J;
+  const int tj = blockIdx.x / p.RC, rc = blockIdx.x - tj * p.RC;
+  const int li = job % (p.L * p.L), l = li / p.L;
+  const int tid = threadIdx.x;
+  const int row0 = rc * RCH, col0 = tj * EC;
+
+  for (int m = tid; m < M; m += ETHREADS) {
+    cA[m] = p.coef[(0L * J + job) * M + m];
+    cB[m] = p.coef[(1L * J + job) * M + m];
+    cC[m] = p.coef[(2L * J + job) * M + m];
+    cK[m] = p.coef[(3L * J + job) * M + m];
+  }
+  __syncthreads();
+  for (long e = tid; e < (long)RCH * M; e += ETHREADS) {
+    const int r = (int)(e / M), m = (int)(e - (long)r * M);
+    const int gi = row0 + r;
+    xs[(long)m * RCH + r] = gi < p.N ? p.X[(long)gi * M + m] : 0.0;
+  }
+  for (int r = tid; r < RCH; r += ETHREADS) {
+    const int gi = row0 + r;
+    wl[r] = gi < p.N ? p.c[(long)l * p.N + gi] : 0.0;      // rows beyond N carry zero weight
+  }
+  for (int e = tid; e < EC * M; e += ETHREADS) {
+    const int r = e / M, m = e - r * M;
+    const int gj = col0 + r;
+    const double y = gj < p.N ? p.X[(long)gj * M + m] : 0.0;
+    yc[m * EC + r] = cC[m] * y;
+    y2[m * EC + r] = cB[m] * y * y;
+  }
+  __syncthreads();
+
+  const int ty = tid >> 4, tx = tid & 15;
+  const int nsub = RCH / 64;
+  for (int s = 0; s < p.ns; ++s) {
+    const unsigned long long mask = p.masks[s];
+    for (int r = tid; r < RCH; r += ETHREADS) {
+      double a = 0.0;
+      for (int m = 0; m < M; ++m)
+        if ((mask >> m) & 1ull) {
+          const double x = xs[(long)m * RCH + r];
+          a += fma(cA[m] * x, x, cK[m]);
+        }
+      su[r] = a;
+    }
+    if (tid < EC) {
+      double b = 0.0;
+      for (int m = 0; m < M; ++m)
+        if ((mask >> m) & 1ull) b += y2[m * EC + tid];
+      sv[tid] = b;
+    }
+    __syncthreads();
+    double colacc[4] = {0.0, 0.0, 0.0, 0.0};
+    double svv[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) svv[v] = sv[tx * 4 + v];
+    for (int sub = 0; sub < nsub; ++sub) {
+      const int rbase = sub * 64 + ty * 4;
+      double e[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) e[u][v] = su[rbase + u] + svv[v];
+      for (int m = 0; m < M; ++m) {
+        if (!((mask >> m) & 1ull)) continue;
+        double av[4], bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) av[u] = xs[(long)m * RCH + rbase + u];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bv[v] = yc[m * EC + tx * 4 + v];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) e[u][v] = fma(av[u], bv[v], e[u][v]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double w = wl[rbase + u];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) colacc[v] = fma(w, exp(e[u][v]), colacc[v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) red[ty * EC + tx * 4 + v] = colacc[v];
+    __syncthreads();
+    if (tid < EC) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += red[k * EC + tid];
+      p.parts[(((long)job * p.RC + rc) * p.ns + s) * ((long)p.T * EC) + col0 + tid] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- gather: V, the Omega bilinear forms R, and the right-hand sides g0_i * u_li of the triangular solve -----------------------------
+// grid (ns, L*L).  Covariant GP (chol_batch == 1): B is n_pad x ncol, column (s*L + l)*L + i, rows i*N + n.
+// Variant GP (chol_batch == L): problem i has its own N_pad x ncol block at B + i*strideB, column s*L + l, rows n.
+__global__ void sobol_error_gather_kernel(const double* __restrict__ parts, int L, int N, int RC, int ns, long ncols_u, const double* __restrict__ c,
+                                          const double* __restrict__ g0, const double* __restrict__ pre, int chol_batch, double* __restrict__ B,
+                                          long ldb, long strideB, int s_offset, double* __restrict__ V, double* __restrict__ R) {
+  __shared__ double red[32];
+  const int s = blockIdx.x, li = blockIdx.y, l = li / L, i = li - l * L;
+  const int J = 2 * L * L;
+  (void)J;
+  const double* pu = parts + (((long)(0 * L * L + li) * RC) * ns + s) * ncols_u;
+  const double* pw = parts + (((long)(1 * L * L + li) * RC) * ns + s) * ncols_u;
+  const long rc_stride = (long)ns * ncols_u;
+  double vacc = 0.0, racc = 0.0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    double u = 0.0, w = 0.0;
+    for (int r = 0; r < RC; ++r) {
+      u += pu[r * rc_stride + n];
+      w += pw[r * rc_stride + n];
+    }
+    vacc = fma(c[(long)i * N + n], u, vacc);
+    racc = fma(c[(long)l * N + n], w, racc);
+    const double f = g0[(long)i * N + n] * u;
+    if (chol_batch == 1) B[((long)i * N + n) * ldb + ((long)s * L + l) * L + i] = f;
+    else B[(long)i * strideB + (long)n * ldb + (long)s * L + l] = f;
+  }
+  vacc = block_sum(vacc, red);
+  racc = block_sum(racc, red);
+  if (threadIdx.x == 0) {
+    V[((long)(s_offset + s) * L + l) * L + i] = vacc;
+    R[((long)s * L + l) * L + i] = pre[i] * racc;
+  }
+}
+
+// partial[chunk][col] = sum over 128 rows of B[row][col]^2
+__global__ void colnorm_partial_kernel(const double* __restrict__ B, long ldb, long strideB, int ncols, double* __restrict__ partial, long stride_partial) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x, chunk = blockIdx.y, z = blockIdx.z;
+  if (col >= ncols) return;
+  const double* b = B + (long)z * strideB + (long)chunk * 128 * ldb + col;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int r = 0; r < 128; ++r) {
+    const double v = b[(long)r * ldb];
+    acc = fma(v, v, acc);
+  }
+  partial[(long)z * stride_partial + (long)chunk * ncols + col] = acc;
+}
+
+// W[s][l][i] = Wraw[l][i] + Wraw[i][l],  Wraw[l][i] = (R[s][l][i] - |psi_li|^2) * (1 + [l == i])
+__global__ void sobol_error_W_kernel(const double* __restrict__ R, const double* __restrict__ partial, long stride_partial, int chunks, int ncols,
+                                     int L, int ns, int chol_batch, int s_offset, double* __restrict__ W) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ns * L * L) return;
+  const int s = e / (L * L), li = e - s * L * L, l = li / L, i = li - l * L;
+  auto raw = [&](int a, int b) {
+    double psi2 = 0.0;
+    const long col = chol_batch == 1 ? ((long)s * L + a) * L + b : (long)s * L + a;
+    const double* pp = partial + (chol_batch == 1 ? 0 : (long)b * stride_partial) + col;
+    for (int k = 0; k < chunks; ++k) psi2 += pp[(long)k * ncols];
+    return (R[((long)s * L + a) * L + b] - psi2) * (a == b ? 2.0 : 1.0);
+  };
+  W[((long)(s_offset + s) * L + l) * L + i] = raw(l, i) + raw(i, l);
+}
+
+namespace {
+struct ErrLayout {
+  size_t coef, pre, parts, B, partial, R, total;
+  int RCH, RC, T, chunk_slices, ncols;
+  long ldb, strideB;
+};
+inline size_t al(size_t b) { return (b + 255) / 256 * 256; }
+int err_row_chunk(int N, int M) {
+  int rch = (int)((144 * 1024) / (8L * M)) / 64 * 64;
+  if (rch > 1024) rch = 1024;
+  if (rch < 64) rch = 64;
+  const int n64 = (N + 63) / 64 * 64;
+  return rch > n64 ? n64 : rch;
+}
+ErrLayout err_layout(int N, int M, int L, int nslices, int n_pad, int chol_batch) {
+  ErrLayout o{};
+  o.RCH = err_row_chunk(N, M);
+  o.RC = (N + o.RCH - 1) / o.RCH;
+  o.T = (N + EC - 1) / EC;
+  o.chunk_slices = nslices < 32 ? nslices : 32;
+  const int J = 2 * L * L;
+  const int per_problem_cols = chol_batch == 1 ? o.chunk_slices * L * L : o.chunk_slices * L;
+  o.ncols = round_up(per_problem_cols, TILE);
+  o.ldb = o.ncols;
+  o.strideB = (long)n_pad * o.ldb;
+  size_t off = 0;
+  o.coef = off; off += al((size_t)4 * J * M * sizeof(double));
+  o.pre = off; off += al((size_t)L * sizeof(double));
+  o.parts = off; off += al((size_t)J * o.RC * o.chunk_slices * o.T * EC * sizeof(double));
+  o.B = off; off += al((size_t)chol_batch * o.strideB * sizeof(double));
+  o.partial = off; off += al((size_t)chol_batch * (n_pad / 128) * o.ncols * sizeof(double));
+  o.R = off; off += al((size_t)o.chunk_slices * L * L * sizeof(double));
+  o.total = off;
+  return o;
+}
+}  // namespace
+
+size_t sobol_error_workspace_bytes(int N, int M, int L, int nslices, int n_pad, int chol_batch) {
+  return err_layout(N, M, L, nslices, n_pad, chol_batch).total;
+}
+
+int sobol_error(const double* X, int N, int M, const double* Lam, const double* F, const double* Phi, const double* g0, const double* g0KY, int L,
+                const double* Achol, int n_pad, long ld, long strideA, int chol_batch, const double* dinv, const unsigned long long* masks,
+                int nslices, void* work, double* V, double* W, cudaStream_t st) {
+  RC_REQUIRE(M >= 1 && M <= 64, -2, "sobol_error: M=%d out of range [1,64]", M);
+  RC_REQUIRE(chol_batch == 1 || chol_batch == L, -2, "sobol_error: chol_batch must be 1 (covariant) or L (variant)");
+  RC_REQUIRE(n_pad >= (chol_batch == 1 ? L * N : N), -2, "sobol_error: n_pad too small");
+  const ErrLayout lay = err_layout(N, M, L, nslices, n_pad, chol_batch);
+  char* base = static_cast<char*>(work);
+  double* coef = reinterpret_cast<double*>(base + lay.coef);
+  double* pre = reinterpret_cast<double*>(base + lay.pre);
+  double* parts = reinterpret_cast<double*>(base + lay.parts);
+  double* B = reinterpret_cast<double*>(base + lay.B);
+  double* partial = reinterpret_cast<double*>(base + lay.partial);
+  double* R = reinterpret_cast<double*>(base + lay.R);
+  const int J = 2 * L * L;
+  static bool configured = false;
+  if (!configured) {
+    RC_CUDA_OK(cudaFuncSetAttribute(sobol_error_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  sobol_error_coeff_kernel<<<(J * M + 255) / 256, 256, 0, st>>>(Phi, Lam, F, L, M, coef, pre);
+  RC_LAUNCH_OK();
+  const size_t smem = (size_t)(4 * M + (long)M * lay.RCH + lay.RCH + 2 * M * EC + lay.RCH + EC + 16 * EC) * sizeof(double);
+  RC_REQUIRE(smem <= 220 * 1024, -2, "sobol_error: shared memory %zu too large", smem);
+  const int chunks = n_pad / 128;
+  const long stride_partial = (long)chunks * lay.ncols;
+  for (int s0 = 0; s0 < nslices; s0 += lay.chunk_slices) {
+    const int ns = nslices - s0 < lay.chunk_slices ? nslices - s0 : lay.chunk_slices;
+    ErrMatvecArgs a{};
+    a.X = X; a.N = N; a.M = M; a.coef = coef; a.c = g0KY; a.L = L; a.J = J; a.T = lay.T; a.RC = lay.RC; a.RCH = lay.RCH; a.ns = ns; a.parts = parts;
+    for (int s = 0; s < ns; ++s) a.masks[s] = masks[s0 + s];
+    sobol_error_matvec_kernel<<<dim3(lay.T * lay.RC, J), ETHREADS, smem, st>>>(a);
+    RC_LAUNCH_OK();
+    RC_CUDA_OK(cudaMemsetAsync(B, 0, (size_t)chol_batch * lay.strideB * sizeof(double), st));
+    sobol_error_gather_kernel<<<dim3(ns, L * L), 256, 0, st>>>(parts, L, N, lay.RC, ns, (long)lay.T * EC, g0KY, g0, pre, chol_batch, B, lay.ldb,
+                                                               lay.strideB, s0, V, R);
+    RC_LAUNCH_OK();
+    int rc = trsm_lower_fwd(Achol, n_pad, ld, strideA, chol_batch, dinv, B, lay.ncols, lay.ldb, lay.strideB, st);
+    if (rc) return rc;
+    colnorm_partial_kernel<<<dim3((lay.ncols + 127) / 128, chunks, chol_batch), 128, 0, st>>>(B, lay.ldb, lay.strideB, lay.ncols, partial,
+                                                                                                 stride_partial);
+    RC_LAUNCH_OK();
+    sobol_error_W_kernel<<<(ns * L * L + 127) / 128, 128, 0, st>>>(R, partial, stride_partial, chunks, lay.ncols, L, ns, chol_batch, s0, W);
+    RC_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // namespace rc

@@ -2,7 +2,7 @@
 
 The precomputation (Phi, g0, mean-centred g0KY) is rc_sobol_prepare; every marginal variance V(m) is the fused
 integrand + contraction kernel rc_sobol_contract, which takes a whole list of marginal subsets per launch (``marginalize_many``).
-``ClosedSobolWithError`` (the T/W error terms, reference :146-402) is not part of this build."""
+``ClosedSobolWithError`` (the T/W error terms, reference :146-402) adds rc_sobol_error (diagonal F, is_T_partial)."""
 from __future__ import annotations
 
 from romcomma.base.definitions import *
@@ -103,11 +103,44 @@ class ClosedSobol(gf.Module, Calibrator):
 
 
 class ClosedSobolWithError(ClosedSobol):
-    """ Sobol indices with errors (T, W): not part of this build."""
+    """ Closed Sobol indices with their standard errors T and the covariances W behind them (reference calibrators.py:146-402).
+
+    As in the reference the kernel variance F must be diagonal (``:380-381``).  ``is_T_partial=True`` (the default ``META`` and what all of
+    the reference's scripts run) asserts that the full model is variance free; the non-partial variant (MIXED rank equations, ``WMm``, ``Q``)
+    is not implemented on the device path.  One rc_sobol_error call evaluates, for every requested marginal subset, the _psi_factor /
+    Upsilon / Omega Gaussian chains as fused pairwise kernels and the triangular solve with K_cho as a single TRSM; V comes out as a by-product.
+    """
 
     @classproperty
     def META(cls) -> Dict[str, Any]:
+        """ ``is_T_partial`` forces W[Mm] = W[MM] = 0."""
         return {'is_T_partial': True}
 
-    def __init__(self, gp: GPR, **kwargs: Any):
-        raise NotImplementedError('ClosedSobolWithError (the T/W error terms) is outside the accelerated hot path of this build.')
+    def _calibrate(self):
+        super()._calibrate()
+        if not self.is_F_diagonal:
+            raise NotImplementedError('If the MOGP kernel covariance is not diagonal, the Sobol error calculation is unstable.')
+        if not self.meta.get('is_T_partial', True):
+            raise NotImplementedError('is_T_partial=False (the MIXED rank equations) is not implemented on the B200 path.')
+        self.Upsilon = self.Lambda2[-1][2]
+        self.V |= {4: HostTensor(self.V[2].numpy() * self.V[2].numpy())}
+        pre = np.sqrt(np.prod(self.Lambda2[1][0].numpy() * self.Lambda2[-1][2].numpy(), axis=-1)) * self.F.numpy()
+        self.mu_phi_mu = {'pre-factor': HostTensor(pre.reshape(-1))}
+        self._fac = self.gp._factorize()[0]                              # K_cho with its solve workspace, resident for the whole sweep
+        self._Lam_d, self._F_d = _capi.dev(self.Lambda.numpy()), _capi.dev(self.F.numpy().reshape(-1))
+        self._g0_d = self.g0.as_subclass(torch.Tensor).reshape(self.L, self.N).contiguous()
+        self.W = HostTensor(self._VW_many([_capi.slice_mask(0, self.M)])[1][0])
+
+    def _VW_many(self, masks: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+        V, W = _capi.sobol_error(self._Xd, self._Lam_d, self._F_d, self._Phi_d, self._g0_d, self._g0KY_d, self._fac, masks)
+        return V.cpu().numpy(), W.cpu().numpy()
+
+    def _results(self, V: np.ndarray, W: np.ndarray) -> List[Dict[str, HostTensor]]:
+        V2, V4 = self.V[2].numpy(), self.V[4].numpy()
+        return [{'V': HostTensor(v), 'S': HostTensor(v / V2), 'W': HostTensor(w), 'T': HostTensor(np.sqrt(np.abs(w) / V4))} for v, w in zip(V, W)]
+
+    def marginalize_many(self, slices: Sequence[Sequence[int]]) -> List[Dict[str, HostTensor]]:
+        return self._results(*self._VW_many([_capi.slice_mask(int(m[0]), int(m[1])) for m in slices]))
+
+    def marginalize_subsets(self, subsets: Sequence[Sequence[int]]) -> List[Dict[str, HostTensor]]:
+        return self._results(*self._VW_many([sum(1 << int(i) for i in set(s)) for s in subsets]))

@@ -29,7 +29,7 @@ class GSA(Model):
             gp: The underlying Gaussian Process.
             kind: first order, closed or total.
             m: A single input ``0 <= m < gp.M``, or anything else for all of ``range(M)``.
-            is_error_calculated: Whether to calculate the standard error on the index (not available in this build).
+            is_error_calculated: Whether to calculate the standard error T (and the covariances W) of the index.
             **kwargs: The calculation meta to override META.
         """
         self.gp, self.kind, self.is_error_calculated = gp, kind, is_error_calculated
@@ -120,4 +120,8 @@ class Sobol(GSA):
         results['V'] = np.concatenate([results['V'], V0], axis=-1)
         S = S0 - results['S'] if self.kind == GSA.Kind.TOTAL else results['S']
         results['S'] = np.concatenate([S, S0], axis=-1)
+        if 'T' in results and not self.meta['is_T_partial']:     # reference models.py:211-213; unreachable here: the calibrator refuses is_T_partial=False
+            T0 = np.asarray(calibrator.T)[..., None]
+            T = T0 + results['T'] if self.kind == GSA.Kind.TOTAL else results['T']
+            results['T'] = np.concatenate([T, T0], axis=-1)
         return results

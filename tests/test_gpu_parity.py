@@ -254,3 +254,35 @@ def test_full_size_properties_cfg3(C):
     for l in range(L):
         ref = 0.5 * ((ky[l * N:(l + 1) * N] ** 2).sum() - Kinv[l * N:(l + 1) * N, l * N:(l + 1) * N].diagonal().sum()).item()
         assert_close(a[0, 1 + L * L + l * L + l].item(), ref, rtol=1e-8, atol=1e-6, what=f'dE[{l},{l}]')
+
+
+# ---- Sobol errors (ClosedSobolWithError) -----------------------------------------------------------------------------------
+@pytest.mark.parametrize('N,M,L,covariant', [(50, 3, 2, True), (130, 5, 3, True), (70, 2, 1, False), (200, 20, 2, False), (257, 12, 3, True)])
+def test_sobol_error_matches_oracle(C, N, M, L, covariant):
+    """rc_sobol_error (V and W for a list of marginal subsets, incl. non-contiguous and empty ones) against oracle/sobol_error.py."""
+    from oracle import sobol_error
+    X, Y, ls, F, E = random_problem(N, M, L, seed=N + M, full_E=False)
+    if covariant:
+        KiY, cho = gp.k_inv_y_mo(X, Y, ls, F, E), gp.k_cho_mo(X, ls, F, E)
+        K = C.gram(C.dev(X), None, C.dev(ls), C.dev(F[None]), C.dev(E[None]), lower_only=True, pad_to=L * N, pad_identity=True)
+    else:
+        var, noise = np.diag(F).copy(), np.diag(E).copy()
+        KiY, cho = gp.k_inv_y_rbf(X, Y, ls, var, noise), gp.k_cho_rbf(X, ls, var, noise)
+        K = C.gram(C.dev(X), None, C.dev(ls), C.dev(var.reshape(L, 1, 1)), C.dev(noise.reshape(L, 1, 1)), batch=L, lower_only=True, pad_to=N,
+                   pad_identity=True)
+    fac = C.Factorization(K)
+    fac.raise_if_failed()
+    ref = sobol_error.ClosedSobolWithError(X, ls, np.diag(F), KiY, cho)
+    dX, dLam, dF = C.dev(X), C.dev(ls), C.dev(np.diag(F).copy())
+    Phi, g0, g0KY = C.sobol_prepare(dX, dLam, dF, C.dev(KiY.reshape(L, N)), True)
+    subsets = [list(range(M)), [0], [M - 1], list(range(1, M)), [], [0, M - 1], list(range(0, M, 2))]
+    masks = [sum(1 << i for i in set(s)) for s in subsets]
+    V, W = C.sobol_error(dX, dLam, dF, Phi, g0, g0KY, fac, masks)
+    V, W = V.cpu().numpy(), W.cpu().numpy()
+    for k, sub in enumerate(subsets):
+        perm = sub + [i for i in range(M) if i not in sub]
+        rp = sobol_error.ClosedSobolWithError(X[:, perm], ls[:, perm], np.diag(F), KiY, cho)       # subset as a prefix slice
+        out = rp.marginalize((0, len(sub)))
+        assert_close(V[k], out['V'], rtol=1e-7, atol=1e-10, what=f'V {sub}')
+        assert_close(W[k], out['W'], rtol=1e-7, atol=1e-10, what=f'W {sub}')
+    assert_close(W[0], ref.W, rtol=1e-7, atol=1e-10, what='full-model W')
