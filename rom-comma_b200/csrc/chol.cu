@@ -7,7 +7,7 @@
 // matrices are `strideA` doubles apart.  `dinv` holds one 128x128 inverse per diagonal block (upper triangle zero):
 // block b of batch z lives at dinv + z*strideD + b*128*128.
 #include "chol.h"
-#include "gemm_dmma.cuh"
+#include "gemm_dmma_ws.cuh"
 
 namespace rc {
 
@@ -247,7 +247,7 @@ int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv
     g.B = dinv + (long)blk * DB * DB; g.ldb = DB; g.strideB = strideD;
     g.C = A + (long)r0 * ld + (long)blk * DB; g.ldc = ld; g.strideC = strideA;
     g.M = n - r0; g.N = DB; g.K = DB; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kmode = K_FULL;
-    return launch_gemm<false, false>(g, batch, st);
+    return launch_gemm_ws<false, false>(g, batch, st);
   };
   for (int b0 = 0; b0 < nblk; b0 += 2) {
     const int w = (b0 + 1 < nblk) ? 2 : 1;
@@ -261,7 +261,7 @@ int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv
       g.B = A + r0 * ld + (long)b0 * DB; g.ldb = ld; g.strideB = strideA;
       g.C = A + r0 * ld + r0; g.ldc = ld; g.strideC = strideA;
       g.M = n - (int)r0; g.N = DB; g.K = DB; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kmode = K_FULL;
-      if ((rc = launch_gemm<false, false>(g, batch, st))) return rc;
+      if ((rc = launch_gemm_ws<false, false>(g, batch, st))) return rc;
       if ((rc = launch_diag(A, ld, strideA, dinv, strideD, b0 + 1, logdet_parts, nblk, info, batch, st))) return rc;
       if ((rc = trsm_panel(b0 + 1))) return rc;
     }
@@ -272,7 +272,7 @@ int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv
       g.B = g.A; g.ldb = ld; g.strideB = strideA;
       g.C = A + r0 * ld + r0; g.ldc = ld; g.strideC = strideA;
       g.M = g.N = n - (int)r0; g.K = w * DB; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1; g.kmode = K_FULL;
-      if ((rc = launch_gemm<false, false>(g, batch, st))) return rc;
+      if ((rc = launch_gemm_ws<false, false>(g, batch, st))) return rc;
     }
   }
   return 0;
@@ -382,7 +382,7 @@ int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, con
     g.B = B + (long)k * DB * ldb; g.ldb = ldb; g.strideB = strideB;
     g.C = B + (long)k * DB * ldb; g.ldc = ldb; g.strideC = strideB;
     g.M = DB; g.N = nrhs; g.K = DB; g.alpha = 1.0; g.beta = 0.0; g.kmode = K_FULL;
-    if ((rc = launch_gemm<false, true>(g, batch, st))) return rc;
+    if ((rc = launch_gemm_ws<false, true>(g, batch, st))) return rc;
     const int r0 = (k + 1) * DB;
     if (r0 < n) {   // B[i>k] -= L[i,k] * B_k
       GemmArgs u{};
@@ -390,7 +390,7 @@ int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, con
       u.B = B + (long)k * DB * ldb; u.ldb = ldb; u.strideB = strideB;
       u.C = B + (long)r0 * ldb; u.ldc = ldb; u.strideC = strideB;
       u.M = n - r0; u.N = nrhs; u.K = DB; u.alpha = -1.0; u.beta = 1.0; u.kmode = K_FULL;
-      if ((rc = launch_gemm<false, true>(u, batch, st))) return rc;
+      if ((rc = launch_gemm_ws<false, true>(u, batch, st))) return rc;
     }
   }
   return 0;
@@ -432,13 +432,13 @@ int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double
         g.B = Az; g.ldb = ld; g.strideB = 2 * h * (ld + 1);
         g.C = Tz; g.ldc = h; g.strideC = h * h;
         g.M = (int)h2; g.N = (int)h; g.K = (int)h; g.alpha = 1.0; g.beta = 0.0; g.kmode = K_GE_N0;
-        if ((rc = launch_gemm<false, true>(g, count, st))) return rc;
+        if ((rc = launch_gemm_ws<false, true>(g, count, st))) return rc;
         GemmArgs u{};   // Z21 = -Z22 * T    (Z22 lower, stored [m][k]  ->  k < m0 + 128)
         u.A = Az + h * ld + h; u.lda = ld; u.strideA = 2 * h * (ld + 1);
         u.B = Tz; u.ldb = h; u.strideB = h * h;
         u.C = Az + h * ld; u.ldc = ld; u.strideC = 2 * h * (ld + 1);
         u.M = (int)h2; u.N = (int)h; u.K = (int)h2; u.alpha = -1.0; u.beta = 0.0; u.kmode = K_LT_M1;
-        if ((rc = launch_gemm<false, true>(u, count, st))) return rc;
+        if ((rc = launch_gemm_ws<false, true>(u, count, st))) return rc;
       }
     }
   }
@@ -454,7 +454,7 @@ int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double
   g.B = Z; g.ldb = ld; g.strideB = strideZ;
   g.C = Kinv; g.ldc = ldk; g.strideC = strideK;
   g.M = g.N = g.K = n; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 1; g.kmode = K_GE_M0;
-  return launch_gemm<true, true>(g, batch, st);
+  return launch_gemm_ws<true, true>(g, batch, st);
 }
 
 // dots[pair(l > l')][i] = sum_{k >= l*N+i} Z[k][l*N+i] * Z[k][l'*N+i] = K^-1[(l,i),(l',i)]: the diagonals of the off-diagonal

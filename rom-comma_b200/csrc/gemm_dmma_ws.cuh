@@ -1,0 +1,273 @@
+// Warp-specialised FP64 tensor-core (DMMA.8x8x4) tile GEMM: same contract as gemm_dmma.cuh (C = alpha * Aop * Bop^T + beta * C over a
+// persistent tile list, triangular structure at tile granularity), different feed.
+//
+//   * one PRODUCER warp streams operand tiles global -> shared with TMA bulk copies (cp.async.bulk, SASS UBLKCP) that complete on an
+//     mbarrier per stage ("full"); it runs ahead of the math across tile boundaries, limited only by the ring depth;
+//   * eight CONSUMER warps (2 x 4, warp tile 64 x 32 = 8 x 4 DMMA tiles, accumulators in registers - FP64 has no tcgen05/TMEM path)
+//     wait on "full", issue DMMA from shared memory and release the stage through an "empty" mbarrier.  There is no CTA-wide
+//     barrier anywhere in the main loop or the epilogue, so the two warps that share a tensor pipe drift apart and keep it busy
+//     while the other one waits, loads fragments or writes its C sub-tile.
+//
+// Operand staging, by storage order of the operand:
+//   * k-contiguous operands ([m][k], "non-transposed"): ONE cp.async.bulk.tensor (TMA tiled load, SASS UTMALDG) per stage through a
+//     CUtensorMap built per launch, box 16 (k) x 128 (rows) doubles, SWIZZLE_128B: the 16-byte chunk index of a 128-byte row is
+//     XORed with (row & 7), which makes every warp fragment read (8 rows x 4 k) hit all 32 banks twice = the 2-wavefront minimum,
+//     without padding.  (128 separate 128-byte bulk copies per stage are TMA-issue bound: measured 10.5 TFLOP/s.)
+//   * m-contiguous operands ([k][m], "transposed"): 16 one-dimensional bulk copies of 1 KB (SASS UBLKCP) into rows padded by 4 doubles.
+#pragma once
+#include "gemm_dmma.cuh"
+#include <cuda.h>
+#include <cstring>
+
+namespace rc {
+
+constexpr int W_STAGES = 6, W_CONSUMERS = 8, W_THREADS = 32 * (W_CONSUMERS + 1);
+
+template <bool TA, bool TB>
+struct GemmWsSmem {
+  static constexpr int A_STAGE = TA ? G_BK * (G_BM + G_PAD) : G_BM * G_BK;   // doubles; k-contiguous operands are dense + swizzled
+  static constexpr int B_STAGE = TB ? G_BK * (G_BN + G_PAD) : G_BN * G_BK;
+  static constexpr size_t up1k(size_t b) { return (b + 1023) / 1024 * 1024; }
+  static constexpr size_t A_BYTES = up1k((size_t)W_STAGES * A_STAGE * sizeof(double));
+  static constexpr size_t B_BYTES = up1k((size_t)W_STAGES * B_STAGE * sizeof(double));
+  static constexpr size_t BYTES = 1024 + A_BYTES + B_BYTES + 2 * W_STAGES * sizeof(unsigned long long);   // + slack to align the base to 1 KB
+  static constexpr unsigned STAGE_TX = 2u * G_BM * G_BK * sizeof(double);   // bytes landing per stage
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_g2s_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// One operand stage by the producer warp.  Transposed storage: 16 rows of 1 KB, one bulk copy per lane.  k-contiguous storage: one
+// tiled TMA load of the 16 x 128 box at (k, row, z) relative to the operand pointer the tensor map was built on.
+template <bool T>
+__device__ __forceinline__ void ws_load_operand(double* dst, const double* src, long ld, const CUtensorMap* map, int z, int mn0, int k0, int lane,
+                                                unsigned long long* bar) {
+  if (!T) {
+    if (lane == 0) tma_g2s_3d(dst, map, k0, mn0, z, bar);
+  } else {
+    if (lane < G_BK) bulk_g2s(dst + lane * (G_BM + G_PAD), src + (long)(k0 + lane) * ld + mn0, G_BM * sizeof(double), bar);
+  }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, long tiles_per_matrix, long total_tiles,
+                                                                    const __grid_constant__ CUtensorMap mapA,
+                                                                    const __grid_constant__ CUtensorMap mapB) {
+  extern __shared__ __align__(16) double smem_raw[];
+  using S = GemmWsSmem<TA, TB>;
+  // SWIZZLE_128B needs its tiles on 1 KB boundaries of the shared address space
+  char* base = reinterpret_cast<char*>(smem_raw) + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  double* As = reinterpret_cast<double*>(base);
+  double* Bs = reinterpret_cast<double*>(base + S::A_BYTES);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(base + S::A_BYTES + S::B_BYTES);
+  unsigned long long* empty = full + W_STAGES;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < W_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, W_CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == W_CONSUMERS) {
+    // ---------------------------------------------------------------- producer
+    int stage = 0;
+    unsigned phase = 0;
+    for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const GemmTile T = gemm_decode_tile(p, tile, tiles_per_matrix);
+      const int z = (int)(tile / tiles_per_matrix);
+      for (int kt = 0; kt < T.nk; ++kt) {
+        mbar_wait(empty + stage, phase ^ 1u);
+        if (lane == 0) mbar_arrive_expect_tx(full + stage, S::STAGE_TX);
+        __syncwarp();
+        ws_load_operand<TA>(As + stage * S::A_STAGE, T.A, p.lda, &mapA, z, T.m0, T.kb + kt * G_BK, lane, full + stage);
+        ws_load_operand<TB>(Bs + stage * S::B_STAGE, T.B, p.ldb, &mapB, z, T.n0, T.kb + kt * G_BK, lane, full + stage);
+        if (++stage == W_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumers
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g = lane >> 2, t = lane & 3;
+  const int swz = ((t >> 1) ^ g), todd = t & 1;    // swizzled k-contiguous tiles: double index = row*16 + (((2*kk) ^ swz) << 1) + todd
+  int stage = 0;
+  unsigned phase = 0;
+  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const GemmTile T = gemm_decode_tile(p, tile, tiles_per_matrix);
+    if (T.nk < 0) continue;
+    if (p.beta != 0.0) {   // pull this warp's 64 x 32 part of C (64 rows x 256 B) towards L2 while the main loop runs
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int line = lane + r * 32;                 // 128 lines of 128 B
+        const double* addr = T.C + (long)(T.m0 + wm * 64 + (line >> 1)) * p.ldc + T.n0 + wn * 32 + (line & 1) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+      }
+    }
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < T.nk; ++kt) {
+      mbar_wait(full + stage, phase);
+      __syncwarp();
+      const double* as = As + stage * S::A_STAGE;
+      const double* bs = Bs + stage * S::B_STAGE;
+#pragma unroll
+      for (int kk = 0; kk < G_BK / 4; ++kk) {
+        double a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          a[i] = TA ? as[(kk * 4 + t) * (G_BM + G_PAD) + wm * 64 + i * 8 + g] : as[(wm * 64 + i * 8 + g) * G_BK + (((2 * kk) ^ swz) << 1) + todd];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          b[j] = TB ? bs[(kk * 4 + t) * (G_BN + G_PAD) + wn * 32 + j * 8 + g] : bs[(wn * 32 + j * 8 + g) * G_BK + (((2 * kk) ^ swz) << 1) + todd];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      // Release the stage to the producer.  The fragment loads above are generic-proxy reads, the refill is an async-proxy (TMA) write:
+      // without a cross-proxy fence ptxas may schedule the arrive right after the last LDS is *issued* and the bulk copy of the next
+      // lap can overtake its second (bank-conflict) wavefront - observed as rare stale 8x8 fragments before this fence was added.
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + stage);
+      if (++stage == W_STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    // Every operand byte of this tile has landed in shared memory (this warp waited on the tile's last "full" barrier), so the
+    // tile-exclusive in-place updates the drivers rely on (C aliasing A or B of the SAME tile) stay safe.
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long row = T.m0 + wm * 64 + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = T.n0 + wn * 32 + j * 8 + t * 2;
+        double2* cp = reinterpret_cast<double2*>(T.C + row * p.ldc + col);
+        double2 v;
+        if (beta == 0.0) {
+          v.x = alpha * acc[i][j][0];
+          v.y = alpha * acc[i][j][1];
+        } else {
+          const double2 o = *cp;
+          v.x = fma(alpha, acc[i][j][0], beta * o.x);
+          v.y = fma(alpha, acc[i][j][1], beta * o.y);
+        }
+        *cp = v;
+      }
+    }
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                           const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                           CUtensorMapFloatOOBfill);
+inline TensorMapEncodeTiledFn tensor_map_encoder() {
+  static TensorMapEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Tensor map over a k-contiguous operand: dims (k, rows, batch), box 16 x 128 x 1 doubles, 128-byte swizzle.
+inline int make_operand_map(CUtensorMap* map, const double* ptr, long ld, long stride, int rows, int K, int batch) {
+  TensorMapEncodeTiledFn enc = tensor_map_encoder();
+  RC_REQUIRE(enc != nullptr, -3, "gemm_dmma_ws: cuTensorMapEncodeTiled is not available from this driver");
+  const bool batched = batch > 1 && stride != 0;
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batched ? batch : 1)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(double), (cuuint64_t)(batched ? stride : (long)rows * ld) * sizeof(double)};
+  const cuuint32_t box[3] = {(cuuint32_t)G_BK, (cuuint32_t)G_BM, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RC_REQUIRE(r == CUDA_SUCCESS, -3, "gemm_dmma_ws: cuTensorMapEncodeTiled failed (%d) for ptr=%p ld=%ld stride=%ld rows=%d K=%d batch=%d", (int)r,
+             (const void*)ptr, ld, stride, rows, K, batch);
+  return 0;
+}
+
+template <bool TA, bool TB>
+inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream) {
+  using S = GemmWsSmem<TA, TB>;
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    RC_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_ws_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
+    int dev = 0;
+    RC_CUDA_OK(cudaGetDevice(&dev));
+    RC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  if (a.M <= 0 || a.N <= 0 || batch <= 0) return 0;
+  RC_REQUIRE(a.M % G_BM == 0 && a.N % G_BN == 0 && a.K % G_BK == 0, -2, "gemm_dmma_ws: M,N must be multiples of 128 and K of 16 (got %d,%d,%d)", a.M,
+             a.N, a.K);
+  RC_REQUIRE(a.lda % 2 == 0 && a.ldb % 2 == 0 && a.ldc % 2 == 0, -2, "gemm_dmma_ws: leading dimensions must be even (16-byte rows)");
+  const long tm = a.M / G_BM, tn = a.N / G_BN;
+  const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  const long total = tiles * batch;
+  const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
+  alignas(64) CUtensorMap mapA, mapB;
+  memset(&mapA, 0, sizeof(mapA));
+  memset(&mapB, 0, sizeof(mapB));
+  int rc;
+  if (!TA && (rc = make_operand_map(&mapA, a.A, a.lda, a.strideA, a.M, a.K, batch))) return rc;
+  if (!TB && (rc = make_operand_map(&mapB, a.B, a.ldb, a.strideB, a.N, a.K, batch))) return rc;
+  const bool prof = profile_enabled();
+  if (prof) profile_gemm_begin(stream);
+  gemm_dmma_ws_kernel<TA, TB><<<grid, W_THREADS, S::BYTES, stream>>>(a, tiles, total, mapA, mapB);
+  if (prof) profile_gemm_end(stream, gemm_tile_flops(a, batch));
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace rc
