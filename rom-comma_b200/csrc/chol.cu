@@ -9,7 +9,30 @@
 #include "chol.h"
 #include "gemm_dmma_ws.cuh"
 
+#include <atomic>
+#include <mutex>
+
 namespace rc {
+
+// Scheduler scratch of the warp-specialised GEMM (see gemm_dmma_ws.cuh): per device, allocated and zeroed on first use.
+int* gemm_sched_slot(int device) {
+  constexpr int MAX_DEV = 64;
+  static int* base[MAX_DEV] = {nullptr};
+  static std::atomic<unsigned> seq[MAX_DEV];
+  static std::mutex mu;
+  if (device < 0 || device >= MAX_DEV) return nullptr;
+  if (!base[device]) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!base[device]) {
+      int* p = nullptr;
+      if (cudaMalloc(&p, (size_t)SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+      if (cudaMemset(p, 0, (size_t)SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;   // synchronous: ordered before any launch
+      base[device] = p;
+    }
+  }
+  const unsigned s = seq[device].fetch_add(1u, std::memory_order_relaxed) % SCHED_SLOTS;
+  return base[device] + 2 * s;
+}
 
 // ----------------------------------------------------------------------------------------------------------------
 // Diagonal block: L = chol(A_kk) in place (lower part only is read/written), Dinv = L^-1, partial log-determinant.

@@ -7,6 +7,11 @@
 //     wait on "full", issue DMMA from shared memory and release the stage through an "empty" mbarrier.  There is no CTA-wide
 //     barrier anywhere in the main loop or the epilogue, so the two warps that share a tensor pipe drift apart and keep it busy
 //     while the other one waits, loads fragments or writes its C sub-tile.
+//   * tiles are handed out DYNAMICALLY: the producer draws the next tile index from a global counter (one atomicAdd per tile) and
+//     passes it to the consumers through a 4-entry shared-memory ring.  Tile lists are ordered by decreasing K range, so with
+//     triangular K ranges (trtri, LAUUM) and skipped tiles ("selected" LAUUM) every SM stays busy until the list is empty
+//     (static striding left the selected LAUUM at 59 % of peak).  Each tile is still computed by one CTA in a fixed order of
+//     operations: results are bitwise independent of the schedule.
 //
 // Operand staging, by storage order of the operand:
 //   * k-contiguous operands ([m][k], "non-transposed"): ONE cp.async.bulk.tensor (TMA tiled load, SASS UTMALDG) per stage through a
@@ -21,7 +26,7 @@
 
 namespace rc {
 
-constexpr int W_STAGES = 6, W_CONSUMERS = 8, W_THREADS = 32 * (W_CONSUMERS + 1);
+constexpr int W_STAGES = 6, W_CONSUMERS = 8, W_THREADS = 32 * (W_CONSUMERS + 1), W_RING = 4;
 
 template <bool TA, bool TB>
 struct GemmWsSmem {
@@ -30,7 +35,7 @@ struct GemmWsSmem {
   static constexpr size_t up1k(size_t b) { return (b + 1023) / 1024 * 1024; }
   static constexpr size_t A_BYTES = up1k((size_t)W_STAGES * A_STAGE * sizeof(double));
   static constexpr size_t B_BYTES = up1k((size_t)W_STAGES * B_STAGE * sizeof(double));
-  static constexpr size_t BYTES = 1024 + A_BYTES + B_BYTES + 2 * W_STAGES * sizeof(unsigned long long);   // + slack to align the base to 1 KB
+  static constexpr size_t BYTES = 1024 + A_BYTES + B_BYTES + (2 * W_STAGES + 2 * W_RING) * sizeof(unsigned long long) + W_RING * sizeof(int);
   static constexpr unsigned STAGE_TX = 2u * G_BM * G_BK * sizeof(double);   // bytes landing per stage
 };
 
@@ -82,7 +87,7 @@ __device__ __forceinline__ void ws_load_operand(double* dst, const double* src, 
 }
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, long tiles_per_matrix, long total_tiles,
+__global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, long tiles_per_matrix, long total_tiles, int* __restrict__ sched,
                                                                     const __grid_constant__ CUtensorMap mapA,
                                                                     const __grid_constant__ CUtensorMap mapB) {
   extern __shared__ __align__(16) double smem_raw[];
@@ -93,6 +98,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
   double* Bs = reinterpret_cast<double*>(base + S::A_BYTES);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(base + S::A_BYTES + S::B_BYTES);
   unsigned long long* empty = full + W_STAGES;
+  unsigned long long* tfull = empty + W_STAGES;     // tile-index ring: producer -> consumers
+  unsigned long long* tempty = tfull + W_RING;
+  volatile int* ring = reinterpret_cast<volatile int*>(tempty + W_RING);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -101,16 +109,43 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
       mbar_init(full + s, 1);
       mbar_init(empty + s, W_CONSUMERS);
     }
+#pragma unroll
+    for (int s = 0; s < W_RING; ++s) {
+      mbar_init(tfull + s, 1);
+      mbar_init(tempty + s, W_CONSUMERS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
   if (warp == W_CONSUMERS) {
     // ---------------------------------------------------------------- producer
-    int stage = 0;
-    unsigned phase = 0;
-    for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const GemmTile T = gemm_decode_tile(p, tile, tiles_per_matrix);
+    int stage = 0, slot = 0;
+    unsigned phase = 0, tphase = 0;
+    for (;;) {
+      long tile = -1;
+      GemmTile T;
+      for (;;) {   // draw tiles until one has work (skipped tiles of a selected list cost one decode)
+        int t = 0;
+        if (lane == 0) t = atomicAdd(sched, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= total_tiles) break;
+        T = gemm_decode_tile(p, t, tiles_per_matrix);
+        if (T.nk >= 0) {
+          tile = t;
+          break;
+        }
+      }
+      mbar_wait(tempty + slot, tphase ^ 1u);
+      if (lane == 0) {
+        ring[slot] = (int)tile;
+        mbar_arrive(tfull + slot);      // release: the consumers' acquire on tfull sees the index
+      }
+      if (++slot == W_RING) {
+        slot = 0;
+        tphase ^= 1u;
+      }
+      if (tile < 0) break;
       const int z = (int)(tile / tiles_per_matrix);
       for (int kt = 0; kt < T.nk; ++kt) {
         mbar_wait(empty + stage, phase ^ 1u);
@@ -124,6 +159,15 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
         }
       }
     }
+    // The last CTA to run dry re-arms the counter pair for the next launch that uses this slot.
+    if (lane == 0) {
+      const int done = atomicAdd(sched + 1, 1);
+      if (done == (int)gridDim.x - 1) {
+        sched[0] = 0;
+        sched[1] = 0;
+        __threadfence();
+      }
+    }
     return;
   }
 
@@ -131,11 +175,19 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
   const int wm = warp >> 2, wn = warp & 3;
   const int g = lane >> 2, t = lane & 3;
   const int swz = ((t >> 1) ^ g), todd = t & 1;    // swizzled k-contiguous tiles: double index = row*16 + (((2*kk) ^ swz) << 1) + todd
-  int stage = 0;
-  unsigned phase = 0;
-  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  int stage = 0, slot = 0;
+  unsigned phase = 0, tphase = 0;
+  for (;;) {
+    mbar_wait(tfull + slot, tphase);
+    const int tile = ring[slot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty + slot);
+    if (++slot == W_RING) {
+      slot = 0;
+      tphase ^= 1u;
+    }
+    if (tile < 0) break;
     const GemmTile T = gemm_decode_tile(p, tile, tiles_per_matrix);
-    if (T.nk < 0) continue;
     if (p.beta != 0.0) {   // pull this warp's 64 x 32 part of C (64 rows x 256 B) towards L2 while the main loop runs
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -236,15 +288,20 @@ inline int make_operand_map(CUtensorMap* map, const double* ptr, long ld, long s
   return 0;
 }
 
+// Per-device scratch of {next tile, CTAs done} counter pairs for the dynamic tile scheduler: the one piece of device memory this
+// library allocates itself (32 KB, once per device, zero-initialised; every launch takes the next pair and leaves it zeroed).
+constexpr int SCHED_SLOTS = 4096;
+int* gemm_sched_slot(int device);   // defined in chol.cu
+
 template <bool TA, bool TB>
 inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream) {
   using S = GemmWsSmem<TA, TB>;
   static bool configured = false;
   static int num_sms = 0;
+  int dev = 0;
+  RC_CUDA_OK(cudaGetDevice(&dev));
   if (!configured) {
     RC_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_ws_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
-    int dev = 0;
-    RC_CUDA_OK(cudaGetDevice(&dev));
     RC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
@@ -264,7 +321,9 @@ inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream) {
   if (!TB && (rc = make_operand_map(&mapB, a.B, a.ldb, a.strideB, a.N, a.K, batch))) return rc;
   const bool prof = profile_enabled();
   if (prof) profile_gemm_begin(stream);
-  gemm_dmma_ws_kernel<TA, TB><<<grid, W_THREADS, S::BYTES, stream>>>(a, tiles, total, mapA, mapB);
+  int* sched = gemm_sched_slot(dev);
+  RC_REQUIRE(sched != nullptr, -3, "gemm_dmma_ws: could not allocate the tile-scheduler scratch");
+  gemm_dmma_ws_kernel<TA, TB><<<grid, W_THREADS, S::BYTES, stream>>>(a, tiles, total, sched, mapA, mapB);
   if (prof) profile_gemm_end(stream, gemm_tile_flops(a, batch));
   RC_LAUNCH_OK();
   return 0;
