@@ -14,6 +14,7 @@
 // Partial sums are written per CTA and reduced in a fixed order: bitwise reproducible, no atomics.
 #include "sobol.h"
 #include "common.cuh"
+#include <vector>
 
 namespace rc {
 
@@ -205,6 +206,227 @@ __global__ void __launch_bounds__(STHREADS) sobol_pair_kernel(SobolPairArgs p) {
   }
 }
 
+
+// ---- sweep form -----------------------------------------------------------------------------------------------------
+// The integrand factorises over the inputs:  H_s[N,n] = prod_{m in s} h_m[N,n],  h_m = exp( su_m[N] + sv_m[n] + gamma_m x_Nm y_nm ).
+// For the slice families the reference sweeps (gsa/models.py:77-90: first order [m:m+1], closed [0:m+1], total-complement [m+1:M], plus the
+// full and the empty slice) that means M exps per sample pair instead of 3M+1: singles are the h_m themselves, closed slices their
+// running prefix products and complements the suffix products.  (Single-input exponents are bounded by gamma (1-p) x^2 with |x| <= 7.04 after
+// the probit normalisation, far from the FP64 range limits; a factor that underflows gives 0 where the summed form gives < 1e-300.)
+// Output per (pair of output rows, tile): 3M values  { F[m] m<M | P[k] k=1..M | S[k] k=1..M-1 | E },
+//   F[m] = sum w h_m,  P[k] = sum w prod_{j<k} h_j,  S[k] = sum w prod_{j>=k} h_j,  E = sum w   (w = c_aN c_bn).
+// Thread (ty,tx) of the 16x16 block evaluates RU x 2 pairs per pass.  The 3M accumulators stay in registers; the h values of a pass are
+// parked in shared memory (thread-private columns, conflict-free) between the prefix and the suffix scan so that two CTAs fit on an SM:
+// the kernel is bound by the latency of the exp dependency chains, not by issue slots.
+template <int MAXM, int RU>
+__global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int M = p.M, nv = 3 * M;
+  double* gam = sm;                 // [M]
+  double* cu = gam + M;             // -1/2 gamma p
+  double* cv = cu + M;              // -1/2 gamma q
+  double* lp = cv + M;              // -1/2 log psi
+  double* gx = lp + M;              // [M][64]  gamma_m * x (rows)
+  double* yy = gx + M * ST;         // [M][64]  y (columns)
+  double* su = yy + M * ST;         // [M][64]  cu_m x^2 + lp_m
+  double* sv = su + M * ST;         // [M][64]  cv_m y^2
+  double* cr = sv + M * ST;         // [64]
+  double* cc = cr + ST;             // [64]
+  double* wpart = cc + ST;          // [8][3*MAXM]
+  double* hs = wpart + 8 * 3 * MAXM;   // [M][2*RU][256]  h of the current pass
+
+  const int pidx = blockIdx.y;
+  int a = (int)((sqrt(8.0 * (double)pidx + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
+  while (a * (a + 1) / 2 > pidx) --a;
+  const int b = pidx - a * (a + 1) / 2;
+  const int ti = blockIdx.x / p.T, tj = blockIdx.x - ti * p.T;
+  double* out = p.parts + ((long)pidx * p.T * p.T + blockIdx.x) * nv;
+  if (a == b && tj > ti) {   // covered by the mirrored tile (weight 2)
+    for (int s = threadIdx.x; s < nv; s += STHREADS) out[s] = 0.0;
+    return;
+  }
+  for (int m = threadIdx.x; m < M; m += STHREADS) {
+    const double pp = p.Phi[a * M + m], qq = p.Phi[b * M + m];
+    const double psi = 1.0 - pp * qq, g = pp * qq / psi;
+    gam[m] = g;
+    cu[m] = -0.5 * g * pp;
+    cv[m] = -0.5 * g * qq;
+    lp[m] = -0.5 * log(psi);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ST * M; e += STHREADS) {
+    const int r = e / M, m = e - r * M;
+    const int gi = ti * ST + r, gj = tj * ST + r;
+    const double x = gi < p.N ? p.X[(long)gi * M + m] : 0.0;
+    const double y = gj < p.N ? p.X[(long)gj * M + m] : 0.0;
+    gx[m * ST + r] = gam[m] * x;
+    yy[m * ST + r] = y;
+    su[m * ST + r] = fma(cu[m] * x, x, lp[m]);
+    sv[m * ST + r] = cv[m] * y * y;
+  }
+  for (int r = threadIdx.x; r < ST; r += STHREADS) {
+    const int gi = ti * ST + r, gj = tj * ST + r;
+    cr[r] = gi < p.N ? p.c[(long)a * p.N + gi] : 0.0;     // rows/columns beyond N carry zero weight
+    cc[r] = gj < p.N ? p.c[(long)b * p.N + gj] : 0.0;
+  }
+  __syncthreads();
+
+  constexpr int NP = 2 * RU;   // pairs per thread per pass
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double accF[MAXM], accP[MAXM], accS[MAXM], accE = 0.0;   // accP[k-1] = P[k]; accS[k] = S[k] (accS[0] unused)
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m) accF[m] = accP[m] = accS[m] = 0.0;
+#pragma unroll 1
+  for (int pass = 0; pass < (ST / (16 * RU)) * 2; ++pass) {
+    const int r0 = (pass >> 1) * 16 * RU + ty * RU, c0 = (pass & 1) * 32 + tx * 2;
+    double w[NP], run[NP];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      w[2 * u] = cr[r0 + u] * cc[c0];
+      w[2 * u + 1] = cr[r0 + u] * cc[c0 + 1];
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      run[q] = w[q];
+      accE += w[q];
+    }
+    double* hme = hs + threadIdx.x;
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {     // exps, singles and prefixes
+      if (m < M) {
+        const double b0 = yy[m * ST + c0], b1 = yy[m * ST + c0 + 1], v0 = sv[m * ST + c0], v1 = sv[m * ST + c0 + 1];
+        double h[NP];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          const double a0 = gx[m * ST + r0 + u], u0 = su[m * ST + r0 + u];
+          h[2 * u] = exp(fma(a0, b0, u0 + v0));
+          h[2 * u + 1] = exp(fma(a0, b1, u0 + v1));
+        }
+        double f = 0.0, pr = 0.0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          if (m >= 1) hme[(m * NP + q) * STHREADS] = h[q];
+          f = fma(w[q], h[q], f);
+          run[q] *= h[q];
+          pr += run[q];
+        }
+        accF[m] += f;
+        accP[m] += pr;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) run[q] = w[q];
+#pragma unroll
+    for (int m = MAXM - 1; m >= 1; --m) {   // suffixes S[m] = prod_{j >= m} h_j
+      if (m < M) {
+        double sf = 0.0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          run[q] *= hme[(m * NP + q) * STHREADS];
+          sf += run[q];
+        }
+        accS[m] += sf;
+      }
+    }
+  }
+  // warp reductions in a fixed order, then one partial per CTA
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m) {
+    if (m < M) {
+      const double f = warp_sum(accF[m]), pr = warp_sum(accP[m]);
+      if (lane == 0) {
+        wpart[warp * 3 * MAXM + m] = f;
+        wpart[warp * 3 * MAXM + MAXM + m] = pr;
+      }
+      if (m >= 1) {
+        const double sf = warp_sum(accS[m]);
+        if (lane == 0) wpart[warp * 3 * MAXM + 2 * MAXM + m] = sf;
+      }
+    }
+  }
+  {
+    const double e = warp_sum(accE);
+    if (lane == 0) wpart[warp * 3 * MAXM + 2 * MAXM] = e;   // slot of the unused S[0]
+  }
+  __syncthreads();
+  const double wgt = (a == b && ti != tj) ? 2.0 : 1.0;
+  for (int s = threadIdx.x; s < nv; s += STHREADS) {
+    // output index -> wpart slot:  F[m] -> m ; P[k] (s = M+k-1) -> MAXM+k-1 ; S[k] (s = 2M+k-1) -> 2MAXM+k ; E (s = 3M-1) -> 2MAXM
+    int slot;
+    if (s < M) slot = s;
+    else if (s < 2 * M) slot = MAXM + (s - M);
+    else if (s < 3 * M - 1) slot = 2 * MAXM + (s - 2 * M + 1);
+    else slot = 2 * MAXM;
+    double v = 0.0;
+    for (int wdx = 0; wdx < 8; ++wdx) v += wpart[wdx * 3 * MAXM + slot];
+    out[s] = v * wgt;
+  }
+}
+
+template <int MAXM, int RU>
+static int launch_sweep(const SobolPairArgs& a, int npairs, cudaStream_t st) {
+  const size_t smem = (size_t)(4 * a.M + 4 * a.M * ST + 2 * ST + 8 * 3 * MAXM + (size_t)a.M * 2 * RU * STHREADS) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    RC_CUDA_OK(cudaFuncSetAttribute(sobol_sweep_kernel<MAXM, RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
+  }
+  RC_REQUIRE(smem <= 160 * 1024, -2, "sobol_contract: shared memory %zu too large", smem);
+  sobol_sweep_kernel<MAXM, RU><<<dim3(a.T * a.T, npairs), STHREADS, smem, st>>>(a);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// index of a structured subset in the sweep kernel's output, or -1 for a general subset
+static int sweep_index(unsigned long long mask, int M) {
+  const unsigned long long full = (M >= 64) ? ~0ull : ((1ull << M) - 1ull);
+  if (mask == 0) return 3 * M - 1;
+  if ((mask & (mask - 1)) == 0) {            // single input
+    int m = 0;
+    while (!((mask >> m) & 1ull)) ++m;
+    return m;
+  }
+  if (((mask + 1) & mask) == 0) {            // prefix [0:k], k >= 2
+    int k = 0;
+    while ((mask >> k) & 1ull) ++k;
+    return M + k - 1;
+  }
+  const unsigned long long comp = full & ~mask;   // suffix [k:M]  <=>  complement is the prefix [0:k]
+  if (comp != 0 && ((comp + 1) & comp) == 0) {
+    int k = 0;
+    while ((comp >> k) & 1ull) ++k;
+    if (k >= 1 && k <= M - 1) return 2 * M + k - 1;
+  }
+  return -1;
+}
+
+struct SweepMap {
+  int idx[SOBOL_MAX_SLICES];
+};
+
+// V[s0+s][l][j] = sum over (a in l, b in j) and tiles of parts[pair][tile][map.idx[s]]
+__global__ void sobol_finish_map_kernel(const double* __restrict__ parts, int P, int Lp, int L, long tiles, int nv, SweepMap map,
+                                        double* __restrict__ V, const int* __restrict__ dest) {
+  __shared__ double red[32];
+  const int s = blockIdx.x, lj = blockIdx.y, l = lj / L, j = lj - l * L;
+  const int col = map.idx[s];
+  double tot = 0.0;
+  for (int ka = 0; ka < Lp; ++ka)
+    for (int kb = 0; kb < Lp; ++kb) {
+      const int a = l * Lp + ka, b = j * Lp + kb;
+      const int hi = max(a, b), lo = min(a, b);
+      const long pidx = (long)hi * (hi + 1) / 2 + lo;
+      const double* pp = parts + pidx * tiles * nv + col;
+      double acc = 0.0;
+      for (long t = threadIdx.x; t < tiles; t += blockDim.x) acc += pp[t * nv];
+      acc = block_sum(acc, red);
+      tot += acc;   // meaningful in thread 0
+    }
+  (void)dest;
+  if (threadIdx.x == 0) V[((long)s * L + l) * L + j] = tot;
+}
+
 // V[s][l][j] = sum_{a in l, b in j} sum_tiles parts[pair(max(a,b),min(a,b))][tile][s]
 __global__ void sobol_finish_kernel(const double* __restrict__ parts, int P, int Lp, int L, long tiles, int ns, double* __restrict__ V) {
   __shared__ double red[32];
@@ -226,8 +448,8 @@ __global__ void sobol_finish_kernel(const double* __restrict__ parts, int P, int
 
 size_t sobol_workspace_bytes(int N, int P, int ns) {
   const long T = (N + ST - 1) / ST;
-  if (ns > SOBOL_MAX_SLICES) ns = SOBOL_MAX_SLICES;
-  return (size_t)((long)P * (P + 1) / 2) * T * T * ns * sizeof(double);
+  (void)ns;   // 64 values per (pair, tile): a chunk of general subsets, or the 3M <= 36 outputs of the sweep form
+  return (size_t)((long)P * (P + 1) / 2) * T * T * SOBOL_MAX_SLICES * sizeof(double);
 }
 
 int sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int Lp,
@@ -241,8 +463,49 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
   }
   const int T = (N + ST - 1) / ST;
   const int npairs = P * (P + 1) / 2;
-  for (int s0 = 0; s0 < nslices; s0 += SOBOL_MAX_SLICES) {
-    const int ns = min(SOBOL_MAX_SLICES, nslices - s0);
+  // Structured subsets (single inputs, prefixes, suffixes, full, empty: everything gsa.models.GSA asks for) go through the sweep form:
+  // ONE launch whatever their number; only general subsets (the all-subsets sweep) pay one exp per (pair, subset) below.
+  std::vector<int> general;
+  if (M <= 12) {
+    std::vector<int> structured, sidx;
+    for (int s = 0; s < nslices; ++s) {
+      const int k = sweep_index(masks[s], M);
+      if (k >= 0) {
+        structured.push_back(s);
+        sidx.push_back(k);
+      } else {
+        general.push_back(s);
+      }
+    }
+    if (!structured.empty()) {
+      SobolPairArgs a{};
+      a.X = X; a.N = N; a.M = M; a.Phi = Phi; a.c = c; a.P = P; a.T = T; a.ns = 3 * M; a.parts = parts;
+      int rc = M <= 4 ? launch_sweep<4, 2>(a, npairs, st) : M <= 8 ? launch_sweep<8, 2>(a, npairs, st) : launch_sweep<12, 2>(a, npairs, st);
+      if (rc) return rc;
+      // contiguous runs of output slots are finished together (<= SOBOL_MAX_SLICES per launch)
+      size_t i = 0;
+      while (i < structured.size()) {
+        size_t j = i;
+        SweepMap map{};
+        while (j < structured.size() && j - i < (size_t)SOBOL_MAX_SLICES && structured[j] == structured[i] + (int)(j - i)) {
+          map.idx[j - i] = sidx[j];
+          ++j;
+        }
+        sobol_finish_map_kernel<<<dim3((unsigned)(j - i), L * L), 256, 0, st>>>(parts, P, Lp, L, (long)T * T, 3 * M, map,
+                                                                                V + (long)structured[i] * L * L, nullptr);
+        RC_LAUNCH_OK();
+        i = j;
+      }
+    }
+    if (general.empty()) return 0;
+  } else {
+    for (int s = 0; s < nslices; ++s) general.push_back(s);
+  }
+  // general subsets: gather them into chunks (the output rows of a chunk need not be contiguous, so each chunk is finished per run)
+  for (size_t g0 = 0; g0 < general.size();) {
+    size_t g1 = g0;
+    while (g1 < general.size() && g1 - g0 < (size_t)SOBOL_MAX_SLICES && general[g1] == general[g0] + (int)(g1 - g0)) ++g1;
+    const int ns = (int)(g1 - g0), s0 = general[g0];
     SobolPairArgs a{};
     a.X = X; a.N = N; a.M = M; a.Phi = Phi; a.c = c; a.P = P; a.T = T; a.ns = ns; a.parts = parts;
     for (int s = 0; s < ns; ++s) a.masks[s] = masks[s0 + s];
@@ -252,6 +515,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
     RC_LAUNCH_OK();
     sobol_finish_kernel<<<dim3(ns, L * L), 256, 0, st>>>(parts, P, Lp, L, (long)T * T, ns, V + (long)s0 * L * L);
     RC_LAUNCH_OK();
+    g0 = g1;
   }
   return 0;
 }
