@@ -176,7 +176,7 @@ def run_reference(args):
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -298,14 +298,14 @@ def run_b200(args):
     # ---- Sobol sweep: 3 kinds x M slices + the full model, sharded over ranks by slice ----------------------------------
     slices = [(m, m + 1) for m in range(M)] + [(0, m + 1) for m in range(M)] + [(m + 1, M) for m in range(M)] + [(0, M)]
     masks = [C.slice_mask(*s) for s in slices]
-    mine = distributed.shard(masks)
     KiY = torch.randn(L, N, dtype=torch.float64, device='cuda', generator=torch.Generator('cuda').manual_seed(7)) * 0.1
     dLam, dFdiag = C.dev(w.lengthscales), C.dev(np.diag(w.F).copy())
-    parts = C.workspace(C.lib().rc_sobol_bufsize(N, L, len(mine)))
+    parts = C.workspace(C.lib().rc_sobol_bufsize(N, L, len(masks)))
 
     def sweep():
         Phi, g0, g0KY = C.sobol_prepare(dX, dLam, dFdiag, KiY, True)
-        return C.sobol_contract(dX, Phi, g0KY, L, True, mine, parts)
+        V = C.sobol_contract(dX, Phi, g0KY, L, True, masks, parts, rank, world)      # this rank's row tiles of the (N, n) pair space
+        return distributed.all_reduce_sum_tensor(V)                                     # NCCL all-reduce of the (slices, L, L) partial sums
     for _ in range(3):
         V = sweep()
     sync_all()
@@ -314,8 +314,6 @@ def run_b200(args):
     s0.record()
     for _ in range(sweeps):
         V = sweep()
-        if world > 1:
-            V = distributed.all_gather_rows(V.reshape(len(mine), -1).cpu().numpy(), len(masks))
     s1.record()
     sync_all()
     sobol_ms = distributed.all_reduce_max(s0.elapsed_time(s1)) / sweeps
@@ -325,13 +323,12 @@ def run_b200(args):
     exps = M * N * N * pair_blocks
     exps_reference = len(masks) * N * N * L * L            # what the reference's formulation evaluates: one exp per (pair, slice), no symmetry
     sobol = {'metric': 'sobol_sweeps_per_s', 'value': 1e3 / sobol_ms, 'unit': 'sweeps/s', 'ms_per_sweep': sobol_ms, 'slices': len(masks),
-             'scaling': 'strong (marginal subsets sharded over ranks, one all_gather)' if world > 1 else 'single GPU',
-             'roofline': {'bound': 'fp64 exp/ALU', 'achieved': exps / (sobol_ms * 1e-3) * 1e-9, 'peak': peaks['exp_gexps'], 'unit': 'Gexp/s',
-                          'frac': exps / (sobol_ms * 1e-3) * 1e-9 / peaks['exp_gexps'], 'exps_per_sweep': exps,
+             'scaling': 'strong (row tiles of the sample-pair space sharded over ranks, one NCCL all-reduce of the partial V)' if world > 1 else 'single GPU',
+             'roofline': {'bound': 'fp64 exp/ALU', 'achieved': exps / world / (sobol_ms * 1e-3) * 1e-9, 'peak': peaks['exp_gexps'], 'unit': 'Gexp/s',
+                          'frac': exps / world / (sobol_ms * 1e-3) * 1e-9 / peaks['exp_gexps'], 'exps_per_sweep': exps,
                           'reference_exps_per_sweep': exps_reference,
                           'note': 'achieved = M exps per (sample pair, pair of output rows) actually required by the factorised integrand / sweep time '
-                                  '(each rank evaluates all of them when the slices are sharded: the sweep form yields every slice from the same M '
-                                  'exps); peak = register-resident libm exp loop measured live; the remaining FP64 work per exp is ~8 FMA/ADD '
+                                  '(per GPU: divided by the number of ranks, which split the pair space); peak = register-resident libm exp loop measured live; the remaining FP64 work per exp is ~8 FMA/ADD '
                                   '(prefix/suffix products, weights)'}}
 
     # ---- CPU baseline on this box's host cores (rank 0, single-GPU runs only) -------------------------------------------
@@ -374,11 +371,20 @@ def run_b200(args):
                         'ms_per_step': 1e3 * e2e_s / args.steps,
                         'path': 'romcomma.gpf.models.MOGPR(data=(pinned host X, Y), ...)._loss_and_grad: H2D of X, Y and hyper-parameters, D2H of LML+gradient'},
                 'gpu_launches': int(launches), 'sobol': sobol, 'clocks': clocks.summary(), 'lml': lml}
-        print(json.dumps(line), flush=True)
+        emit(line)
     distributed.barrier()
 
 
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else written to fd 1 meanwhile (NCCL's version banner, library
+    chatter) has been diverted to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
 if __name__ == '__main__':
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == 'reference':
         run_reference(a)

@@ -130,6 +130,12 @@ int rc_sobol_prepare(const double* X, int N, int M, const double* Lam, const dou
 int rc_sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int is_F_diagonal,
                       const unsigned long long* masks_host, int nslices, void* parts, double* V, rc_stream_t stream);
 
+/* Multi-GPU form of rc_sobol_contract: evaluates only the 64-row tiles ti of the (N, n) pair space with ti % nparts == part and returns
+ * the PARTIAL sums V; the caller adds the parts (ncclAllReduce over the ranks).  The slice loop of romcomma/gsa/models.py:127-134 has no
+ * exchange step, so this is the only collective a sharded sweep needs. */
+int rc_sobol_contract_part(const double* X, int N, int M, const double* Phi, const double* c, int L, int is_F_diagonal,
+                           const unsigned long long* masks_host, int nslices, int part, int nparts, void* parts, double* V, rc_stream_t stream);
+
 /* rc_sobol_error: ClosedSobolWithError.marginalize / _calibrate (romcomma/gsa/calibrators.py:146-402) for a list of marginal subsets,
  * in the only configuration the reference supports: diagonal F (:380-381) and is_T_partial (META, :149-157).  Evaluates the
  * _psi_factor (:290-309), _UpsilonGaussian (:244-257), _OmegaGaussian (:214-242) and _mu_phi_mu (:259-288) chains as fused pairwise

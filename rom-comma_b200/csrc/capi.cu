@@ -332,7 +332,14 @@ int rc_sobol_prepare(const double* X, int N, int M, const double* Lam, const dou
 int rc_sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int is_F_diagonal,
                       const unsigned long long* masks_host, int nslices, void* parts, double* V, rc_stream_t stream) {
   RC_REQUIRE(X && Phi && c && masks_host && parts && V && nslices > 0, -2, "rc_sobol_contract: null pointer or empty subset list");
-  return sobol_contract(X, N, M, Phi, c, L, is_F_diagonal ? 1 : L, masks_host, nslices, static_cast<double*>(parts), V, (cudaStream_t)stream);
+  return sobol_contract(X, N, M, Phi, c, L, is_F_diagonal ? 1 : L, masks_host, nslices, static_cast<double*>(parts), V, 0, 1, (cudaStream_t)stream);
+}
+
+int rc_sobol_contract_part(const double* X, int N, int M, const double* Phi, const double* c, int L, int is_F_diagonal,
+                           const unsigned long long* masks_host, int nslices, int part, int nparts, void* parts, double* V, rc_stream_t stream) {
+  RC_REQUIRE(X && Phi && c && masks_host && parts && V && nslices > 0, -2, "rc_sobol_contract_part: null pointer or empty subset list");
+  return sobol_contract(X, N, M, Phi, c, L, is_F_diagonal ? 1 : L, masks_host, nslices, static_cast<double*>(parts), V, part, nparts,
+                        (cudaStream_t)stream);
 }
 
 size_t rc_sobol_error_bufsize(int N, int M, int L, int nslices, int n_pad, int chol_batch) {

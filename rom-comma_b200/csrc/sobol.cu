@@ -89,6 +89,7 @@ struct SobolPairArgs {
   int P, T;            // T = ceil(N / 64)
   int ns;
   double* parts;       // [npairs][T*T][ns]
+  int part, nparts;    // this call evaluates the row tiles ti with ti % nparts == part (multi-GPU: partial V, summed by the caller)
   unsigned long long masks[SOBOL_MAX_SLICES];
 };
 
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(STHREADS) sobol_pair_kernel(SobolPairArgs p) {
   const int b = pidx - a * (a + 1) / 2;
   const int ti = blockIdx.x / p.T, tj = blockIdx.x - ti * p.T;
   double* out = p.parts + ((long)pidx * p.T * p.T + blockIdx.x) * ns;
-  if (a == b && tj > ti) {   // covered by the mirrored tile (weight 2)
+  if ((a == b && tj > ti) || (ti % p.nparts) != p.part) {   // covered by the mirrored tile (weight 2), or another rank's row tile
     for (int s = threadIdx.x; s < ns; s += STHREADS) out[s] = 0.0;
     return;
   }
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs 
   const int b = pidx - a * (a + 1) / 2;
   const int ti = blockIdx.x / p.T, tj = blockIdx.x - ti * p.T;
   double* out = p.parts + ((long)pidx * p.T * p.T + blockIdx.x) * nv;
-  if (a == b && tj > ti) {   // covered by the mirrored tile (weight 2)
+  if ((a == b && tj > ti) || (ti % p.nparts) != p.part) {   // covered by the mirrored tile (weight 2), or another rank's row tile
     for (int s = threadIdx.x; s < nv; s += STHREADS) out[s] = 0.0;
     return;
   }
@@ -453,8 +454,9 @@ size_t sobol_workspace_bytes(int N, int P, int ns) {
 }
 
 int sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int Lp,
-                   const unsigned long long* masks, int nslices, double* parts, double* V, cudaStream_t st) {
+                   const unsigned long long* masks, int nslices, double* parts, double* V, int part, int nparts, cudaStream_t st) {
   RC_REQUIRE(M >= 1 && M <= 64, -2, "sobol_contract: M=%d out of range [1,64]", M);
+  RC_REQUIRE(nparts >= 1 && part >= 0 && part < nparts, -2, "sobol_contract: part %d of %d", part, nparts);
   const int P = L * Lp;
   static bool configured = false;
   if (!configured) {
@@ -479,7 +481,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
     }
     if (!structured.empty()) {
       SobolPairArgs a{};
-      a.X = X; a.N = N; a.M = M; a.Phi = Phi; a.c = c; a.P = P; a.T = T; a.ns = 3 * M; a.parts = parts;
+      a.X = X; a.N = N; a.M = M; a.Phi = Phi; a.c = c; a.P = P; a.T = T; a.ns = 3 * M; a.parts = parts; a.part = part; a.nparts = nparts;
       int rc = M <= 4 ? launch_sweep<4, 2>(a, npairs, st) : M <= 8 ? launch_sweep<8, 2>(a, npairs, st) : launch_sweep<12, 2>(a, npairs, st);
       if (rc) return rc;
       // contiguous runs of output slots are finished together (<= SOBOL_MAX_SLICES per launch)
@@ -507,7 +509,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
     while (g1 < general.size() && g1 - g0 < (size_t)SOBOL_MAX_SLICES && general[g1] == general[g0] + (int)(g1 - g0)) ++g1;
     const int ns = (int)(g1 - g0), s0 = general[g0];
     SobolPairArgs a{};
-    a.X = X; a.N = N; a.M = M; a.Phi = Phi; a.c = c; a.P = P; a.T = T; a.ns = ns; a.parts = parts;
+    a.X = X; a.N = N; a.M = M; a.Phi = Phi; a.c = c; a.P = P; a.T = T; a.ns = ns; a.parts = parts; a.part = part; a.nparts = nparts;
     for (int s = 0; s < ns; ++s) a.masks[s] = masks[s0 + s];
     const size_t smem = (size_t)(4 * M + 3 * M * ST + 2 * ns * ST + 2 * ST + 8 * ns) * sizeof(double);
     RC_REQUIRE(smem <= 200 * 1024, -2, "sobol_contract: shared memory %zu too large", smem);

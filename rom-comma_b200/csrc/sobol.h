@@ -14,8 +14,9 @@ int sobol_prepare(const double* X, int N, int M, const double* Lam, const double
 size_t sobol_workspace_bytes(int N, int P, int ns);
 
 // V[s][l][j] for s < nslices; masks are host-side bit sets over the M inputs (bit m set <=> input m is in the subset).
+// part/nparts: only the 64-row tiles ti with ti % nparts == part are evaluated (V is then a partial sum; 0/1 = everything).
 int sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int Lp, const unsigned long long* masks, int nslices,
-                   double* parts, double* V, cudaStream_t st);
+                   double* parts, double* V, int part, int nparts, cudaStream_t st);
 
 // ClosedSobolWithError (diagonal F, is_T_partial): V[s][l][i] and W[s][l][i] = (mu_phi_mu - mu_psi_mu) + transpose for every subset.
 // Phi (L,M), g0 (L,N), g0KY (L,N) come from sobol_prepare; Achol/dinv from potrf_lower with chol_batch = 1 (covariant GP, n_pad >= L*N)

@@ -61,6 +61,8 @@ _SIGNATURES = {
                                         c_double_p, c_double_p, c_double_p, ctypes.c_void_p]),
     'rc_sobol_contract': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, c_double_p, ctypes.c_void_p]),
+    'rc_sobol_contract_part': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_double_p, ctypes.c_void_p]),
     'rc_sobol_error_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'rc_sobol_error': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                       ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_void_p,
@@ -313,8 +315,9 @@ def slice_mask(m0: int, m1: int) -> int:
     return ((1 << max(m1 - m0, 0)) - 1) << m0
 
 
-def sobol_contract(X, Phi, c, L: int, is_F_diagonal: bool, masks: Sequence[int], parts: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """-> V (len(masks), L, L) on the device."""
+def sobol_contract(X, Phi, c, L: int, is_F_diagonal: bool, masks: Sequence[int], parts: Optional[torch.Tensor] = None, part: int = 0,
+                   nparts: int = 1) -> torch.Tensor:
+    """-> V (len(masks), L, L) on the device; with nparts > 1 the partial sums over the row tiles ti % nparts == part."""
     N, M = X.shape
     P = Phi.shape[0]
     ns = len(masks)
@@ -322,8 +325,8 @@ def sobol_contract(X, Phi, c, L: int, is_F_diagonal: bool, masks: Sequence[int],
         parts = workspace(lib().rc_sobol_bufsize(N, P, ns), X.device)
     V = torch.empty((ns, L, L), dtype=torch.float64, device=X.device)
     arr = (ctypes.c_ulonglong * ns)(*[int(m) for m in masks])
-    check(lib().rc_sobol_contract(ptr(X), N, M, ptr(Phi), ptr(c), L, int(is_F_diagonal), ctypes.cast(arr, ctypes.c_void_p), ns, raw_ptr(parts),
-                                  ptr(V), stream_ptr()), 'rc_sobol_contract')
+    check(lib().rc_sobol_contract_part(ptr(X), N, M, ptr(Phi), ptr(c), L, int(is_F_diagonal), ctypes.cast(arr, ctypes.c_void_p), ns, int(part),
+                                       int(nparts), raw_ptr(parts), ptr(V), stream_ptr()), 'rc_sobol_contract_part')
     return V
 
 

@@ -90,3 +90,10 @@ def all_reduce_sum(value: float) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=_device_for_collectives())
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def all_reduce_sum_tensor(t: torch.Tensor) -> torch.Tensor:
+    """ In-place sum over the ranks of a device (NCCL) or host (gloo) tensor; identity for a single process."""
+    if is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t

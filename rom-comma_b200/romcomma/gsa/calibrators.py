@@ -8,7 +8,7 @@ from __future__ import annotations
 from romcomma.base.definitions import *
 from romcomma.gpr.models import GPR
 from romcomma.gsa.base import Calibrator
-from romcomma import _capi
+from romcomma import _capi, distributed
 from romcomma._tensors import DeviceTensor, HostTensor, as_device
 
 
@@ -84,7 +84,11 @@ class ClosedSobol(gf.Module, Calibrator):
 
     def _V_many(self, masks: Sequence[int]) -> np.ndarray:
         """ V for a list of subsets given as bit masks over the inputs -> host array (len(masks), L, L)."""
-        V = _capi.sobol_contract(self._Xd, self._Phi_d, self._g0KY_d, self.L, self.is_F_diagonal, masks)
+        # With several ranks (torchrun) the (N, n) pair space is split by row tile and the partial sums are added with one all-reduce.
+        w = distributed.world_size() if self.meta.get('shard_pair_space', False) else 1
+        V = _capi.sobol_contract(self._Xd, self._Phi_d, self._g0KY_d, self.L, self.is_F_diagonal, masks, None, distributed.rank() if w > 1 else 0, w)
+        if w > 1:
+            distributed.all_reduce_sum_tensor(V)
         return V.cpu().numpy()
 
     def marginalize_many(self, slices: Sequence[Sequence[int]]) -> List[Dict[str, HostTensor]]:

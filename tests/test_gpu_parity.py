@@ -286,3 +286,22 @@ def test_sobol_error_matches_oracle(C, N, M, L, covariant):
         assert_close(V[k], out['V'], rtol=1e-7, atol=1e-10, what=f'V {sub}')
         assert_close(W[k], out['W'], rtol=1e-7, atol=1e-10, what=f'W {sub}')
     assert_close(W[0], ref.W, rtol=1e-7, atol=1e-10, what='full-model W')
+
+
+def test_sobol_pair_space_parts_add_up(C):
+    """rc_sobol_contract_part: the row-tile parts a multi-GPU sweep all-reduces sum to the single-GPU result, for structured slices
+    (sweep form) and general subsets (one exp per subset) alike."""
+    N, M, L = 333, 6, 3
+    X, Y, ls, F, E = random_problem(N, M, L, seed=21, full_E=False)
+    KiY = gp.k_inv_y_mo(X, Y, ls, F, E)
+    dX = C.dev(X)
+    Phi, g0, g0KY = C.sobol_prepare(dX, C.dev(ls), C.dev(np.diag(F).copy()), C.dev(KiY.reshape(L, N)), True)
+    masks = [C.slice_mask(0, M), C.slice_mask(2, 3), C.slice_mask(0, 4), C.slice_mask(3, M), 0, 0b101001, 0b010110, C.slice_mask(1, 4)]
+    full = C.sobol_contract(dX, Phi, g0KY, L, True, masks).cpu().numpy()
+    cal = sobol.ClosedSobol(X, ls, F, KiY, True)
+    assert_close(full[0], cal.V[0], rtol=1e-8, atol=1e-12, what='full model')
+    assert_close(full[7], cal._V(1, 4), rtol=1e-8, atol=1e-12, what='interior contiguous slice (general path)')
+    assert_close(full[5], sobol.subset_V(X, ls, F, KiY, [0, 3, 5])['V'], rtol=1e-8, atol=1e-12, what='subset {0,3,5}')
+    for nparts in (2, 5):
+        total = sum(C.sobol_contract(dX, Phi, g0KY, L, True, masks, None, part, nparts).cpu().numpy() for part in range(nparts))
+        assert_close(total, full, rtol=1e-12, atol=1e-14, what=f'sum of {nparts} parts')
