@@ -243,6 +243,31 @@ def k_inv_y_rbf(X, Y, ls, variance, noise):
     return np.stack([sla.cho_solve((cho[l], True), Y[:, l]) for l in range(Y.shape[1])])[:, None, :]
 
 
+def predict_gradient_rbf(X, Y, ls, variance, noise, xs):
+    """gpr/models.py:386-415, variant branch (the covariant branch of the reference raises a TypeError at :405).
+    mean (o,L,M) = d/dx of the predictive mean; var (O,o,L,M,m) = -W^T W with W = K_cho^-1 dK(X,x)/dx, plus, on the M == m diagonal,
+    Lambda[L,M]^2 k_L(x_O, x_o) with Lambda = 1/lengthscale - exactly the reference's expression (it drops the (x-x')^2 term of the second
+    derivative and fills only the diagonal in M)."""
+    X, Y, xs = np.asarray(X, float), np.asarray(Y, float), np.asarray(xs, float)
+    L, M, o = Y.shape[1], X.shape[1], xs.shape[0]
+    cho = k_cho_rbf(X, ls, variance, noise)
+    KiY = k_inv_y_rbf(X, Y, ls, variance, noise)
+    mean = np.zeros((o, L, M))
+    var = np.zeros((o, o, L, M, M))
+    for l in range(L):
+        K = gram_rbf(X, xs, ls[l], variance[l])                                            # (N,o)
+        J = K[:, :, None] * (X[:, None, :] - xs[None, :, :]) / (ls[l] ** 2)[None, None, :]   # (N,o,M)
+        mean[:, l, :] = np.einsum('NoM,N->oM', J, KiY[l, 0])
+        W = sla.solve_triangular(cho[l], J.reshape(X.shape[0], o * M), lower=True).reshape(X.shape[0], o, M)
+        var[:, :, l] = -np.einsum('NOM,Nom->OoMm', W, W)
+        kxx = gram_rbf(xs, xs, ls[l], variance[l])
+        lam = 1.0 / ls[l]
+        dd = lam[None, None, :] * lam[None, None, :] * kxx[:, :, None]                     # (O,o,M)
+        idx = np.arange(M)
+        var[:, :, l, idx, idx] += dd
+    return mean, var
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # the timed CPU unit: one LML + gradient evaluation through LAPACK (potrf + potri), blocked gram
 # ----------------------------------------------------------------------------------------------------------------

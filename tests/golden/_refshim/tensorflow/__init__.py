@@ -239,13 +239,32 @@ class RaggedTensor:
 
 
 class GradientTape:
-    """Not needed by the golden generator (gradients are taken with torch.autograd directly); present so imports resolve."""
+    """Eager torch autograd records everything already; ``jacobian`` is what romcomma/gpr/models.py:396 needs
+    (``tape.jacobian(KXx, x)`` -> shape ``KXx.shape + x.shape``), one reverse pass per target element (small cases only)."""
+
+    def __init__(self, persistent=False, watch_accessed_variables=True):
+        pass
 
     def __enter__(self):
         return self
 
     def __exit__(self, *exc):
         return False
+
+    def watch(self, tensor):
+        return None
+
+    def jacobian(self, target, sources, **kwargs):
+        target, sources = _t(target), _t(sources)
+        flat = target.reshape(-1)
+        rows = []
+        for i in range(flat.numel()):
+            g, = _torch.autograd.grad(flat[i], sources, retain_graph=True, allow_unused=True)
+            rows.append(_torch.zeros_like(sources) if g is None else g)
+        return Tensor.wrap(_torch.stack(rows).reshape(tuple(target.shape) + tuple(sources.shape)).detach())
+
+    def gradient(self, target, sources, **kwargs):
+        return Tensor.wrap(_torch.autograd.grad(_t(target), _t(sources), retain_graph=True)[0])
 
 
 class _Data:

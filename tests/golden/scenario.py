@@ -147,6 +147,18 @@ def run(api: SimpleNamespace, name: str, root: Path) -> Dict[str, np.ndarray]:
         mean, std = gp.predict(xs, y_instead_of_f=flag)
         out[f'predict.{tag}.mean'], out[f'predict.{tag}.std'] = np.asarray(mean, dtype=np.float64), np.asarray(std, dtype=np.float64)
 
+    # ---- 8(f)2: the gradient GP dy/dx at a few points (mean (o,L,M) and the reference's covariance tensor, gpr/models.py:386-415) -------
+    #       Variant GPs only: for a covariant GP the reference itself fails (``kernel(x)`` at :405 calls MOStationary.__call__ without X2).
+    if cov:
+        try:
+            gp.predict_gradient(xs[:3])
+            out['predict_gradient.covariant_raises'] = np.array(False)
+        except TypeError:
+            out['predict_gradient.covariant_raises'] = np.array(True)
+    else:
+        mean, var = gp.predict_gradient(xs[:3])
+        out['predict_gradient.mean'], out['predict_gradient.var'] = to_np(mean), to_np(var)
+
     # ---- a9: Cholesky factor and K^-1 Y as GSA consumes them -----------------------------------------------------------------
     out['K_cho'] = np.tril(to_np(gp.K_cho))
     out['K_inv_Y'] = to_np(gp.K_inv_Y)

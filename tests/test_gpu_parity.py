@@ -304,4 +304,4 @@ def test_sobol_pair_space_parts_add_up(C):
     assert_close(full[5], sobol.subset_V(X, ls, F, KiY, [0, 3, 5])['V'], rtol=1e-8, atol=1e-12, what='subset {0,3,5}')
     for nparts in (2, 5):
         total = sum(C.sobol_contract(dX, Phi, g0KY, L, True, masks, None, part, nparts).cpu().numpy() for part in range(nparts))
-        assert_close(total, full, rtol=1e-12, atol=1e-14, what=f'sum of {nparts} parts')
+        assert_close(total, full, rtol=1e-10, atol=1e-12, what=f'sum of {nparts} parts (summation order differs)')
