@@ -149,13 +149,19 @@ __device__ __forceinline__ void diag_trtri_block(double (&zz)[8][8], const DiagC
   }
 }
 
+// MODE 0: factor block `blk` and invert it (one launch per block).  MODE 1: factor only - what the critical path of potrf_lower needs
+// (the panel below is solved against L directly).  MODE 2: invert only, all blocks at once (grid = (nblk, batch), blk = blockIdx.x):
+// the inverses feed the later solves / trtri and are computed off the critical path, in one wave.
+template <int MODE>
 __global__ void __launch_bounds__(DB_THREADS, 1)
-diag_potrf_inv_kernel(double* __restrict__ A, long ld, long strideA, double* __restrict__ dinv, long strideD, int blk,
+diag_potrf_inv_kernel(double* __restrict__ A, long ld, long strideA, double* __restrict__ dinv, long strideD, int blk_arg,
                       double* __restrict__ logdet_parts, int nblk, int* __restrict__ info) {
   extern __shared__ __align__(16) double sm[];
   double* S = sm;                       // [128][129]  L, for phase 2
   double* red = sm + DB * DB_LD + 5 * DB;
-  const int tid = threadIdx.x, z = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int z = MODE == 2 ? blockIdx.y : blockIdx.x;
+  const int blk = MODE == 2 ? blockIdx.x : blk_arg;
   DiagCtx c;
   c.colbuf = sm + DB * DB_LD;           // [2][128]
   c.rowbuf = c.colbuf + 2 * DB;         // [2][128]
@@ -181,15 +187,17 @@ diag_potrf_inv_kernel(double* __restrict__ A, long ld, long strideA, double* __r
       a[ia][ib] = (ib <= ia && col <= r) ? Ab[(long)r * ld + col] : 0.0;
     }
   }
-  diag_produce_col<0>(a, dc, c, 0);
-  diag_potrf_block<0>(a, dr, dc, c);
-  diag_potrf_block<1>(a, dr, dc, c);
-  diag_potrf_block<2>(a, dr, dc, c);
-  diag_potrf_block<3>(a, dr, dc, c);
-  diag_potrf_block<4>(a, dr, dc, c);
-  diag_potrf_block<5>(a, dr, dc, c);
-  diag_potrf_block<6>(a, dr, dc, c);
-  diag_potrf_block<7>(a, dr, dc, c);
+  if (MODE != 2) {
+    diag_produce_col<0>(a, dc, c, 0);
+    diag_potrf_block<0>(a, dr, dc, c);
+    diag_potrf_block<1>(a, dr, dc, c);
+    diag_potrf_block<2>(a, dr, dc, c);
+    diag_potrf_block<3>(a, dr, dc, c);
+    diag_potrf_block<4>(a, dr, dc, c);
+    diag_potrf_block<5>(a, dr, dc, c);
+    diag_potrf_block<6>(a, dr, dc, c);
+    diag_potrf_block<7>(a, dr, dc, c);
+  }
 
   // L -> global (lower part) and shared memory; log-determinant part
   double logsum = 0.0;
@@ -200,14 +208,21 @@ diag_potrf_inv_kernel(double* __restrict__ A, long ld, long strideA, double* __r
     for (int ib = 0; ib <= ia; ++ib) {
       const int col = tx + 16 * ib;
       if (col <= r) {
-        Ab[(long)r * ld + col] = a[ia][ib];
-        S[r * DB_LD + col] = a[ia][ib];
-        if (col == r) logsum += log(a[ia][ib]);
+        if (MODE != 2) Ab[(long)r * ld + col] = a[ia][ib];
+        if (MODE != 1) S[r * DB_LD + col] = a[ia][ib];
+        if (col == r) {
+          logsum += log(a[ia][ib]);
+          if (MODE == 2) c.rinvs[r] = 1.0 / a[ia][ib];      // a holds the finished factor read back from A
+        }
       }
     }
   }
-  logsum = block_sum(logsum, red);               // contains the barriers that publish S and rinvs
-  if (tid == 0) logdet_parts[(long)z * nblk + blk] = logsum;
+  if (MODE != 2) {
+    logsum = block_sum(logsum, red);
+    if (tid == 0) logdet_parts[(long)z * nblk + blk] = logsum;
+  }
+  if (MODE == 1) return;
+  __syncthreads();                               // publishes S and rinvs
 
   // Phase 2: Z = L^-1.  Start from the identity and apply E_j^-1 for j = 0..127: row j <- row j / L_jj, rows i > j -= L[i][j] * row j.
 #pragma unroll
@@ -234,14 +249,136 @@ diag_potrf_inv_kernel(double* __restrict__ A, long ld, long strideA, double* __r
   }
 }
 
-static int launch_diag(double* A, long ld, long strideA, double* dinv, long strideD, int blk, double* logdet_parts, int nblk, int* info,
-                       int batch, cudaStream_t st) {
+static int launch_diag_factor(double* A, long ld, long strideA, double* dinv, long strideD, int blk, double* logdet_parts, int nblk, int* info,
+                              int batch, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(diag_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+    RC_CUDA_OK(cudaFuncSetAttribute(diag_potrf_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
     configured = true;
   }
-  diag_potrf_inv_kernel<<<batch, DB_THREADS, DB_SMEM, st>>>(A, ld, strideA, dinv, strideD, blk, logdet_parts, nblk, info);
+  diag_potrf_inv_kernel<1><<<batch, DB_THREADS, DB_SMEM, st>>>(A, ld, strideA, dinv, strideD, blk, logdet_parts, nblk, info);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+static int launch_diag_invert_all(double* A, long ld, long strideA, double* dinv, long strideD, int nblk, int batch, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    RC_CUDA_OK(cudaFuncSetAttribute(diag_potrf_inv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
+    configured = true;
+  }
+  diag_potrf_inv_kernel<2><<<dim3(nblk, batch), DB_THREADS, DB_SMEM, st>>>(A, ld, strideA, dinv, strideD, 0, nullptr, nblk, nullptr);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Panel solve  P <- P * L_kk^-T  for the 128-row tiles below a freshly factored diagonal block (the TRSM of the right-looking step),
+// against L itself: the inverse of the block is not on the critical path any more.
+// One CTA per 128 x 128 tile; warp w owns rows [16w, 16w+16) and keeps them as DMMA accumulators (2 x 16 tiles of 8 x 8).  The 128
+// columns are processed in four blocks of 32:  (1) the block's accumulators go to a per-warp staging area, (2) two lanes per row solve the
+// 16 x 32 system against the 32 x 32 diagonal sub-block by substitution in registers (column j finished, broadcast by a shuffle, eliminated
+// from the later columns; all indices static), (3) the solved block X eliminates itself from the later column blocks on the tensor cores:
+// acc[:, c] -= X * L[c, block]^T with A fragments from the staging area and B fragments from the staged factor.  No CTA barrier after staging.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int PT_LP = DB + 4;                       // pitch of the staged factor (conflict-free half-warp fragment reads)
+constexpr int PT_XP = 32 + 4;                       // pitch of a warp's 16 x 32 staging block
+constexpr size_t PT_SMEM = (size_t)(DB * PT_LP + 8 * 16 * PT_XP + DB) * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+panel_trsm_kernel(double* __restrict__ A, long ld, long strideA, int blk) {
+  extern __shared__ __align__(16) double sm[];
+  double* Ls = sm;                                   // [128][PT_LP]  L[k][j], lower part valid
+  double* Xs_all = sm + DB * PT_LP;                  // [8][16][PT_XP]
+  double* rinv = Xs_all + 8 * 16 * PT_XP;            // [128]  1 / L[j][j]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, z = blockIdx.y;
+  const int g = lane >> 2, t = lane & 3;
+  double* Az = A + (long)z * strideA;
+  const double* Lb = Az + (long)blk * DB * (ld + 1);
+  double* Pt = Az + ((long)(blk + 1 + blockIdx.x) * DB + warp * 16) * ld + (long)blk * DB;    // this warp's 16 rows
+  // accumulators: acc[h][c][e] = P[8h + g][8c + 2t + e]
+  double acc[2][16][2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const double2 v = *reinterpret_cast<const double2*>(Pt + (long)(8 * h + g) * ld + 8 * c + 2 * t);
+      acc[h][c][0] = v.x;
+      acc[h][c][1] = v.y;
+    }
+  for (int idx = tid; idx < DB * (DB / 2); idx += 256) {         // stage the factor: 64 double2 per row, coalesced
+    const int k = idx >> 6, j2 = (idx & 63) * 2;
+    if (j2 <= k) {
+      const double2 v = *reinterpret_cast<const double2*>(Lb + (long)k * ld + j2);
+      Ls[k * PT_LP + j2] = v.x;
+      Ls[k * PT_LP + j2 + 1] = v.y;
+      if (j2 == k) rinv[k] = 1.0 / v.x;
+      if (j2 + 1 == k) rinv[k] = 1.0 / v.y;
+    }
+  }
+  __syncthreads();
+  double* Xs = Xs_all + warp * 16 * PT_XP;
+  const int rr = lane >> 1, par = lane & 1;                        // substitution: row rr of the warp, columns of parity par
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) {
+    // (1) accumulators of this column block -> staging (C layout: row 8h+g, columns 8c' + 2t + e)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        Xs[(8 * h + g) * PT_XP + 8 * c + 2 * t] = acc[h][4 * cb + c][0];
+        Xs[(8 * h + g) * PT_XP + 8 * c + 2 * t + 1] = acc[h][4 * cb + c][1];
+      }
+    __syncwarp();
+    // (2) 16 x 32 substitution against the diagonal 32 x 32 sub-block
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = Xs[rr * PT_XP + 2 * i + par];
+    const double* Ld = Ls + (32 * cb) * PT_LP + 32 * cb;          // L[32cb + k][32cb + j] = Ld[k * PT_LP + j]
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int i0 = j >> 1;
+      const double mine = x[i0] * rinv[32 * cb + j];
+      const double xj = __shfl_sync(0xffffffffu, mine, (lane & ~1) | (j & 1));
+      if (par == (j & 1)) x[i0] = xj;
+      if ((j & 1) == 0 && par == 1) x[i0] = fma(-xj, Ld[(j + 1) * PT_LP + j], x[i0]);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i > i0) x[i] = fma(-xj, Ld[(2 * i + par) * PT_LP + j], x[i]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      Xs[rr * PT_XP + 2 * i + par] = x[i];                         // solved block: A operand of the update ...
+      Pt[(long)rr * ld + 32 * cb + 2 * i + par] = x[i];            // ... and the result
+    }
+    __syncwarp();
+    // (3) eliminate the solved block from the later column blocks: acc[:, c] -= X * L[c, block]^T
+    if (cb < 3) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const double a0 = -Xs[g * PT_XP + 4 * ks + t], a1 = -Xs[(8 + g) * PT_XP + 4 * ks + t];
+#pragma unroll
+        for (int c = 4 * (cb + 1); c < 16; ++c) {
+          const double bv = Ls[(8 * c + g) * PT_LP + 32 * cb + 4 * ks + t];
+          dmma884(acc[0][c][0], acc[0][c][1], a0, bv);
+          dmma884(acc[1][c][0], acc[1][c][1], a1, bv);
+        }
+      }
+      __syncwarp();                                                // staging area is rewritten by step (1) of the next block
+    }
+  }
+}
+
+static int launch_panel_trsm(double* A, int n, long ld, long strideA, int blk, int batch, cudaStream_t st) {
+  const int tiles = n / DB - blk - 1;
+  if (tiles <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    RC_CUDA_OK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+    configured = true;
+  }
+  panel_trsm_kernel<<<dim3(tiles, batch), 256, PT_SMEM, st>>>(A, ld, strideA, blk);
   RC_LAUNCH_OK();
   return 0;
 }
@@ -262,19 +399,10 @@ int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv
   const long strideD = (long)nblk * DB * DB;
   RC_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
   int rc;
-  auto trsm_panel = [&](int blk) -> int {   // rows below block `blk`, its 128 columns:  P <- P * Dinv^T
-    const int r0 = (blk + 1) * DB;
-    if (r0 >= n) return 0;
-    GemmArgs g{};
-    g.A = A + (long)r0 * ld + (long)blk * DB; g.lda = ld; g.strideA = strideA;
-    g.B = dinv + (long)blk * DB * DB; g.ldb = DB; g.strideB = strideD;
-    g.C = A + (long)r0 * ld + (long)blk * DB; g.ldc = ld; g.strideC = strideA;
-    g.M = n - r0; g.N = DB; g.K = DB; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kmode = K_FULL;
-    return launch_gemm_ws<false, false>(g, batch, st);
-  };
+  auto trsm_panel = [&](int blk) -> int { return launch_panel_trsm(A, n, ld, strideA, blk, batch, st); };
   for (int b0 = 0; b0 < nblk; b0 += 2) {
     const int w = (b0 + 1 < nblk) ? 2 : 1;
-    if ((rc = launch_diag(A, ld, strideA, dinv, strideD, b0, logdet_parts, nblk, info, batch, st))) return rc;
+    if ((rc = launch_diag_factor(A, ld, strideA, dinv, strideD, b0, logdet_parts, nblk, info, batch, st))) return rc;
     if ((rc = trsm_panel(b0))) return rc;
     if (w == 2) {
       // columns of block b0+1, rows from block b0+1 down:  A -= P0 * P0[b0+1]^T
@@ -285,7 +413,7 @@ int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv
       g.C = A + r0 * ld + r0; g.ldc = ld; g.strideC = strideA;
       g.M = n - (int)r0; g.N = DB; g.K = DB; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kmode = K_FULL;
       if ((rc = launch_gemm_ws<false, false>(g, batch, st))) return rc;
-      if ((rc = launch_diag(A, ld, strideA, dinv, strideD, b0 + 1, logdet_parts, nblk, info, batch, st))) return rc;
+      if ((rc = launch_diag_factor(A, ld, strideA, dinv, strideD, b0 + 1, logdet_parts, nblk, info, batch, st))) return rc;
       if ((rc = trsm_panel(b0 + 1))) return rc;
     }
     const long r0 = (long)(b0 + w) * DB;
@@ -298,6 +426,8 @@ int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv
       if ((rc = launch_gemm_ws<false, false>(g, batch, st))) return rc;
     }
   }
+  // the 128 x 128 inverses the solves / trtri need: all blocks in one wave, off the critical path
+  if ((rc = launch_diag_invert_all(A, ld, strideA, dinv, strideD, nblk, batch, st))) return rc;
   return 0;
 }
 
