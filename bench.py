@@ -364,6 +364,31 @@ def run_b200(args):
                                   '(per GPU: divided by the number of ranks, which split the pair space); peak = register-resident libm exp loop measured live; the remaining FP64 work per exp is ~8 FMA/ADD '
                                   '(prefix/suffix products, weights)'}}
 
+    # ---- Sobol sweep WITH errors (ClosedSobolWithError, gsa/calibrators.py:146-402; on by default in the reference's scripts): V, W for the same
+    #      25 slices; needs the Cholesky factor of the noisy gram (factorised once, outside the timed loop, as the calibrator holds it).
+    sobol_err = None
+    if rank == 0 and world == 1:
+        Kfac = C.gram(dX, None, dls, dF, dE, lower_only=True, pad_to=n, pad_identity=True)
+        fac = C.Factorization(Kfac)
+        Phi, g0, g0KY = C.sobol_prepare(dX, dLam, dFdiag, KiY, True)
+
+        def err_sweep():
+            return C.sobol_error(dX, dLam, dFdiag, Phi, g0, g0KY, fac, masks)
+        for _ in range(2):
+            err_sweep()
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(3):
+            err_sweep()
+        q1.record()
+        torch.cuda.synchronize()
+        err_ms = q0.elapsed_time(q1) / 3
+        sobol_err = {'metric': 'sobol_error_sweeps_per_s', 'value': 1e3 / err_ms, 'unit': 'sweeps/s', 'ms_per_sweep': err_ms, 'slices': len(masks),
+                     'note': 'V and W (error covariances) of the 25 slices: 2 L^2 pairwise kernels per slice + one TRSM over all (slice, l, i) right-hand sides'}
+        del fac, Kfac
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline on this box's host cores (rank 0, single-GPU runs only) -------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -403,7 +428,7 @@ def run_b200(args):
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                         'ms_per_step': 1e3 * e2e_s / args.steps,
                         'path': 'romcomma.gpf.models.MOGPR(data=(pinned host X, Y), ...)._loss_and_grad: H2D of X, Y and hyper-parameters, D2H of LML+gradient'},
-                'gpu_launches': int(launches), 'concurrent_streams': concurrent, 'sobol': sobol, 'clocks': clocks.summary(), 'lml': lml}
+                'gpu_launches': int(launches), 'concurrent_streams': concurrent, 'sobol': sobol, 'sobol_with_error': sobol_err, 'clocks': clocks.summary(), 'lml': lml}
         emit(line)
     distributed.barrier()
 

@@ -380,7 +380,7 @@ static int launch_sweep(const SobolPairArgs& a, int npairs, cudaStream_t st) {
 }
 
 // index of a structured subset in the sweep kernel's output, or -1 for a general subset
-static int sweep_index(unsigned long long mask, int M) {
+int sobol_sweep_index(unsigned long long mask, int M) {
   const unsigned long long full = (M >= 64) ? ~0ull : ((1ull << M) - 1ull);
   if (mask == 0) return 3 * M - 1;
   if ((mask & (mask - 1)) == 0) {            // single input
@@ -471,7 +471,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
   if (M <= 12) {
     std::vector<int> structured, sidx;
     for (int s = 0; s < nslices; ++s) {
-      const int k = sweep_index(masks[s], M);
+      const int k = sobol_sweep_index(masks[s], M);
       if (k >= 0) {
         structured.push_back(s);
         sidx.push_back(k);

@@ -13,6 +13,10 @@ int sobol_prepare(const double* X, int N, int M, const double* Lam, const double
 
 size_t sobol_workspace_bytes(int N, int P, int ns);
 
+// Position of a structured subset (single input, prefix [0:k], suffix [k:M], full, empty) in the 3M outputs of the sweep-form kernels
+// { F[m] m<M | P[k] k=1..M | S[k] k=1..M-1 | E }, or -1 for a general subset.
+int sobol_sweep_index(unsigned long long mask, int M);
+
 // V[s][l][j] for s < nslices; masks are host-side bit sets over the M inputs (bit m set <=> input m is in the subset).
 // part/nparts: only the 64-row tiles ti with ti % nparts == part are evaluated (V is then a partial sum; 0/1 = everything).
 int sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int Lp, const unsigned long long* masks, int nslices,

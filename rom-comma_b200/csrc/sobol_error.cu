@@ -14,6 +14,8 @@
 #include "sobol.h"
 #include "chol.h"
 #include "common.cuh"
+#include <algorithm>
+#include <vector>
 
 namespace rc {
 
@@ -179,19 +181,164 @@ __global__ void __launch_bounds__(ETHREADS) sobol_error_matvec_kernel(ErrMatvecA
   }
 }
 
+
+// ---- sweep form of the mat-vec ----------------------------------------------------------------------------------------------
+// Like the closed indices (sobol.cu, sobol_sweep_kernel) the pairwise kernels factorise over the inputs, K_s = prod_{m in s} k_m with
+// k_m[N,n] = exp( cA_m x^2 + cK_m + cB_m y^2 + cC_m x y ), so the slices GSA sweeps (singles, prefixes, suffixes, full, empty) cost M exps per
+// (sample pair, job) instead of 3M+1.  CTA = (job, 16 columns n, chunk of SW_RCH rows N); thread (ty,tx) owns one column and walks the chunk
+// 4 rows at a time; its 3M column sums stay in registers, the k_m of a step are parked in thread-private shared-memory columns for the suffix scan.
+// Output layout per (job, row chunk):  [3M][T*32]  with the value order { F[m] | P[k] k=1..M | S[k] k=1..M-1 | E } of sobol_sweep_kernel.
+constexpr int SW_EC = 16;       // columns per CTA
+constexpr int SW_RCH = 512;     // rows per chunk
+
+template <int MAXM>
+__global__ void __launch_bounds__(ETHREADS, 2) sobol_error_sweep_kernel(ErrMatvecArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int M = p.M, RCH = p.RCH, nv = 3 * M;
+  double* cA = sm;                  // [M]
+  double* cB = cA + M;
+  double* cC = cB + M;
+  double* cK = cC + M;
+  double* xs = cK + M;              // [M][RCH]
+  double* wl = xs + (long)M * RCH;  // [RCH]
+  double* yc = wl + RCH;            // [M][16]   cC_m * y
+  double* y2 = yc + M * SW_EC;      // [M][16]   cB_m * y^2
+  double* red = y2 + M * SW_EC;     // [16][16]
+  double* hs = red + 16 * SW_EC;    // [M][4][256]
+
+  const int job = blockIdx.y, J = p.J;
+  const int tj = blockIdx.x / p.RC, rc = blockIdx.x - tj * p.RC;
+  const int li = job % (p.L * p.L), l = li / p.L;
+  const int tid = threadIdx.x;
+  const int row0 = rc * RCH, col0 = tj * SW_EC;
+  for (int m = tid; m < M; m += ETHREADS) {
+    cA[m] = p.coef[(0L * J + job) * M + m];
+    cB[m] = p.coef[(1L * J + job) * M + m];
+    cC[m] = p.coef[(2L * J + job) * M + m];
+    cK[m] = p.coef[(3L * J + job) * M + m];
+  }
+  __syncthreads();
+  for (long e = tid; e < (long)RCH * M; e += ETHREADS) {
+    const int r = (int)(e / M), m = (int)(e - (long)r * M);
+    const int gi = row0 + r;
+    xs[(long)m * RCH + r] = gi < p.N ? p.X[(long)gi * M + m] : 0.0;
+  }
+  for (int r = tid; r < RCH; r += ETHREADS) {
+    const int gi = row0 + r;
+    wl[r] = gi < p.N ? p.c[(long)l * p.N + gi] : 0.0;
+  }
+  for (int e = tid; e < SW_EC * M; e += ETHREADS) {
+    const int r = e / M, m = e - r * M;
+    const int gj = col0 + r;
+    const double y = gj < p.N ? p.X[(long)gj * M + m] : 0.0;
+    yc[m * SW_EC + r] = cC[m] * y;
+    y2[m * SW_EC + r] = cB[m] * y * y;
+  }
+  __syncthreads();
+
+  const int ty = tid >> 4, tx = tid & 15;       // 4 rows per step (ty), one column (tx)
+  double accF[MAXM], accP[MAXM], accS[MAXM], accE = 0.0;
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m) accF[m] = accP[m] = accS[m] = 0.0;
+  double* hme = hs + tid;
+#pragma unroll 1
+  for (int sub = 0; sub < RCH / 64; ++sub) {
+    const int r0 = sub * 64 + 4 * ty;
+    double w[4], run[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      w[q] = wl[r0 + q];
+      run[q] = w[q];
+      accE += w[q];
+    }
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+      if (m < M) {
+        const double b0 = yc[m * SW_EC + tx], v0 = y2[m * SW_EC + tx], ca = cA[m], ck = cK[m];
+        double f = 0.0, pr = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double x = xs[(long)m * RCH + r0 + q];
+          const double h = exp(fma(x, b0, fma(ca * x, x, ck) + v0));
+          if (m >= 1) hme[(m * 4 + q) * ETHREADS] = h;
+          f = fma(w[q], h, f);
+          run[q] *= h;
+          pr += run[q];
+        }
+        accF[m] += f;
+        accP[m] += pr;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) run[q] = w[q];
+#pragma unroll
+    for (int m = MAXM - 1; m >= 1; --m) {
+      if (m < M) {
+        double sf = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          run[q] *= hme[(m * 4 + q) * ETHREADS];
+          sf += run[q];
+        }
+        accS[m] += sf;
+      }
+    }
+  }
+  // column sums over the 16 thread rows, one output value at a time (fixed order)
+  double* outbase = p.parts + (((long)job * p.RC + rc) * nv) * ((long)p.T * SW_EC) + col0;
+  auto reduce_store = [&](double v, int slot) {
+    red[ty * SW_EC + tx] = v;
+    __syncthreads();
+    if (tid < SW_EC) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += red[k * SW_EC + tid];
+      outbase[(long)slot * ((long)p.T * SW_EC) + tid] = t;
+    }
+    __syncthreads();
+  };
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m) {
+    if (m < M) {
+      reduce_store(accF[m], m);
+      reduce_store(accP[m], M + m);                       // P[k], k = m+1
+      if (m >= 1) reduce_store(accS[m], 2 * M + m - 1);   // S[k], k = m
+    }
+  }
+  reduce_store(accE, 3 * M - 1);
+}
+
+template <int MAXM>
+static int launch_error_sweep(const ErrMatvecArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)(4 * a.M + (long)a.M * a.RCH + a.RCH + 2 * a.M * SW_EC + 16 * SW_EC + (long)a.M * 4 * ETHREADS) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    RC_CUDA_OK(cudaFuncSetAttribute(sobol_error_sweep_kernel<MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  RC_REQUIRE(smem <= 200 * 1024, -2, "sobol_error: shared memory %zu too large", smem);
+  sobol_error_sweep_kernel<MAXM><<<dim3(a.T * a.RC, a.J), ETHREADS, smem, st>>>(a);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+// slice -> (column of the mat-vec output, destination row of V / W); passed by value
+struct ErrMap {
+  int col[32];
+  int dest[32];
+};
+
 // ---- gather: V, the Omega bilinear forms R, and the right-hand sides g0_i * u_li of the triangular solve -----------------------------
 // grid (ns, L*L).  Covariant GP (chol_batch == 1): B is n_pad x ncol, column (s*L + l)*L + i, rows i*N + n.
 // Variant GP (chol_batch == L): problem i has its own N_pad x ncol block at B + i*strideB, column s*L + l, rows n.
-__global__ void sobol_error_gather_kernel(const double* __restrict__ parts, int L, int N, int RC, int ns, long ncols_u, const double* __restrict__ c,
+__global__ void sobol_error_gather_kernel(const double* __restrict__ parts, int L, int N, int RC, int nv, long ncols_u, const double* __restrict__ c,
                                           const double* __restrict__ g0, const double* __restrict__ pre, int chol_batch, double* __restrict__ B,
-                                          long ldb, long strideB, int s_offset, double* __restrict__ V, double* __restrict__ R) {
+                                          long ldb, long strideB, ErrMap map, double* __restrict__ V, double* __restrict__ R) {
   __shared__ double red[32];
   const int s = blockIdx.x, li = blockIdx.y, l = li / L, i = li - l * L;
-  const int J = 2 * L * L;
-  (void)J;
-  const double* pu = parts + (((long)(0 * L * L + li) * RC) * ns + s) * ncols_u;
-  const double* pw = parts + (((long)(1 * L * L + li) * RC) * ns + s) * ncols_u;
-  const long rc_stride = (long)ns * ncols_u;
+  const double* pu = parts + (((long)(0 * L * L + li) * RC) * nv + map.col[s]) * ncols_u;     // nv values per (job, row chunk)
+  const double* pw = parts + (((long)(1 * L * L + li) * RC) * nv + map.col[s]) * ncols_u;
+  const long rc_stride = (long)nv * ncols_u;
   double vacc = 0.0, racc = 0.0;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     double u = 0.0, w = 0.0;
@@ -208,7 +355,7 @@ __global__ void sobol_error_gather_kernel(const double* __restrict__ parts, int 
   vacc = block_sum(vacc, red);
   racc = block_sum(racc, red);
   if (threadIdx.x == 0) {
-    V[((long)(s_offset + s) * L + l) * L + i] = vacc;
+    V[((long)map.dest[s] * L + l) * L + i] = vacc;
     R[((long)s * L + l) * L + i] = pre[i] * racc;
   }
 }
@@ -229,7 +376,7 @@ __global__ void colnorm_partial_kernel(const double* __restrict__ B, long ldb, l
 
 // W[s][l][i] = Wraw[l][i] + Wraw[i][l],  Wraw[l][i] = (R[s][l][i] - |psi_li|^2) * (1 + [l == i])
 __global__ void sobol_error_W_kernel(const double* __restrict__ R, const double* __restrict__ partial, long stride_partial, int chunks, int ncols,
-                                     int L, int ns, int chol_batch, int s_offset, double* __restrict__ W) {
+                                     int L, int ns, int chol_batch, ErrMap map, double* __restrict__ W) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ns * L * L) return;
   const int s = e / (L * L), li = e - s * L * L, l = li / L, i = li - l * L;
@@ -240,7 +387,7 @@ __global__ void sobol_error_W_kernel(const double* __restrict__ R, const double*
     for (int k = 0; k < chunks; ++k) psi2 += pp[(long)k * ncols];
     return (R[((long)s * L + a) * L + b] - psi2) * (a == b ? 2.0 : 1.0);
   };
-  W[((long)(s_offset + s) * L + l) * L + i] = raw(l, i) + raw(i, l);
+  W[((long)map.dest[s] * L + l) * L + i] = raw(l, i) + raw(i, l);
 }
 
 namespace {
@@ -271,7 +418,11 @@ ErrLayout err_layout(int N, int M, int L, int nslices, int n_pad, int chol_batch
   size_t off = 0;
   o.coef = off; off += al((size_t)4 * J * M * sizeof(double));
   o.pre = off; off += al((size_t)L * sizeof(double));
-  o.parts = off; off += al((size_t)J * o.RC * o.chunk_slices * o.T * EC * sizeof(double));
+  {
+    const size_t general = (size_t)J * o.RC * o.chunk_slices * o.T * EC;                                        // [J][RC][chunk][T*64]
+    const size_t sweep = M <= 12 ? (size_t)J * ((N + SW_RCH - 1) / SW_RCH) * 3 * M * ((N + SW_EC - 1) / SW_EC) * SW_EC : 0;   // [J][RC'][3M][T'*32]
+    o.parts = off; off += al((general > sweep ? general : sweep) * sizeof(double));
+  }
   o.B = off; off += al((size_t)chol_batch * o.strideB * sizeof(double));
   o.partial = off; off += al((size_t)chol_batch * (n_pad / 128) * o.ncols * sizeof(double));
   o.R = off; off += al((size_t)o.chunk_slices * L * L * sizeof(double));
@@ -310,24 +461,61 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
   RC_REQUIRE(smem <= 220 * 1024, -2, "sobol_error: shared memory %zu too large", smem);
   const int chunks = n_pad / 128;
   const long stride_partial = (long)chunks * lay.ncols;
-  for (int s0 = 0; s0 < nslices; s0 += lay.chunk_slices) {
-    const int ns = nslices - s0 < lay.chunk_slices ? nslices - s0 : lay.chunk_slices;
-    ErrMatvecArgs a{};
-    a.X = X; a.N = N; a.M = M; a.coef = coef; a.c = g0KY; a.L = L; a.J = J; a.T = lay.T; a.RC = lay.RC; a.RCH = lay.RCH; a.ns = ns; a.parts = parts;
-    for (int s = 0; s < ns; ++s) a.masks[s] = masks[s0 + s];
-    sobol_error_matvec_kernel<<<dim3(lay.T * lay.RC, J), ETHREADS, smem, st>>>(a);
-    RC_LAUNCH_OK();
+  // Structured slices (singles, prefixes, suffixes, full, empty) share ONE sweep-form launch; general subsets take the summed-exponent kernel.
+  std::vector<int> structured, scol, general;
+  for (int s = 0; s < nslices; ++s) {
+    const int k = M <= 12 ? sobol_sweep_index(masks[s], M) : -1;
+    if (k >= 0) {
+      structured.push_back(s);
+      scol.push_back(k);
+    } else {
+      general.push_back(s);
+    }
+  }
+  auto finish_chunk = [&](const ErrMap& map, int ns, int nv, int RC, long ncols_u) -> int {
     RC_CUDA_OK(cudaMemsetAsync(B, 0, (size_t)chol_batch * lay.strideB * sizeof(double), st));
-    sobol_error_gather_kernel<<<dim3(ns, L * L), 256, 0, st>>>(parts, L, N, lay.RC, ns, (long)lay.T * EC, g0KY, g0, pre, chol_batch, B, lay.ldb,
-                                                               lay.strideB, s0, V, R);
+    sobol_error_gather_kernel<<<dim3(ns, L * L), 256, 0, st>>>(parts, L, N, RC, nv, ncols_u, g0KY, g0, pre, chol_batch, B, lay.ldb, lay.strideB, map,
+                                                               V, R);
     RC_LAUNCH_OK();
     int rc = trsm_lower_fwd(Achol, n_pad, ld, strideA, chol_batch, dinv, B, lay.ncols, lay.ldb, lay.strideB, st);
     if (rc) return rc;
     colnorm_partial_kernel<<<dim3((lay.ncols + 127) / 128, chunks, chol_batch), 128, 0, st>>>(B, lay.ldb, lay.strideB, lay.ncols, partial,
                                                                                                  stride_partial);
     RC_LAUNCH_OK();
-    sobol_error_W_kernel<<<(ns * L * L + 127) / 128, 128, 0, st>>>(R, partial, stride_partial, chunks, lay.ncols, L, ns, chol_batch, s0, W);
+    sobol_error_W_kernel<<<(ns * L * L + 127) / 128, 128, 0, st>>>(R, partial, stride_partial, chunks, lay.ncols, L, ns, chol_batch, map, W);
     RC_LAUNCH_OK();
+    return 0;
+  };
+  if (!structured.empty()) {
+    ErrMatvecArgs a{};
+    a.X = X; a.N = N; a.M = M; a.coef = coef; a.c = g0KY; a.L = L; a.J = J;
+    a.RCH = SW_RCH; a.RC = (N + SW_RCH - 1) / SW_RCH; a.T = (N + SW_EC - 1) / SW_EC; a.ns = 3 * M; a.parts = parts;
+    int rc = M <= 4 ? launch_error_sweep<4>(a, st) : M <= 8 ? launch_error_sweep<8>(a, st) : launch_error_sweep<12>(a, st);
+    if (rc) return rc;
+    for (size_t i0 = 0; i0 < structured.size(); i0 += lay.chunk_slices) {
+      const int ns = (int)std::min<size_t>(lay.chunk_slices, structured.size() - i0);
+      ErrMap map{};
+      for (int s = 0; s < ns; ++s) {
+        map.col[s] = scol[i0 + s];
+        map.dest[s] = structured[i0 + s];
+      }
+      if ((rc = finish_chunk(map, ns, 3 * M, a.RC, (long)a.T * SW_EC))) return rc;
+    }
+  }
+  for (size_t i0 = 0; i0 < general.size(); i0 += lay.chunk_slices) {
+    const int ns = (int)std::min<size_t>(lay.chunk_slices, general.size() - i0);
+    ErrMatvecArgs a{};
+    a.X = X; a.N = N; a.M = M; a.coef = coef; a.c = g0KY; a.L = L; a.J = J; a.T = lay.T; a.RC = lay.RC; a.RCH = lay.RCH; a.ns = ns; a.parts = parts;
+    ErrMap map{};
+    for (int s = 0; s < ns; ++s) {
+      a.masks[s] = masks[general[i0 + s]];
+      map.col[s] = s;
+      map.dest[s] = general[i0 + s];
+    }
+    sobol_error_matvec_kernel<<<dim3(lay.T * lay.RC, J), ETHREADS, smem, st>>>(a);
+    RC_LAUNCH_OK();
+    int rc = finish_chunk(map, ns, ns, lay.RC, (long)lay.T * EC);
+    if (rc) return rc;
   }
   return 0;
 }
