@@ -468,7 +468,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
   // Structured subsets (single inputs, prefixes, suffixes, full, empty: everything gsa.models.GSA asks for) go through the sweep form:
   // ONE launch whatever their number; only general subsets (the all-subsets sweep) pay one exp per (pair, subset) below.
   std::vector<int> general;
-  if (M <= 12) {
+  if (M <= 20) {
     std::vector<int> structured, sidx;
     for (int s = 0; s < nslices; ++s) {
       const int k = sobol_sweep_index(masks[s], M);
@@ -482,7 +482,8 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
     if (!structured.empty()) {
       SobolPairArgs a{};
       a.X = X; a.N = N; a.M = M; a.Phi = Phi; a.c = c; a.P = P; a.T = T; a.ns = 3 * M; a.parts = parts; a.part = part; a.nparts = nparts;
-      int rc = M <= 4 ? launch_sweep<4, 2>(a, npairs, st) : M <= 8 ? launch_sweep<8, 2>(a, npairs, st) : launch_sweep<12, 2>(a, npairs, st);
+      int rc = M <= 4 ? launch_sweep<4, 2>(a, npairs, st) : M <= 8 ? launch_sweep<8, 2>(a, npairs, st)
+               : M <= 12 ? launch_sweep<12, 2>(a, npairs, st) : launch_sweep<20, 1>(a, npairs, st);
       if (rc) return rc;
       // contiguous runs of output slots are finished together (<= SOBOL_MAX_SLICES per launch)
       size_t i = 0;

@@ -305,3 +305,17 @@ def test_sobol_pair_space_parts_add_up(C):
     for nparts in (2, 5):
         total = sum(C.sobol_contract(dX, Phi, g0KY, L, True, masks, None, part, nparts).cpu().numpy() for part in range(nparts))
         assert_close(total, full, rtol=1e-10, atol=1e-12, what=f'sum of {nparts} parts (summation order differs)')
+
+
+@pytest.mark.parametrize('N,M,L', [(100, 15, 2), (70, 20, 1), (130, 11, 3), (64, 1, 2)])
+def test_sobol_sweep_form_all_widths(C, N, M, L):
+    """Every register-tiling variant of the sweep-form kernel (M <= 4, 8, 12, 20) on the slice families GSA uses, against the oracle."""
+    X, Y, ls, F, E = random_problem(N, M, L, seed=7 * N + M, full_E=False)
+    KiY = gp.k_inv_y_mo(X, Y, ls, F, E)
+    dX = C.dev(X)
+    Phi, g0, g0KY = C.sobol_prepare(dX, C.dev(ls), C.dev(np.diag(F).copy()), C.dev(KiY.reshape(L, N)), True)
+    slices = [(m, m + 1) for m in range(M)] + [(0, m + 1) for m in range(M)] + [(m + 1, M) for m in range(M)] + [(0, M)]
+    V = C.sobol_contract(dX, Phi, g0KY, L, True, [C.slice_mask(*s) for s in slices]).cpu().numpy()
+    cal = sobol.ClosedSobol(X, ls, F, KiY, True)
+    for k, s in enumerate(slices):
+        assert_close(V[k], cal._V(*s), rtol=1e-8, atol=1e-12, what=f'slice {s}')
