@@ -204,6 +204,12 @@ WORKER = textwrap.dedent('''
     full = distributed.all_gather_rows(local, total)
     assert full.shape == (7, 2) and np.array_equal(full[:, 0], 10.0 * np.arange(7)), full
     assert distributed.all_reduce_max(float(r)) == 1.0 and distributed.all_reduce_sum(1.0) == 2.0
+    # the Sobol sweep's partial V (slices, L, L): each rank holds the sum over its row tiles, one all-reduce adds them
+    import torch
+    tiles = np.arange(12.0).reshape(6, 2, 1) * np.ones((6, 2, 2))          # 6 row tiles, contribution of tile t is t everywhere
+    part = torch.from_numpy(tiles[[t for t in range(6) if t % w == r]].sum(axis=0))
+    distributed.all_reduce_sum_tensor(part)
+    assert np.array_equal(part.numpy(), tiles.sum(axis=0)), part
     distributed.barrier()
     print('rank', r, 'ok')
 ''')
