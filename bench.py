@@ -34,9 +34,12 @@ for p in (ROOT, ROOT / 'rom-comma_b200'):
         sys.path.insert(0, str(p))
 
 METRIC, UNIT = 'mogpr_lml_grad_evals_per_s', 'evals/s'
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` captures (profiles/r01_ncu_syrk.md:
-# first rank-256 trailing update, 2.25 GB; profiles/r01_ncu_lauum.md: full LAUUM, 41.3 GB), per launch.  None until captured.
-NCU_TRAFFIC = {'syrk_rank256_first_launch_bytes': 2.254e9, 'lauum_full_launch_bytes': 41.29e9, 'source': 'profiles/r01_ncu_syrk.md, profiles/r01_ncu_lauum.md'}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (gemm_dmma_ws_kernel) from the committed `ncu --set full` captures, per
+# launch: the first rank-256 trailing update of potrf (profiles/r01_ncu_ws_syrk.md), the top level of trtri and the selected LAUUM
+# (profiles/r01_ncu_ws_trtri_lauum.md).  Algorithmic bytes of the same launches (operands once + C read/write): 2.1 GB, 1.6 GB, 0.8 GB - the
+# re-reads of the long-K launches are L2 capacity misses; at 1.1 TB/s (17 % of the HBM bandwidth) in the worst launch they are not the bound.
+NCU_TRAFFIC = {'syrk_rank256_first_launch_bytes': 2.230e9, 'trtri_top_level_launch_bytes': 18.02e9, 'lauum_selected_launch_bytes': 3.42e9,
+               'source': 'profiles/r01_ncu_ws_syrk.md, profiles/r01_ncu_ws_trtri_lauum.md'}
 
 
 def parse():
@@ -411,9 +414,9 @@ def run_b200(args):
                 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': workload_description(w, L, M), 'parallelism': f'replicas x{world} (one hyper-parameter point per GPU)',
                            'l2': 'inputs larger than L2: each step rewrites and re-reads 2.1 GB matrices (126 MB L2), no explicit flush needed'},
-                'roofline': {'bound': 'tensor', 'kernel': 'gemm_dmma_kernel (FP64 DMMA.8x8x4 tiles: Cholesky trailing update, TRSM, triangular inverse, LAUUM)',
+                'roofline': {'bound': 'tensor', 'kernel': 'gemm_dmma_ws_kernel (warp-specialised TMA-fed FP64 DMMA.8x8x4 tiles: Cholesky trailing update, triangular inverse, LAUUM)',
                              'achieved': achieved, 'peak': peaks['dmma_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['dmma_tflops'],
-                             'traffic': NCU_TRAFFIC['lauum_full_launch_bytes'], 'traffic_detail': NCU_TRAFFIC,
+                             'traffic': NCU_TRAFFIC['trtri_top_level_launch_bytes'], 'traffic_detail': NCU_TRAFFIC,
                              'launches_per_step': prof.launches, 'kernel_ms_per_step': prof.ms, 'kernel_share_of_step': prof.ms / ms_per_step,
                              'flops_per_step': prof.flops, 'reference_flops_per_step': float(n) ** 3,
                              'step_tflops_on_executed_flops': prof.flops / (ms_per_step * 1e-3) * 1e-12,
@@ -422,7 +425,7 @@ def run_b200(args):
                                      'n^3 (n^3/3 potrf + n^3/3 trtri + n^3/3 lauum) because, with the default trainables and a diagonal F, K^-1 is only '
                                      'formed on its diagonal (l,l) blocks (RC_GRAD_F_DIAGONAL); peak = FP64 tensor peak measured live by a '
                                      'register-resident DMMA loop (MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 is ~37-40 TFLOP/s); '
-                                     'traffic = ncu dram bytes (read+write) per launch averaged over the launches of profiles/r01_ncu_*.md',
+                                     'traffic = ncu dram bytes (read+write) of the launch with the most traffic (top level of trtri, 16.4 ms); see traffic_detail for the other captured launches',
                              'stages': stages},
                 'cpu_baseline': cpu,
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
