@@ -301,8 +301,8 @@ __global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs 
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
           const double a0 = gx[m * ST + r0 + u], u0 = su[m * ST + r0 + u];
-          h[2 * u] = exp(fma(a0, b0, u0 + v0));
-          h[2 * u + 1] = exp(fma(a0, b1, u0 + v1));
+          h[2 * u] = exp_pairwise(fma(a0, b0, u0 + v0));
+          h[2 * u + 1] = exp_pairwise(fma(a0, b1, u0 + v1));
         }
         double f = 0.0, pr = 0.0;
 #pragma unroll

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(ETHREADS, 2) sobol_error_sweep_kernel(ErrMatve
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const double x = xs[(long)m * RCH + r0 + q];
-          const double h = exp(fma(x, b0, fma(ca * x, x, ck) + v0));
+          const double h = exp_pairwise(fma(x, b0, fma(ca * x, x, ck) + v0));
           if (m >= 1) hme[(m * 4 + q) * ETHREADS] = h;
           f = fma(w[q], h, f);
           run[q] *= h;
