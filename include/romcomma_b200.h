@@ -102,6 +102,11 @@ int rc_extract_lower(const double* src, long ld, long stride_src, double* dst, i
  * RC_GRAD_LENGTHSCALES and for L > 1, batch == 1 this lets K^-1 be formed on the diagonal (l,l) blocks only ("selected" LAUUM);
  * the off-diagonal entries of dF are then returned as zero.  dE is always complete. */
 #define RC_GRAD_F_DIAGONAL 4
+/* With RC_OVERLAP_PANELS=<2..16> in the environment the gradient path of a single matrix (batch == 1) runs the independent part of the
+ * triangular inverse on an internal low-priority stream inside the idle phases of the factorisation (events fork from / join to
+ * `stream`; capturable).  Off by default (measured gain <= 1 %).  This bit keeps every kernel on `stream` regardless - what per-kernel
+ * timing (rc_profile_begin/end) needs.  Same results to rounding. */
+#define RC_NO_OVERLAP 8
 int rc_lml_grad_stride(int L, int M);
 size_t rc_lml_grad_bufsize(int N, int M, int L, int batch, int flags);
 int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch, const double* ls, const double* F, const double* E,

@@ -1,4 +1,5 @@
 // extern "C" boundary (include/romcomma_b200.h).  Plain pointers and sizes only; no torch types.
+#include <cstdlib>
 #include "../../include/romcomma_b200.h"
 #include "chol.h"
 #include "common.cuh"
@@ -211,6 +212,14 @@ int rc_lml_grad_stride(int L, int M) { return 1 + 2 * L * L + L * M; }
 namespace {
 // "Selected inversion": when dF is only wanted on its diagonal and no lengthscale gradient is requested, the gradient needs just
 // the diagonal (l,l) blocks of K^-1 and the diagonals of its off-diagonal blocks, so LAUUM is restricted to those tiles.
+// Column panels of the overlapped potrf + trtri (chol.cu).  OFF unless RC_OVERLAP_PANELS >= 2 is set in the environment: measured on the B200 it
+// gains 0.3-1 % (cfg3 119.8 -> 118.7 ms at 2-4 panels, cfg4 959.7 -> 954.1 ms), because only the one-CTA diagonal kernels leave SMs
+// free - a panel-solve CTA owns its SM's whole register file - which is not worth two extra streams on the default path.
+int overlap_panels() {
+  const char* e = getenv("RC_OVERLAP_PANELS");
+  const int v = e ? atoi(e) : 0;
+  return v < 0 ? 0 : v;
+}
 bool lml_selected(int L, int batch, int flags) {
   return (flags & RC_GRAD_F_DIAGONAL) && (flags & RC_GRAD_VARIANCE) && !(flags & RC_GRAD_LENGTHSCALES) && L > 1 && batch == 1;
 }
@@ -237,13 +246,15 @@ LmlLayout lml_layout(int N, int M, int L, int batch, int flags) {
 }
 }  // namespace
 
-size_t rc_lml_grad_bufsize(int N, int M, int L, int batch, int flags) { return lml_layout(N, M, L, batch, flags).total; }
+size_t rc_lml_grad_bufsize(int N, int M, int L, int batch, int flags) { return lml_layout(N, M, L, batch, flags & ~RC_NO_OVERLAP).total; }
 
 int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch, const double* ls, const double* F, const double* E,
                 const double* Kunit, int flags, void* work, size_t work_bytes, double* out, int* info, rc_stream_t stream) {
   RC_REQUIRE(X && Y && ls && F && E && work && out && info, -2, "rc_lml_grad: null pointer");
   RC_REQUIRE(N > 0 && M > 0 && L > 0 && batch > 0, -2, "rc_lml_grad: non-positive size");
   RC_REQUIRE(!Kunit || batch == 1, -2, "rc_lml_grad: a cached unit gram is only supported for batch == 1");
+  const bool overlap = !(flags & RC_NO_OVERLAP) && batch == 1 && (flags & ~RC_NO_OVERLAP) != RC_GRAD_NONE;
+  flags &= ~RC_NO_OVERLAP;
   const LmlLayout lay = lml_layout(N, M, L, batch, flags);
   RC_REQUIRE(work_bytes >= lay.total, -2, "rc_lml_grad: workspace too small (%zu < %zu)", work_bytes, lay.total);
   cudaStream_t st = (cudaStream_t)stream;
@@ -272,8 +283,12 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
     g.out = A; g.ld_out = n_pad; g.stride_out = mat; g.rows_pad = n_pad; g.cols_pad = n_pad; g.lower_only = 1; g.pad_identity = 1;
     if ((rc = gram(g, batch, st))) return rc;
   }
-  // 2. factor, log-determinant
-  if ((rc = potrf_lower(A, n_pad, n_pad, mat, batch, pw.dinv, pw.logdet_parts, info, st))) return rc;
+  // 2. factor, log-determinant (gradient of one matrix: Z = L^-1 is produced as well, its independent part inside the factorisation)
+  if (overlap) {
+    if ((rc = potrf_trtri_lower(A, n_pad, n_pad, pw.dinv, pw.logdet_parts, info, Kinv, (size_t)mat, overlap_panels(), st))) return rc;
+  } else if ((rc = potrf_lower(A, n_pad, n_pad, mat, batch, pw.dinv, pw.logdet_parts, info, st))) {
+    return rc;
+  }
   if ((rc = sum_parts(pw.logdet_parts, n_pad / TILE, batch, logdet, 1.0, st))) return rc;
   // 3. alpha = L^-1 y, quad = alpha^T alpha
   pack_y_kernel<<<dim3((n_pad + 255) / 256, batch), 256, 0, st>>>(Y, N, L, batch, n_pad, yv);
@@ -286,7 +301,7 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
     // 4. Z = L^-1 in place first: alpha = Z y and K^-1 y = Z^T alpha are then two passes over the triangle instead of
     //    2 x n/128 dependent substitution steps; K^-1 = Z^T Z.
     double* tg = reinterpret_cast<double*>(base + lay.tg);
-    if ((rc = trtri_lower(A, n_pad, n_pad, mat, batch, pw.dinv, Kinv, mat, st))) return rc;
+    if (!overlap && (rc = trtri_lower(A, n_pad, n_pad, mat, batch, pw.dinv, Kinv, mat, st))) return rc;
     if ((rc = tri_gemv_lower(A, n_pad, n_pad, mat, batch, yv, alpha, n_pad, 0, tg, st))) return rc;
     if ((rc = dot_batched(alpha, alpha, n_pad, n_pad, batch, quad, st))) return rc;
     if ((rc = tri_gemv_lower(A, n_pad, n_pad, mat, batch, alpha, kinvy, n_pad, 1, tg, st))) return rc;

@@ -9,6 +9,7 @@
 #include "chol.h"
 #include "gemm_dmma_ws.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 
@@ -392,7 +393,12 @@ size_t potrf_workspace_bytes(int n, int batch) {
          + (size_t)batch * nblk * sizeof(double);          // logdet parts
 }
 
-int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st) {
+// The factorisation proper.  `after_panel(done)` (optional) is called once the panel solve of block `done - 1` has been enqueued, i.e. when
+// block columns [0, done) of L are final for ALL rows in stream order - the hook the overlapped inverse below forks its side work from.
+// `invert_all`: finish with the batched launch of the 128 x 128 inverses (off the critical path).
+template <typename Hook>
+static int potrf_core(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st,
+                      Hook&& after_panel, bool invert_all) {
   RC_REQUIRE(n > 0 && n % DB == 0, -2, "potrf_lower: n=%d must be a positive multiple of 128", n);
   RC_REQUIRE(ld >= n && ld % 2 == 0, -2, "potrf_lower: ld=%ld must be even and >= n", ld);
   const int nblk = n / DB;
@@ -416,6 +422,7 @@ int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv
       if ((rc = launch_diag_factor(A, ld, strideA, dinv, strideD, b0 + 1, logdet_parts, nblk, info, batch, st))) return rc;
       if ((rc = trsm_panel(b0 + 1))) return rc;
     }
+    if ((rc = after_panel(b0 + w))) return rc;
     const long r0 = (long)(b0 + w) * DB;
     if (r0 < n) {   // trailing update, lower tiles only, rank 128*w
       GemmArgs g{};
@@ -427,8 +434,12 @@ int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv
     }
   }
   // the 128 x 128 inverses the solves / trtri need: all blocks in one wave, off the critical path
-  if ((rc = launch_diag_invert_all(A, ld, strideA, dinv, strideD, nblk, batch, st))) return rc;
+  if (invert_all && (rc = launch_diag_invert_all(A, ld, strideA, dinv, strideD, nblk, batch, st))) return rc;
   return 0;
+}
+
+int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st) {
+  return potrf_core(A, n, ld, strideA, batch, dinv, logdet_parts, info, st, [](int) { return 0; }, true);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -608,6 +619,140 @@ int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double
   g.C = Kinv; g.ldc = ldk; g.strideC = strideK;
   g.M = g.N = g.K = n; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 1; g.kmode = K_GE_M0;
   return launch_gemm_ws<true, true>(g, batch, st);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// potrf + trtri with the inverse OVERLAPPED into the factorisation (one matrix).
+//
+// The critical path of the right-looking Cholesky (diagonal factor -> panel solve, ~80 us per 128-block, ~10 ms at n = 16384) leaves
+// most SMs idle; trtri has no such chain.  With the block columns cut into `panels` column panels P_i = [s_i, s_i+1),
+//     Z_ii        = trtri(L_ii)                                   needs columns < s_i+1 of L
+//     T_i         = L[s_i+1:, P_i] * Z_ii                         needs columns < s_i+1 of L  (final for all rows once potrf passes s_i+1)
+//     Z[s_i+1:, P_i] = -Z[s_i+1:, s_i+1:] * T_i                   needs the inverse of the whole trailing block: after the factorisation, i descending
+// the first two lines (a third of the trtri flops at 8 panels) are enqueued on a low-priority SIDE stream as soon as the factorisation
+// has passed s_i+1, and the factorisation itself runs on an internal HIGH-priority stream: the T_i products are YIELDING launches (one
+// tile per CTA, launch_gemm_ws), so their CTAs fill whatever SMs the chain leaves idle and the block scheduler hands every SM that
+// retires to the pending chain / trailing-update CTAs first.  Same flops as trtri_lower (n^3/3), same tile kernel; every
+// tile is still computed by one CTA in a fixed order, so the result is bitwise reproducible (it differs in the last bits from
+// trtri_lower's pairing).  Works under stream capture (both internal streams are forked from and joined to `st` by events).
+// ----------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int OV_MAX_PANELS = 16;
+struct OverlapCtx {
+  int device = -1;
+  cudaStream_t user = nullptr;
+  cudaStream_t side = nullptr, hi = nullptr;
+  cudaEvent_t fork[OV_MAX_PANELS + 1] = {};
+  cudaEvent_t fork0 = nullptr, join = nullptr, join_hi = nullptr;
+};
+// one side stream + event set per (device, caller stream): two evaluations in flight on two streams do not serialise each other
+OverlapCtx* overlap_ctx(int device, cudaStream_t user) {
+  constexpr int MAX_CTX = 32;
+  static OverlapCtx ctx[MAX_CTX];
+  static int used = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < used; ++i)
+    if (ctx[i].device == device && ctx[i].user == user) return &ctx[i];
+  if (used == MAX_CTX) return nullptr;
+  OverlapCtx& c = ctx[used];
+  int lo = 0, hi = 0;
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;   // lo = least priority (what default streams have), hi = greatest
+  if (cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&c.hi, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&c.fork0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&c.join_hi, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  for (int i = 0; i <= OV_MAX_PANELS; ++i)
+    if (cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  c.device = device;
+  c.user = user;
+  ++used;
+  return &c;
+}
+}  // namespace
+
+size_t potrf_trtri_tmp_doubles(int n, int panels) {
+  const long nblk = n / DB;
+  if (panels < 2 || nblk < 2 * panels) return (size_t)n * n / 4;
+  long wblk = (nblk + panels - 1) / panels;
+  wblk += wblk & 1;
+  size_t total = (size_t)(wblk * DB) * (wblk * DB) / 4;   // scratch of the panel-local trtri
+  for (long s = 0; s + wblk < nblk; s += wblk) total += (size_t)(nblk - s - wblk) * DB * wblk * DB;
+  return total;
+}
+
+int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_parts, int* info, double* tmp, size_t tmp_doubles, int panels,
+                      cudaStream_t st) {
+  RC_REQUIRE(n > 0 && n % DB == 0, -2, "potrf_trtri_lower: n=%d must be a positive multiple of 128", n);
+  const int nblk = n / DB;
+  int rc;
+  if (panels > OV_MAX_PANELS) panels = OV_MAX_PANELS;
+  int dev = 0;
+  RC_CUDA_OK(cudaGetDevice(&dev));
+  OverlapCtx* cx = (panels >= 2 && nblk >= 2 * panels && potrf_trtri_tmp_doubles(n, panels) <= tmp_doubles) ? overlap_ctx(dev, st) : nullptr;
+  if (!cx) {   // small problem (nothing to hide) or no scratch: plain sequence
+    RC_REQUIRE(tmp_doubles >= (size_t)n * n / 4, -2, "potrf_trtri_lower: scratch too small");
+    if ((rc = potrf_lower(A, n, ld, 0, 1, dinv, logdet_parts, info, st))) return rc;
+    return trtri_lower(A, n, ld, 0, 1, dinv, tmp, 0, st);
+  }
+  int wblk = (nblk + panels - 1) / panels;
+  wblk += wblk & 1;                                   // panel boundaries on the factorisation's two-block steps
+  const int np = (nblk + wblk - 1) / wblk;
+  double* scratch = tmp;                              // panel-local trtri scratch, then the T_i one after the other
+  double* Tbase = tmp + (size_t)(wblk * DB) * (wblk * DB) / 4;
+  double* Tptr[OV_MAX_PANELS + 1];
+  {
+    double* t = Tbase;
+    for (int i = 0; i < np; ++i) {
+      Tptr[i] = t;
+      const long s1 = (long)(i + 1) * wblk;
+      if (s1 < nblk) t += (size_t)(nblk - s1) * DB * wblk * DB;
+    }
+  }
+  cudaStream_t side = cx->side, hi = cx->hi;
+  RC_CUDA_OK(cudaEventRecord(cx->fork0, st));
+  RC_CUDA_OK(cudaStreamWaitEvent(hi, cx->fork0, 0));
+  // side work of panel i, forked from the factorisation stream at its current position
+  auto panel_side_work = [&](int i) -> int {
+    const int s0 = i * wblk, s1 = std::min(nblk, (i + 1) * wblk), wn = (s1 - s0) * DB;
+    RC_CUDA_OK(cudaEventRecord(cx->fork[i], hi));
+    RC_CUDA_OK(cudaStreamWaitEvent(side, cx->fork[i], 0));
+    double* Aii = A + (long)s0 * DB * (ld + 1);
+    double* Dii = dinv + (long)s0 * DB * DB;
+    int r;
+    if ((r = launch_diag_invert_all(Aii, ld, 0, Dii, 0, s1 - s0, 1, side))) return r;
+    if ((r = trtri_lower(Aii, wn, ld, 0, 1, Dii, scratch, 0, side))) return r;
+    if (s1 < nblk) {   // T_i = L[s1:, P_i] * Z_ii, yielding
+      GemmArgs g{};
+      g.A = A + (long)s1 * DB * ld + (long)s0 * DB; g.lda = ld;
+      g.B = Aii; g.ldb = ld;
+      g.C = Tptr[i]; g.ldc = wn;
+      g.M = (nblk - s1) * DB; g.N = wn; g.K = wn; g.alpha = 1.0; g.beta = 0.0; g.kmode = K_GE_N0;
+      if ((r = launch_gemm_ws<false, true>(g, 1, side, 1))) return r;
+    }
+    return 0;
+  };
+  auto after_panel = [&](int done) -> int {
+    if (done % wblk == 0 || done == nblk) return panel_side_work((done - 1) / wblk);
+    return 0;
+  };
+  if ((rc = potrf_core(A, n, ld, 0, 1, dinv, logdet_parts, info, hi, after_panel, false))) return rc;
+  RC_CUDA_OK(cudaEventRecord(cx->join_hi, hi));
+  RC_CUDA_OK(cudaEventRecord(cx->join, side));
+  RC_CUDA_OK(cudaStreamWaitEvent(st, cx->join_hi, 0));
+  RC_CUDA_OK(cudaStreamWaitEvent(st, cx->join, 0));
+  for (int i = np - 2; i >= 0; --i) {   // Z[s1:, P_i] = -Z[s1:, s1:] * T_i
+    const int s0 = i * wblk, s1 = (i + 1) * wblk, wn = wblk * DB;
+    const long r = (long)s1 * DB;
+    GemmArgs u{};
+    u.A = A + r * ld + r; u.lda = ld;
+    u.B = Tptr[i]; u.ldb = wn;
+    u.C = A + r * ld + (long)s0 * DB; u.ldc = ld;
+    u.M = n - (int)r; u.N = wn; u.K = n - (int)r; u.alpha = -1.0; u.beta = 0.0; u.kmode = K_LT_M1;
+    if ((rc = launch_gemm_ws<false, true>(u, 1, st))) return rc;
+  }
+  return 0;
 }
 
 // dots[pair(l > l')][i] = sum_{k >= l*N+i} Z[k][l*N+i] * Z[k][l'*N+i] = K^-1[(l,i),(l',i)]: the diagonals of the off-diagonal

@@ -23,6 +23,13 @@ int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, con
 // A (holding L) <- L^-1 in place; tmp needs n*n/4 doubles per matrix.
 int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double* dinv, double* tmp, long strideT, cudaStream_t st);
 
+// potrf_lower + trtri_lower of ONE matrix with the independent part of the inverse running on a side stream inside the factorisation's
+// idle phases (chol.cu); on return (in stream order) A holds Z = L^-1, dinv the block inverses, logdet_parts / info as potrf_lower.
+// tmp: potrf_trtri_tmp_doubles(n, panels) doubles; panels < 2 (or a small n) selects the plain sequence.
+size_t potrf_trtri_tmp_doubles(int n, int panels);
+int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_parts, int* info, double* tmp, size_t tmp_doubles, int panels,
+                      cudaStream_t st);
+
 // Kinv(lower 128-tiles) = Z^T Z; sel_block > 0 restricts it to the tiles that intersect the diagonal blocks of that size.
 int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double* Kinv, long ldk, long strideK, int sel_block, cudaStream_t st);
 

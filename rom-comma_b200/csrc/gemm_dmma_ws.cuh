@@ -88,7 +88,7 @@ __device__ __forceinline__ void ws_load_operand(double* dst, const double* src, 
 
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, long tiles_per_matrix, long total_tiles, int* __restrict__ sched,
-                                                                    const __grid_constant__ CUtensorMap mapA,
+                                                                    int tiles_per_cta, const __grid_constant__ CUtensorMap mapA,
                                                                     const __grid_constant__ CUtensorMap mapB) {
   extern __shared__ __align__(16) double smem_raw[];
   using S = GemmWsSmem<TA, TB>;
@@ -120,12 +120,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
 
   if (warp == W_CONSUMERS) {
     // ---------------------------------------------------------------- producer
-    int stage = 0, slot = 0;
+    int stage = 0, slot = 0, drawn = 0;
     unsigned phase = 0, tphase = 0;
     for (;;) {
       long tile = -1;
       GemmTile T;
       for (;;) {   // draw tiles until one has work (skipped tiles of a selected list cost one decode)
+        if (tiles_per_cta > 0 && drawn == tiles_per_cta) break;   // yielding launch: this CTA has had its share, retire
         int t = 0;
         if (lane == 0) t = atomicAdd(sched, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
         T = gemm_decode_tile(p, t, tiles_per_matrix);
         if (T.nk >= 0) {
           tile = t;
+          ++drawn;
           break;
         }
       }
@@ -293,8 +295,11 @@ inline int make_operand_map(CUtensorMap* map, const double* ptr, long ld, long s
 constexpr int SCHED_SLOTS = 4096;
 int* gemm_sched_slot(int device);   // defined in chol.cu
 
+// tiles_per_cta = 0: persistent grid (one CTA per SM draws tiles until the list is empty).  tiles_per_cta = k > 0: a YIELDING launch of
+// ceil(tiles / k) CTAs that retire after k tiles each - for background work on a low-priority stream: the SMs return to the block
+// scheduler every few tiles, so pending CTAs of a higher-priority stream never wait longer than that.
 template <bool TA, bool TB>
-inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream) {
+inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream, int tiles_per_cta = 0) {
   using S = GemmWsSmem<TA, TB>;
   static bool configured = false;
   static int num_sms = 0;
@@ -312,7 +317,7 @@ inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream) {
   const long tm = a.M / G_BM, tn = a.N / G_BN;
   const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   const long total = tiles * batch;
-  const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
+  const unsigned grid = tiles_per_cta > 0 ? (unsigned)((total + tiles_per_cta - 1) / tiles_per_cta) : (unsigned)(total < num_sms ? total : num_sms);
   alignas(64) CUtensorMap mapA, mapB;
   memset(&mapA, 0, sizeof(mapA));
   memset(&mapB, 0, sizeof(mapB));
@@ -323,7 +328,7 @@ inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream) {
   if (prof) profile_gemm_begin(stream);
   int* sched = gemm_sched_slot(dev);
   RC_REQUIRE(sched != nullptr, -3, "gemm_dmma_ws: could not allocate the tile-scheduler scratch");
-  gemm_dmma_ws_kernel<TA, TB><<<grid, W_THREADS, S::BYTES, stream>>>(a, tiles, total, sched, mapA, mapB);
+  gemm_dmma_ws_kernel<TA, TB><<<grid, W_THREADS, S::BYTES, stream>>>(a, tiles, total, sched, tiles_per_cta, mapA, mapB);
   if (prof) profile_gemm_end(stream, gemm_tile_flops(a, batch));
   RC_LAUNCH_OK();
   return 0;

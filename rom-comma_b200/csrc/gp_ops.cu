@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
       const int l_j = lj[c], n_j = nj[c];
       double val;
       if (l_i >= 0 && l_j >= 0) {
-        val = exp(-0.5 * acc[u][v]);
+        val = exp_pairwise(-0.5 * acc[u][v]);
         if (F) val *= F[l_i * p.L + l_j];
         if (E && n_i == n_j) val += E[l_i * p.L + l_j];
       } else {
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(GTHREADS) grad_reduce_kernel(GradArgs p) {
       const bool valid = li[r] >= 0 && lj[c] >= 0 && gj <= gi && (!p.diag_blocks_only || li[r] == lj[c]);
       const double wgt = (gj < gi && li[r] == lj[c]) ? 2.0 : 1.0;   // diagonal (l,l) blocks are symmetric: count the mirror
       const double W = valid ? (ar[r] * ac[c] - kv[v]) : 0.0;
-      const double U = exp(-0.5 * d2[u][v]);
+      const double U = exp_pairwise(-0.5 * d2[u][v]);
       wu[u][v] = wgt * W * U;
       wn[u][v] = (valid && ni[r] == nj[c]) ? wgt * W : 0.0;
       wfu[u][v] = (valid && gj < gi) ? W * U * F[li[r] * L + lj[c]] : 0.0;

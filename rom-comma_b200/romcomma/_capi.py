@@ -17,7 +17,7 @@ _LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / 'librc_b200.so'
 _lib: Optional[ctypes.CDLL] = None
 
 c_double_p = ctypes.c_void_p
-RC_GRAD_NONE, RC_GRAD_VARIANCE, RC_GRAD_LENGTHSCALES, RC_GRAD_F_DIAGONAL = 0, 1, 2, 4
+RC_GRAD_NONE, RC_GRAD_VARIANCE, RC_GRAD_LENGTHSCALES, RC_GRAD_F_DIAGONAL, RC_NO_OVERLAP = 0, 1, 2, 4, 8
 
 _SIGNATURES = {
     'rc_version': (ctypes.c_int, []),

@@ -107,7 +107,7 @@ def gsa(name: str, repo: Repository, is_covariant: Optional[bool], is_isotropic:
         is_covariant, is_isotropic: select the model as in ``gpr``; None runs both.
         kinds: first_order, closed or total; a Sequence runs consecutively.
         m: a single input ``0 <= m < M``, or anything else for all of them.
-        is_error_calculated: errors on the indices (not available in this build).
+        is_error_calculated: also compute the standard errors T and covariances W of the indices (ClosedSobolWithError).
         kwargs: calculation options which update the GSA META.
     Returns: The calculation folders which have been written, relative to repo.folder.
     """

@@ -142,6 +142,36 @@ def test_lml_grad_selected_inverse(C, N, M, L):
     assert np.all(res['dls'] == 0.0)
 
 
+@pytest.mark.parametrize('N,M,L,panels', [(700, 4, 3, 8), (1100, 3, 2, 8), (1024, 5, 2, 4), (600, 3, 4, 2), (900, 2, 3, 16)])
+def test_lml_grad_overlapped_inverse(C, N, M, L, panels, monkeypatch):
+    """The default gradient path of one matrix runs Z_ii = trtri(L_ii) and T_i = L[below, P_i] Z_ii of every column panel on a side stream
+    inside the factorisation (chol.cu: potrf_trtri_lower) - ragged last panels included.  It must match the oracle, the one-stream
+    sequence (RC_NO_OVERLAP) to rounding, and itself bit for bit from call to call."""
+    monkeypatch.setenv('RC_OVERLAP_PANELS', str(panels))
+    X, Y, ls, F, E = random_problem(N, M, L, seed=N + 3, full_F=False)
+    args = (C.dev(ls), C.dev(F[None]), C.dev(E[None]))
+    flags = C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES
+    plan = C.LmlGradPlan(C.dev(X), C.dev(Y), L, 1, flags)
+    out1 = plan(*args).cpu().numpy().copy()
+    plan.work.fill_(0xFF)   # poisoned scratch (NaN bit patterns) must not matter
+    out2 = plan(*args).cpu().numpy().copy()
+    assert plan.info.cpu().tolist() == [0]
+    assert np.array_equal(out1, out2), 'overlapped evaluation is not bitwise reproducible'
+    serial = C.LmlGradPlan(C.dev(X), C.dev(Y), L, 1, flags | C.RC_NO_OVERLAP)
+    out_s = serial(*args).cpu().numpy()
+    res, res_s = plan.unpack(out1)[0], serial.unpack(out_s)[0]
+    ref = gp.lml_grad_mo(X, Y, ls, F, E)
+    assert_close(res['lml'], ref['lml'], what='lml')
+    for k in ('dF', 'dE', 'dls'):
+        assert_close(res[k], ref[k], atol=1e-10 * L * N, what=k)
+        assert_close(res[k], res_s[k], atol=1e-10 * L * N, what=k + ' (overlapped vs one stream)')
+    # the selected-inverse variant on the same path
+    sel = C.LmlGradPlan(C.dev(X), C.dev(Y), L, 1, C.RC_GRAD_VARIANCE | C.RC_GRAD_F_DIAGONAL)
+    r2 = sel.unpack(sel(*args).cpu().numpy())[0]
+    assert_close(np.diag(r2['dF']), np.diag(ref['dF']), atol=1e-10 * L * N, what='diag dF (selected)')
+    assert_close(r2['dE'], ref['dE'], atol=1e-10 * L * N, what='dE (selected)')
+
+
 def test_lml_grad_variant_batch(C):
     X, Y, ls, F, E = random_problem(180, 6, 3, seed=21, full_E=False)
     var, noise = np.diag(F).copy(), np.diag(E).copy()
@@ -321,9 +351,11 @@ def test_sobol_sweep_form_all_widths(C, N, M, L):
         assert_close(V[k], cal._V(*s), what=f'slice {s}')
 
 
-def test_lml_grad_plan_cuda_graph_replay_is_bit_identical(C):
-    """Opt-in CUDA-graph replay of the evaluation (LmlGradPlan(use_graph=True)): same bits as the eager launches, for changing hyper-parameters."""
-    X, Y, ls, F, E = random_problem(300, 4, 2, seed=31, full_E=False)
+@pytest.mark.parametrize('N', [300, 700])
+def test_lml_grad_plan_cuda_graph_replay_is_bit_identical(C, N):
+    """Opt-in CUDA-graph replay of the evaluation (LmlGradPlan(use_graph=True)): same bits as the eager launches, for changing hyper-parameters.
+    N=700 (n_pad = 1408, 11 blocks) takes the overlapped potrf+trtri, whose two internal streams are forked and joined inside the capture."""
+    X, Y, ls, F, E = random_problem(N, 4, 2, seed=31, full_E=False)
     dX, dY = C.dev(X), C.dev(Y)
     flags = C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES
     eager, graph = C.LmlGradPlan(dX, dY, 2, 1, flags, use_graph=False), C.LmlGradPlan(dX, dY, 2, 1, flags, use_graph=True)
