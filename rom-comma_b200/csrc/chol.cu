@@ -10,6 +10,7 @@
 #include "gemm_dmma_ws.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 
@@ -534,28 +535,42 @@ int trsv_lower(const double* A, int n, long ld, long strideA, int batch, const d
 // ----------------------------------------------------------------------------------------------------------------
 // Multi right-hand-side forward solve  B <- L^-1 B  (B is n x nrhs row-major, nrhs a multiple of 128), GEMM based.
 // ----------------------------------------------------------------------------------------------------------------
+// Two levels (wide right-hand sides): inside a super-block of TRSM_SB 128-blocks the classic right-looking substitution (B_k <- Dinv_k B_k, then a K = 128 update
+// of the few block rows left in the super-block - latency-sized launches), then ONE update of everything below the super-block with
+// K = 128 * TRSM_SB, long enough for the tile kernel to run near its peak (K = 128 updates of the whole remainder ran at ~60 % of it).
+// Measured at n = 16384 (tools/time_predict.py, profiles/r01_trsm_predict.jsonl): 512 right-hand sides 10.2 ms with super-block 1 vs 11.1 with 8
+// (the launches are latency-sized either way); 2048: 24.7 -> 22.4 ms; 8192: 81.2 -> 70.6 ms (27.1 -> 31.2 TFLOP/s).
+static int trsm_super_block(int nrhs) {
+  const char* e = getenv("RC_TRSM_SB");
+  const int v = e ? atoi(e) : (nrhs <= 1024 ? 1 : 8);
+  return v < 1 ? 1 : v;
+}
 int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, const double* dinv, double* B, int nrhs, long ldb, long strideB,
                    cudaStream_t st) {
   RC_REQUIRE(n % DB == 0 && nrhs % DB == 0, -2, "trsm_lower_fwd: n=%d and nrhs=%d must be multiples of 128", n, nrhs);
-  const int nblk = n / DB;
+  const int nblk = n / DB, TRSM_SB = trsm_super_block(nrhs);
   const long strideD = (long)nblk * DB * DB;
   int rc;
-  for (int k = 0; k < nblk; ++k) {
-    GemmArgs g{};   // B_k <- Dinv_k * B_k   (tile-exclusive in place: a CTA owns its 128 columns over all 128 k-rows)
-    g.A = dinv + (long)k * DB * DB; g.lda = DB; g.strideA = strideD;
-    g.B = B + (long)k * DB * ldb; g.ldb = ldb; g.strideB = strideB;
-    g.C = B + (long)k * DB * ldb; g.ldc = ldb; g.strideC = strideB;
-    g.M = DB; g.N = nrhs; g.K = DB; g.alpha = 1.0; g.beta = 0.0; g.kmode = K_FULL;
-    if ((rc = launch_gemm_ws<false, true>(g, batch, st))) return rc;
-    const int r0 = (k + 1) * DB;
-    if (r0 < n) {   // B[i>k] -= L[i,k] * B_k
-      GemmArgs u{};
-      u.A = A + (long)r0 * ld + (long)k * DB; u.lda = ld; u.strideA = strideA;
-      u.B = B + (long)k * DB * ldb; u.ldb = ldb; u.strideB = strideB;
-      u.C = B + (long)r0 * ldb; u.ldc = ldb; u.strideC = strideB;
-      u.M = n - r0; u.N = nrhs; u.K = DB; u.alpha = -1.0; u.beta = 1.0; u.kmode = K_FULL;
-      if ((rc = launch_gemm_ws<false, true>(u, batch, st))) return rc;
+  auto update = [&](int r0, int r1, int k0, int k1) -> int {   // B[r0:r1] -= L[r0:r1, k0:k1] * B[k0:k1]   (block indices)
+    GemmArgs u{};
+    u.A = A + (long)r0 * DB * ld + (long)k0 * DB; u.lda = ld; u.strideA = strideA;
+    u.B = B + (long)k0 * DB * ldb; u.ldb = ldb; u.strideB = strideB;
+    u.C = B + (long)r0 * DB * ldb; u.ldc = ldb; u.strideC = strideB;
+    u.M = (r1 - r0) * DB; u.N = nrhs; u.K = (k1 - k0) * DB; u.alpha = -1.0; u.beta = 1.0; u.kmode = K_FULL;
+    return launch_gemm_ws<false, true>(u, batch, st);
+  };
+  for (int k0 = 0; k0 < nblk; k0 += TRSM_SB) {
+    const int k1 = std::min(nblk, k0 + TRSM_SB);
+    for (int k = k0; k < k1; ++k) {
+      GemmArgs g{};   // B_k <- Dinv_k * B_k   (tile-exclusive in place: a CTA owns its 128 columns over all 128 k-rows)
+      g.A = dinv + (long)k * DB * DB; g.lda = DB; g.strideA = strideD;
+      g.B = B + (long)k * DB * ldb; g.ldb = ldb; g.strideB = strideB;
+      g.C = B + (long)k * DB * ldb; g.ldc = ldb; g.strideC = strideB;
+      g.M = DB; g.N = nrhs; g.K = DB; g.alpha = 1.0; g.beta = 0.0; g.kmode = K_FULL;
+      if ((rc = launch_gemm_ws<false, true>(g, batch, st))) return rc;
+      if (k + 1 < k1 && (rc = update(k + 1, k1, k, k + 1))) return rc;
     }
+    if (k1 < nblk && (rc = update(k1, nblk, k0, k1))) return rc;
   }
   return 0;
 }
