@@ -283,21 +283,24 @@ class _GPR(Module):
         return self._predict(Xnew, full_cov, full_output_cov, True)
 
 
-def predict_core(X, Y, ls, F, E, Xn, L: int, batch: int, y_instead_of_f: bool = False):
+def predict_core(X, Y, ls, F, E, Xn, L: int, batch: int, y_instead_of_f: bool = False, fac=None):
     """Shared by the variant and covariant models. Returns mean and variance, each (batch, n*, L), on the device.
 
     mean = Kmn^T K^-1 y and var = diag(Knn) - colsumsq(L^-1 Kmn) (+ diag E): gpflow ``base_conditional`` (called at
     romcomma/gpf/models.py:97 and inside gpflow GPR.predict_f) without the full (L n*)^2 covariance.
-    F, E are host arrays (batch, L, L).
+    F, E are host arrays (batch, L, L).  ``fac``: an existing factorisation of the noisy gram at exactly these hyper-parameters
+    (romcomma.gpr.models.MOGP keeps one per fitted GP); without it the gram is built and factorised here, as the reference does per call.
     """
     N, nstar = X.shape[0], Xn.shape[0]
     n, c = L * N, L * nstar
     n_pad, c_pad = _capi.padded(n), _capi.padded(c)
     F, E = np.asarray(F, dtype=np.float64).reshape(batch, L, L), np.asarray(E, dtype=np.float64).reshape(batch, L, L)
     dF, dE = _capi.dev(F), _capi.dev(E)
-    Kmm = _capi.gram(X, None, ls, dF, dE, batch=batch, lower_only=True, pad_to=n, pad_identity=True)
-    fac = _capi.Factorization(Kmm)
-    fac.raise_if_failed()
+    if fac is None:
+        Kmm = _capi.gram(X, None, ls, dF, dE, batch=batch, lower_only=True, pad_to=n, pad_identity=True)
+        fac = _capi.Factorization(Kmm)
+        fac.raise_if_failed()
+    assert fac.batch == batch and fac.n_pad == n_pad
     y = torch.zeros((batch, n_pad), dtype=torch.float64, device=X.device)
     y[:, :n] = Y.reshape(N, batch, L).permute(1, 2, 0).reshape(batch, n)          # y = vec(Y^T) per problem (gpf/models.py:130)
     alpha = fac.trsv(y)

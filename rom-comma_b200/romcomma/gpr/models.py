@@ -231,6 +231,7 @@ class MOGP(GPR):
 
     def calibrate(self, method: str = 'L-BFGS-B', **kwargs) -> Dict[str, Any]:
         """ Optimize the hyper-parameters. ``kernel={...}`` / ``likelihood={...}`` override the trainability META of each."""
+        self._fac_cache = self._kiy_cache = None
         meta = (self.read_meta() if self._meta_json.exists() else self.META)
         kernel_options = self._kernel.calibrate(**(meta.pop('kernel', {}) | kwargs.pop('kernel', {})))
         likelihood_options = self._likelihood.calibrate(**(meta.pop('likelihood', {}) | kwargs.pop('likelihood', {})))
@@ -265,16 +266,29 @@ class MOGP(GPR):
         return _capi.dev(ls), F, E, 1, self._L
 
     def _factorize(self):
+        """ The Cholesky factorisation of the noisy gram at the CURRENT hyper-parameters, kept until they change.
+
+        The reference factorises afresh in K_cho, again inside K_inv_Y (gpr/models.py:427-444: two Choleskys per Sobol calibrator, six per
+        fold of user.run.gsa) and again in every predict; here predict, predict_gradient, K_cho, K_inv_Y and the Sobol calibrators of one
+        fitted GP share one factor (same numbers: it is the same deterministic computation, done once).  The factor is read-only for
+        its users; ``calibrate`` drops it before the optimiser allocates its own workspace."""
         ls, F, E, L, batch = self._hyper()
+        key = (ls.cpu().numpy().tobytes(), np.ascontiguousarray(F).tobytes(), np.ascontiguousarray(E).tobytes())
+        cached = getattr(self, '_fac_cache', None)
+        if cached is not None and cached[0] == key:
+            return cached[1], L, batch
+        self._fac_cache = None
         Xd = as_device(self._X)
         K = _capi.gram(Xd, None, ls, _capi.dev(F), _capi.dev(E), batch=batch, lower_only=True, pad_to=L * self._N, pad_identity=True)
         fac = _capi.Factorization(K)
         fac.raise_if_failed()
+        self._fac_cache = (key, fac)
         return fac, L, batch
 
     def predict(self, X: NP.Matrix, y_instead_of_f: bool = True) -> Tuple[NP.Matrix, NP.Matrix]:
         ls, F, E, L, batch = self._hyper()
-        mean, var = gf.predict_core(as_device(self._X), as_device(self._Y), ls, F, E, as_device(np.asarray(X, dtype=FLOAT())), L, batch, y_instead_of_f)
+        mean, var = gf.predict_core(as_device(self._X), as_device(self._Y), ls, F, E, as_device(np.asarray(X, dtype=FLOAT())), L, batch, y_instead_of_f,
+                                    fac=self._factorize()[0])
         mean, var = mean.cpu().numpy(), var.cpu().numpy()                       # (batch, o, L_problem)
         mean = np.concatenate(list(mean), axis=1)
         var = np.concatenate(list(var), axis=1)
@@ -331,11 +345,16 @@ class MOGP(GPR):
     @property
     def K_inv_Y(self) -> DeviceTensor:
         fac, L, batch = self._factorize()
+        cached = getattr(self, '_kiy_cache', None)
+        if cached is not None and cached[0] is fac:          # same factor object = same hyper-parameters (see _factorize)
+            return DeviceTensor.wrap(cached[1].clone())
         n = L * self._N
         y = torch.zeros((batch, fac.n_pad), dtype=torch.float64, device='cuda')
         y[:, :n] = as_device(self._Y).reshape(self._N, batch, L).permute(1, 2, 0).reshape(batch, n)
         x = fac.trsv(fac.trsv(y), transpose=True)
-        return DeviceTensor.wrap(x[:, :n].reshape(self._L, 1, self._N).contiguous())
+        x = x[:, :n].reshape(self._L, 1, self._N).contiguous()
+        self._kiy_cache = (fac, x)
+        return DeviceTensor.wrap(x.clone())
 
     def check_K_inv_Y(self, x: NP.Matrix) -> NP.Matrix:
         """ FOR TESTING PURPOSES ONLY. kernel(x, X) K_inv_Y - predicted mean: should be 0 to within numerical tolerance."""
