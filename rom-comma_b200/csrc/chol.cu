@@ -308,16 +308,16 @@ panel_trsm_kernel(double* __restrict__ A, long ld, long strideA, int blk) {
       acc[h][c][0] = v.x;
       acc[h][c][1] = v.y;
     }
-  for (int idx = tid; idx < DB * (DB / 2); idx += 256) {         // stage the factor: 64 double2 per row, coalesced
+  // Stage the factor with cp.async (16 B per request, coalesced, all 32 requests of a thread in flight at once): as a load -> store loop
+  // the 32 iterations were 32 serial L2 round trips - half of this kernel's 40 us (ncu source view: long-scoreboard + barrier samples).
+  for (int idx = tid; idx < DB * (DB / 2); idx += 256) {
     const int k = idx >> 6, j2 = (idx & 63) * 2;
-    if (j2 <= k) {
-      const double2 v = *reinterpret_cast<const double2*>(Lb + (long)k * ld + j2);
-      Ls[k * PT_LP + j2] = v.x;
-      Ls[k * PT_LP + j2 + 1] = v.y;
-      if (j2 == k) rinv[k] = 1.0 / v.x;
-      if (j2 + 1 == k) rinv[k] = 1.0 / v.y;
-    }
+    if (j2 <= k) cp_async16(Ls + k * PT_LP + j2, Lb + (long)k * ld + j2);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  if (tid < DB) rinv[tid] = 1.0 / Ls[tid * PT_LP + tid];
   __syncthreads();
   double* Xs = Xs_all + warp * 16 * PT_XP;
   const int rr = lane >> 1, par = lane & 1;                        // substitution: row rr of the warp, columns of parity par

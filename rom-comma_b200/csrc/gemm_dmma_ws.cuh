@@ -26,7 +26,7 @@
 
 namespace rc {
 
-constexpr int W_STAGES = 6, W_CONSUMERS = 8, W_THREADS = 32 * (W_CONSUMERS + 1), W_RING = 4;
+constexpr int W_STAGES = 6, W_CONSUMERS = 8, W_THREADS = 32 * (W_CONSUMERS + 1), W_RING = 4, W_EPI_ROWS = 2;
 
 template <bool TA, bool TB>
 struct GemmWsSmem {
@@ -237,23 +237,37 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
     // Every operand byte of this tile has landed in shared memory (this warp waited on the tile's last "full" barrier), so the
     // tile-exclusive in-place updates the drivers rely on (C aliasing A or B of the SAME tile) stay safe.
     const double alpha = p.alpha, beta = p.beta;
+    if (beta == 0.0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const long row = T.m0 + wm * 64 + i * 8 + g;
+      for (int i = 0; i < 8; ++i) {
+        const long row = T.m0 + wm * 64 + i * 8 + g;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int col = T.n0 + wn * 32 + j * 8 + t * 2;
-        double2* cp = reinterpret_cast<double2*>(T.C + row * p.ldc + col);
-        double2 v;
-        if (beta == 0.0) {
-          v.x = alpha * acc[i][j][0];
-          v.y = alpha * acc[i][j][1];
-        } else {
-          const double2 o = *cp;
-          v.x = fma(alpha, acc[i][j][0], beta * o.x);
-          v.y = fma(alpha, acc[i][j][1], beta * o.y);
+        for (int j = 0; j < 4; ++j) {
+          const int col = T.n0 + wn * 32 + j * 8 + t * 2;
+          *reinterpret_cast<double2*>(T.C + row * p.ldc + col) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
         }
-        *cp = v;
+      }
+    } else {
+      // Read-modify-write of C, W_EPI_ROWS fragment rows at a time: all their loads are issued before the first store.  Written as
+      // load / fma / store per element the compiler may not move a load above an earlier store (same array, run-time ldc), which made
+      // the epilogue eight dependent L2 round trips per warp - most of what a K = 256 trailing-update tile lost against a long-K tile.
+#pragma unroll
+      for (int i0 = 0; i0 < 8; i0 += W_EPI_ROWS) {
+        double2 o[W_EPI_ROWS][4];
+#pragma unroll
+        for (int i = 0; i < W_EPI_ROWS; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[i][j] = *reinterpret_cast<const double2*>(T.C + (long)(T.m0 + wm * 64 + (i0 + i) * 8 + g) * p.ldc + T.n0 + wn * 32 + j * 8 + t * 2);
+#pragma unroll
+        for (int i = 0; i < W_EPI_ROWS; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double2 v;
+            v.x = fma(alpha, acc[i0 + i][j][0], beta * o[i][j].x);
+            v.y = fma(alpha, acc[i0 + i][j][1], beta * o[i][j].y);
+            *reinterpret_cast<double2*>(T.C + (long)(T.m0 + wm * 64 + (i0 + i) * 8 + g) * p.ldc + T.n0 + wn * 32 + j * 8 + t * 2) = v;
+          }
       }
     }
   }

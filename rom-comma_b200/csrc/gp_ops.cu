@@ -16,21 +16,22 @@ constexpr int GTHREADS = 256;   // 16 x 16 threads, 4 x 4 outputs each
 // (transposed so that the inner loop reads consecutive doubles). Indices >= L*Npts are padding (coordinate 0, l = -1).
 __device__ __forceinline__ void stage_scaled(double* __restrict__ s, int* __restrict__ lidx, int* __restrict__ nidx, const double* __restrict__ X,
                                              int Npts, int M, const double* __restrict__ ls, int L, long g0) {
+  const int total = L * Npts, base = (int)g0;                       // L * N < 2^31 (row tiles are limited to 65535 x 64)
   for (int e = threadIdx.x; e < GT * M; e += GTHREADS) {
     const int r = e / M, m = e - r * M;
-    const long gi = g0 + r;
+    const int gi = base + r;
     double v = 0.0;
-    if (gi < (long)L * Npts) {
-      const int l = (int)(gi / Npts), n = (int)(gi - (long)l * Npts);
+    if (gi < total) {
+      const int l = gi / Npts, n = gi - l * Npts;
       v = X[(long)n * M + m] / ls[l * M + m];
     }
     s[m * GT + r] = v;
   }
   for (int r = threadIdx.x; r < GT; r += GTHREADS) {
-    const long gi = g0 + r;
-    if (gi < (long)L * Npts) {
-      lidx[r] = (int)(gi / Npts);
-      nidx[r] = (int)(gi % Npts);
+    const int gi = base + r;
+    if (gi < total) {
+      lidx[r] = gi / Npts;
+      nidx[r] = gi % Npts;
     } else {
       lidx[r] = -1;
       nidx[r] = -1;
@@ -39,27 +40,23 @@ __device__ __forceinline__ void stage_scaled(double* __restrict__ s, int* __rest
 }
 
 // out[i][j] = F[l_i,l_j] * exp(-1/2 |s_i - s_j|^2) + E[l_i,l_j] * [n_i == n_j];  identity in the padding (square case).
+// One CTA per 64-row x (GSTRIP * 64)-column strip: the scaled coordinates of the rows are staged once and the prologue (global loads,
+// the divisions by the lengthscales, one barrier) is paid once per GSTRIP tiles; with one tile per CTA the prologue latency was ~60 % of
+// the kernel (0.72 ms for the 1.07 GB lower triangle at n = 16384; FP64 issue and HBM both far from busy).
+constexpr int GSTRIP = 4;
 __global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
   extern __shared__ __align__(16) double sm[];
-  double* sr = sm;
-  double* sc = sm + GT * p.M;
-  int* li = reinterpret_cast<int*>(sm + 2 * GT * p.M);
+  double* sr = sm;                              // [M][64]
+  double* sc = sm + GT * p.M;                   // [GSTRIP][M][64]
+  int* li = reinterpret_cast<int*>(sm + (1 + GSTRIP) * GT * p.M);
   int* ni = li + GT;
-  int* lj = ni + GT;
-  int* nj = lj + GT;
+  int* lj = ni + GT;                            // [GSTRIP][64]
+  int* nj = lj + GSTRIP * GT;                   // [GSTRIP][64]
 
-  int ti, tj;
-  if (p.lower_only) {
-    const int idx = blockIdx.x;
-    ti = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
-    while ((long)(ti + 1) * (ti + 2) / 2 <= idx) ++ti;
-    while ((long)ti * (ti + 1) / 2 > idx) --ti;
-    tj = idx - ti * (ti + 1) / 2;
-  } else {
-    const int tcols = p.cols_pad / GT;
-    ti = blockIdx.x / tcols;
-    tj = blockIdx.x - ti * tcols;
-  }
+  const int ti = blockIdx.y, tj0 = blockIdx.x * GSTRIP;
+  int ntj = min(GSTRIP, p.cols_pad / GT - tj0);
+  if (p.lower_only) ntj = min(ntj, ti - tj0 + 1);
+  if (ntj <= 0) return;                         // strip entirely above the diagonal
   const int z = blockIdx.z;
   const double* ls = p.ls + (long)z * p.stride_ls;
   const double* F = p.F ? p.F + (long)z * p.stride_FE : nullptr;
@@ -67,64 +64,88 @@ __global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
   double* out = p.out + (long)z * p.stride_out;
 
   stage_scaled(sr, li, ni, p.X, p.N, p.M, ls, p.L, (long)ti * GT);
-  stage_scaled(sc, lj, nj, p.X2, p.N2, p.M, ls, p.L, (long)tj * GT);
+  for (int s = 0; s < ntj; ++s) stage_scaled(sc + s * GT * p.M, lj + s * GT, nj + s * GT, p.X2, p.N2, p.M, ls, p.L, (long)(tj0 + s) * GT);
   __syncthreads();
 
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  double acc[4][4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-  for (int m = 0; m < p.M; ++m) {
-    double a[4], b[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = sr[m * GT + ty * 4 + u];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) b[v] = sc[m * GT + tx * 4 + v];
+  for (int s = 0; s < ntj; ++s) {
+    const int tj = tj0 + s;
+    const double* scs = sc + s * GT * p.M;
+    double acc[4][4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const double d = a[u] - b[v];
-        acc[u][v] = fma(d, d, acc[u][v]);
-      }
-  }
+      for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+    for (int m = 0; m < p.M; ++m) {
+      double a[4], b[4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int r = ty * 4 + u;
-    const long gi = (long)ti * GT + r;
-    const int l_i = li[r], n_i = ni[r];
-    double o[4];
+      for (int u = 0; u < 4; ++u) a[u] = sr[m * GT + ty * 4 + u];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int c = tx * 4 + v;
-      const long gj = (long)tj * GT + c;
-      const int l_j = lj[c], n_j = nj[c];
-      double val;
-      if (l_i >= 0 && l_j >= 0) {
-        val = exp_pairwise(-0.5 * acc[u][v]);
-        if (F) val *= F[l_i * p.L + l_j];
-        if (E && n_i == n_j) val += E[l_i * p.L + l_j];
-      } else {
-        val = (p.pad_identity && gi == gj) ? 1.0 : 0.0;
-      }
-      o[v] = val;
+      for (int v = 0; v < 4; ++v) b[v] = scs[m * GT + tx * 4 + v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const double d = a[u] - b[v];
+          acc[u][v] = fma(d, d, acc[u][v]);
+        }
     }
-    double2* dst = reinterpret_cast<double2*>(out + gi * p.ld_out + (long)tj * GT + tx * 4);
-    dst[0] = make_double2(o[0], o[1]);
-    dst[1] = make_double2(o[2], o[3]);
+    // Fast path (all but the tiles that straddle an output boundary, the padding or the noise diagonal): one (l_i, l_j) pair for the
+    // whole tile and no sample shared between its rows and columns, so the epilogue is one multiply per element.
+    const int li0 = li[0], lj0 = lj[s * GT];
+    const bool uniform = li0 >= 0 && lj0 >= 0 && li[GT - 1] == li0 && lj[s * GT + GT - 1] == lj0 && (!E || abs(ni[0] - nj[s * GT]) >= GT);
+    if (uniform) {
+      const double f = F ? F[li0 * p.L + lj0] : 1.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long gi = (long)ti * GT + ty * 4 + u;
+        double2* dst = reinterpret_cast<double2*>(out + gi * p.ld_out + (long)tj * GT + tx * 4);
+        dst[0] = make_double2(f * exp_pairwise(-0.5 * acc[u][0]), f * exp_pairwise(-0.5 * acc[u][1]));
+        dst[1] = make_double2(f * exp_pairwise(-0.5 * acc[u][2]), f * exp_pairwise(-0.5 * acc[u][3]));
+      }
+      continue;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = ty * 4 + u;
+      const long gi = (long)ti * GT + r;
+      const int l_i = li[r], n_i = ni[r];
+      double o[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int c = tx * 4 + v;
+        const long gj = (long)tj * GT + c;
+        const int l_j = lj[s * GT + c], n_j = nj[s * GT + c];
+        double val;
+        if (l_i >= 0 && l_j >= 0) {
+          val = exp_pairwise(-0.5 * acc[u][v]);
+          if (F) val *= F[l_i * p.L + l_j];
+          if (E && n_i == n_j) val += E[l_i * p.L + l_j];
+        } else {
+          val = (p.pad_identity && gi == gj) ? 1.0 : 0.0;
+        }
+        o[v] = val;
+      }
+      double2* dst = reinterpret_cast<double2*>(out + gi * p.ld_out + (long)tj * GT + tx * 4);
+      dst[0] = make_double2(o[0], o[1]);
+      dst[1] = make_double2(o[2], o[3]);
+    }
   }
 }
 
 int gram(const GramArgs& a, int batch, cudaStream_t st) {
-  RC_REQUIRE(a.M >= 1 && a.M <= 256, -2, "gram: M=%d out of range [1,256]", a.M);
+  RC_REQUIRE(a.M >= 1 && a.M <= 80, -2, "gram: M=%d out of range [1,80]", a.M);
   RC_REQUIRE(a.rows_pad % GT == 0 && a.cols_pad % GT == 0 && a.ld_out % 2 == 0, -2, "gram: padded sizes must be multiples of 64");
   RC_REQUIRE(!a.lower_only || a.rows_pad == a.cols_pad, -2, "gram: lower_only needs a square output");
   const long tr = a.rows_pad / GT, tc = a.cols_pad / GT;
-  const long tiles = a.lower_only ? tr * (tr + 1) / 2 : tr * tc;
-  const size_t smem = (size_t)2 * GT * a.M * sizeof(double) + 4 * GT * sizeof(int);
-  gram_kernel<<<dim3((unsigned)tiles, 1, batch), GTHREADS, smem, st>>>(a);
+  RC_REQUIRE(tr <= 65535 && batch <= 65535, -2, "gram: %ld row tiles / %d problems exceed the grid limits", tr, batch);
+  const size_t smem = (size_t)(1 + GSTRIP) * GT * a.M * sizeof(double) + (size_t)(2 + 2 * GSTRIP) * GT * sizeof(int);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    RC_CUDA_OK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  gram_kernel<<<dim3((unsigned)((tc + GSTRIP - 1) / GSTRIP), (unsigned)tr, batch), GTHREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
   return 0;
 }
@@ -191,14 +212,14 @@ __global__ void __launch_bounds__(GTHREADS) grad_reduce_kernel(GradArgs p) {
   double* parts = p.parts + ((long)z * gridDim.x + idx) * p.nvals;
   const int L = p.L, M = p.M;
 
+  for (int e = threadIdx.x; e < p.nvals; e += GTHREADS) parts[e] = 0.0;
+  if (p.diag_blocks_only && ((long)ti * GT) / p.N > ((long)tj * GT + GT - 1) / p.N) return;   // tile lies wholly in off-diagonal blocks
   stage_scaled(sr, li, ni, p.X, p.N, M, ls, L, (long)ti * GT);
   stage_scaled(sc, lj, nj, p.X, p.N, M, ls, L, (long)tj * GT);
   for (int r = threadIdx.x; r < GT; r += GTHREADS) {
     ar[r] = alpha[(long)ti * GT + r];
     ac[r] = alpha[(long)tj * GT + r];
   }
-  for (int e = threadIdx.x; e < p.nvals; e += GTHREADS) parts[e] = 0.0;
-  if (p.diag_blocks_only && ((long)ti * GT) / p.N > ((long)tj * GT + GT - 1) / p.N) return;   // tile lies wholly in off-diagonal blocks
   __syncthreads();
 
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
