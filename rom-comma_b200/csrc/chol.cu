@@ -397,6 +397,13 @@ size_t potrf_workspace_bytes(int n, int batch) {
 // The factorisation proper.  `after_panel(done)` (optional) is called once the panel solve of block `done - 1` has been enqueued, i.e. when
 // block columns [0, done) of L are final for ALL rows in stream order - the hook the overlapped inverse below forks its side work from.
 // `invert_all`: finish with the batched launch of the 128 x 128 inverses (off the critical path).
+// Block columns factored between two trailing updates (rank 128 * group).  RC_POTRF_GROUP overrides (1..8).
+static int potrf_group() {
+  const char* e = getenv("RC_POTRF_GROUP");
+  const int v = e ? atoi(e) : 4;
+  return v < 1 ? 1 : (v > 8 ? 8 : v);
+}
+
 template <typename Hook>
 static int potrf_core(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st,
                       Hook&& after_panel, bool invert_all) {
@@ -406,22 +413,21 @@ static int potrf_core(double* A, int n, long ld, long strideA, int batch, double
   const long strideD = (long)nblk * DB * DB;
   RC_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
   int rc;
-  auto trsm_panel = [&](int blk) -> int { return launch_panel_trsm(A, n, ld, strideA, blk, batch, st); };
-  for (int b0 = 0; b0 < nblk; b0 += 2) {
-    const int w = (b0 + 1 < nblk) ? 2 : 1;
-    if ((rc = launch_diag_factor(A, ld, strideA, dinv, strideD, b0, logdet_parts, nblk, info, batch, st))) return rc;
-    if ((rc = trsm_panel(b0))) return rc;
-    if (w == 2) {
-      // columns of block b0+1, rows from block b0+1 down:  A -= P0 * P0[b0+1]^T
-      GemmArgs g{};
-      const long r0 = (long)(b0 + 1) * DB;
-      g.A = A + r0 * ld + (long)b0 * DB; g.lda = ld; g.strideA = strideA;
-      g.B = A + r0 * ld + (long)b0 * DB; g.ldb = ld; g.strideB = strideA;
-      g.C = A + r0 * ld + r0; g.ldc = ld; g.strideC = strideA;
-      g.M = n - (int)r0; g.N = DB; g.K = DB; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kmode = K_FULL;
-      if ((rc = launch_gemm_ws<false, false>(g, batch, st))) return rc;
-      if ((rc = launch_diag_factor(A, ld, strideA, dinv, strideD, b0 + 1, logdet_parts, nblk, info, batch, st))) return rc;
-      if ((rc = trsm_panel(b0 + 1))) return rc;
+  const int W = potrf_group();
+  for (int b0 = 0; b0 < nblk; b0 += W) {
+    const int w = std::min(W, nblk - b0);
+    for (int j = 0; j < w; ++j) {
+      const long r0 = (long)(b0 + j) * DB;
+      if (j > 0) {   // block column b0+j, rows from block b0+j down:  A -= P[:, b0:b0+j] * P[b0+j, b0:b0+j]^T
+        GemmArgs g{};
+        g.A = A + r0 * ld + (long)b0 * DB; g.lda = ld; g.strideA = strideA;
+        g.B = g.A; g.ldb = ld; g.strideB = strideA;
+        g.C = A + r0 * ld + r0; g.ldc = ld; g.strideC = strideA;
+        g.M = n - (int)r0; g.N = DB; g.K = j * DB; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kmode = K_FULL;
+        if ((rc = launch_gemm_ws<false, false>(g, batch, st))) return rc;
+      }
+      if ((rc = launch_diag_factor(A, ld, strideA, dinv, strideD, b0 + j, logdet_parts, nblk, info, batch, st))) return rc;
+      if ((rc = launch_panel_trsm(A, n, ld, strideA, b0 + j, batch, st))) return rc;
     }
     if ((rc = after_panel(b0 + w))) return rc;
     const long r0 = (long)(b0 + w) * DB;
@@ -691,7 +697,7 @@ size_t potrf_trtri_tmp_doubles(int n, int panels) {
   const long nblk = n / DB;
   if (panels < 2 || nblk < 2 * panels) return (size_t)n * n / 4;
   long wblk = (nblk + panels - 1) / panels;
-  wblk += wblk & 1;
+  wblk = (wblk + 7) / 8 * 8;
   size_t total = (size_t)(wblk * DB) * (wblk * DB) / 4;   // scratch of the panel-local trtri
   for (long s = 0; s + wblk < nblk; s += wblk) total += (size_t)(nblk - s - wblk) * DB * wblk * DB;
   return total;
@@ -705,14 +711,15 @@ int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_pa
   if (panels > OV_MAX_PANELS) panels = OV_MAX_PANELS;
   int dev = 0;
   RC_CUDA_OK(cudaGetDevice(&dev));
-  OverlapCtx* cx = (panels >= 2 && nblk >= 2 * panels && potrf_trtri_tmp_doubles(n, panels) <= tmp_doubles) ? overlap_ctx(dev, st) : nullptr;
+  const bool aligned = (8 % potrf_group()) == 0;      // panel boundaries (multiples of 8 blocks) must fall on group boundaries
+  OverlapCtx* cx = (aligned && panels >= 2 && nblk >= 2 * panels && potrf_trtri_tmp_doubles(n, panels) <= tmp_doubles) ? overlap_ctx(dev, st) : nullptr;
   if (!cx) {   // small problem (nothing to hide) or no scratch: plain sequence
     RC_REQUIRE(tmp_doubles >= (size_t)n * n / 4, -2, "potrf_trtri_lower: scratch too small");
     if ((rc = potrf_lower(A, n, ld, 0, 1, dinv, logdet_parts, info, st))) return rc;
     return trtri_lower(A, n, ld, 0, 1, dinv, tmp, 0, st);
   }
   int wblk = (nblk + panels - 1) / panels;
-  wblk += wblk & 1;                                   // panel boundaries on the factorisation's two-block steps
+  wblk = (wblk + 7) / 8 * 8;                          // panel boundaries on the factorisation's group steps (any RC_POTRF_GROUP in 1, 2, 4, 8)
   const int np = (nblk + wblk - 1) / wblk;
   double* scratch = tmp;                              // panel-local trtri scratch, then the T_i one after the other
   double* Tbase = tmp + (size_t)(wblk * DB) * (wblk * DB) / 4;

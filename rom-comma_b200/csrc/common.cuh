@@ -81,13 +81,17 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return r;
 }
 
-// exp(x) for the pairwise Gaussian-integrand kernels: branch-free, 17 FP64 + 3 integer instructions (libm's exp needs ~30 with its
-// special-case handling; the Sobol sweep kernels are bound by exactly this instruction stream).  x is clamped to [-708, 708]: below that
-// the true value is < 3.4e-308 and irrelevant to a sum of O(1) terms, above it cannot occur (exponents are bounded by gamma (1-p) x^2 with
-// |x| <= 7.04).  k = round(x / ln 2) by the 1.5 * 2^52 trick, r = x - k ln 2 in two steps (Cody-Waite), exp(r) by the degree-11 Taylor
-// polynomial on |r| <= 0.3466 (truncation 6e-15 relative), 2^k added into the exponent field.  Max relative error 7e-15.
+// exp(x) for the pairwise Gaussian-integrand kernels: branch-free, 15 FP64 + 6 integer instructions (libm's exp needs ~30 with its
+// special-case handling; the Sobol sweep kernels are bound by exactly this instruction stream).  k = round(x / ln 2) by the 1.5 * 2^52
+// trick, r = x - k ln 2 in two steps (Cody-Waite), exp(r) by the degree-11 Taylor polynomial on |r| <= 0.3466 (truncation 6e-15
+// relative), 2^k added into the exponent field.  Max relative error 7e-15.  Range: x below -708 is replaced by -708 with an INTEGER
+// compare of its high word and two selects (an FP64 fmin/fmax pair costs two DSETP on the FP64 pipe and four selects per call): the
+// result there is ~3e-308 instead of the true value below that - irrelevant to a sum of O(1) terms - however negative x gets (a line
+// search can make a lengthscale tiny).  x > 709 cannot occur (exponents are bounded by gamma (1-p) x^2 with |x| <= 7.04; gram and
+// gradient arguments are <= 0).
 __device__ __forceinline__ double exp_pairwise(double x) {
-  x = fmin(fmax(x, -708.0), 708.0);
+  // high word in (hi(-708), hi(-inf)]: negative, |x| > 708, not a NaN (sign-magnitude order of the high word; NaNs propagate)
+  if ((unsigned)__double2hiint(x) - 0xC0862001u <= 0xFFF00000u - 0xC0862001u) x = -708.0;
   const double magic = 6755399441055744.0;
   const double t = fma(x, 1.4426950408889634074, magic);
   const double k = t - magic;
