@@ -363,9 +363,14 @@ def run_b200(args):
              'roofline': {'bound': 'fp64 exp/ALU', 'achieved': exps / world / (sobol_ms * 1e-3) * 1e-9, 'peak': peaks['exp_gexps'], 'unit': 'Gexp/s',
                           'frac': exps / world / (sobol_ms * 1e-3) * 1e-9 / peaks['exp_gexps'], 'exps_per_sweep': exps,
                           'reference_exps_per_sweep': exps_reference,
+                          'fp64_instructions_per_exp': 21.25,
+                          'fp64_pipe_frac': exps / world / (sobol_ms * 1e-3) * 21.25 / (peaks['dmma_tflops'] * 0.5e12),
                           'note': 'achieved = M exps per (sample pair, pair of output rows) actually required by the factorised integrand / sweep time '
-                                  '(per GPU: divided by the number of ranks, which split the pair space); peak = register-resident libm exp loop measured live; the remaining FP64 work per exp is ~8 FMA/ADD '
-                                  '(prefix/suffix products, weights)'}}
+                                  '(per GPU: divided by the number of ranks, which split the pair space); peak = register-resident loop of the kernels\' own '
+                                  'branch-free exp (14 FP64 instructions; libm\'s exp, ~30 instructions, measures 845 Gexp/s) timed live. Besides its exp the '
+                                  'kernel issues ~7 FP64 instructions per exp (argument, weights, prefix/suffix products, sums): 21.25 in all by SASS count at '
+                                  'M = 8, so fp64_pipe_frac = exps x 21.25 / time against the FP64 FMA issue rate (measured DMMA TFLOP/s / 2 per lane-op) '
+                                  'is the share of the FP64 pipe the sweep keeps busy'}}
 
     # ---- Sobol sweep WITH errors (ClosedSobolWithError, gsa/calibrators.py:146-402; on by default in the reference's scripts): V, W for the same
     #      25 slices; needs the Cholesky factor of the noisy gram (factorised once, outside the timed loop, as the calibrator holds it).

@@ -81,14 +81,16 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return r;
 }
 
-// exp(x) for the pairwise Gaussian-integrand kernels: branch-free, 15 FP64 + 6 integer instructions (libm's exp needs ~30 with its
+// exp(x) for the pairwise Gaussian-integrand kernels: branch-free, 14 FP64 + 6 integer instructions (libm's exp needs ~30 with its
 // special-case handling; the Sobol sweep kernels are bound by exactly this instruction stream).  k = round(x / ln 2) by the 1.5 * 2^52
-// trick, r = x - k ln 2 in two steps (Cody-Waite), exp(r) by the degree-11 Taylor polynomial on |r| <= 0.3466 (truncation 6e-15
-// relative), 2^k added into the exponent field.  Max relative error 7e-15.  Range: x below -708 is replaced by -708 with an INTEGER
+// trick, r = x - k ln 2 in two steps (Cody-Waite), exp(r) by a degree-10 near-minimax polynomial on |r| <= 0.3466,
+// 2^k added into the exponent field.  Max relative error 1e-15.  Range: x below -708 is replaced by -708 with an INTEGER
 // compare of its high word and two selects (an FP64 fmin/fmax pair costs two DSETP on the FP64 pipe and four selects per call): the
 // result there is ~3e-308 instead of the true value below that - irrelevant to a sum of O(1) terms - however negative x gets (a line
 // search can make a lengthscale tiny).  x > 709 cannot occur (exponents are bounded by gamma (1-p) x^2 with |x| <= 7.04; gram and
 // gradient arguments are <= 0).
+// (Constants as literals on purpose: from a __constant__ table the register-resident loop gains 12 %, but the sweep kernels, which are
+// out of registers, lose 7 % to the extra uniform-register loads.)
 __device__ __forceinline__ double exp_pairwise(double x) {
   // high word in (hi(-708), hi(-inf)]: negative, |x| > 708, not a NaN (sign-magnitude order of the high word; NaNs propagate)
   if ((unsigned)__double2hiint(x) - 0xC0862001u <= 0xFFF00000u - 0xC0862001u) x = -708.0;
@@ -97,17 +99,16 @@ __device__ __forceinline__ double exp_pairwise(double x) {
   const double k = t - magic;
   double r = fma(k, -6.93147180369123816490e-01, x);
   r = fma(k, -1.90821492927058770002e-10, r);
-  double p = 2.5052108385441720e-08;              // 1/11!
-  p = fma(p, r, 2.7557319223985888e-07);          // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);          // 1/9!
-  p = fma(p, r, 2.4801587301587302e-05);          // 1/8!
-  p = fma(p, r, 1.9841269841269841e-04);          // 1/7!
-  p = fma(p, r, 1.3888888888888889e-03);          // 1/6!
-  p = fma(p, r, 8.3333333333333332e-03);          // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);          // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);          // 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
+  double p = 2.74649892754840101e-07;             // degree-10 Chebyshev interpolant of exp on |r| <= 0.34662 (coefficients computed in
+  p = fma(p, r, 2.76428065197613745e-06);         // 80-bit arithmetic, tools/exp_poly.py): max relative error 8e-16 - ten times tighter than
+  p = fma(p, r, 2.48019467832707630e-05);         // the degree-11 Taylor polynomial it replaces, with one FMA less
+  p = fma(p, r, 1.98411638732997871e-04);
+  p = fma(p, r, 1.38888885130029937e-03);
+  p = fma(p, r, 8.33333339078338141e-03);
+  p = fma(p, r, 4.16666666681718770e-02);
+  p = fma(p, r, 1.66666666665395619e-01);
+  p = fma(p, r, 4.99999999999979683e-01);
+  p = fma(p, r, 1.00000000000000799e+00);
   p = fma(p, r, 1.0);
   const int ki = __double2loint(t);
   return __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
