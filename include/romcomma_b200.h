@@ -51,7 +51,8 @@ int rc_profile_end(double* gemm_ms_host, double* gemm_flops_host, long* gemm_lau
  * X2 == NULL means X2 = X.  rows_pad/cols_pad: multiples of 64 >= L*N, L*N2; lower_only computes 64-tiles on/below the
  * diagonal only; pad_identity puts 1 on the padded diagonal (factorisation input) instead of 0.
  * batch > 1 (variant path, gpflow kernels.RBF per output, romcomma/gpr/kernels.py:176-177, gpr/models.py:340-342):
- * problem z uses ls + z*L*M, F + z*L*L, E + z*L*L and writes out + z*stride_out (X, X2 shared). */
+ * problem z uses ls + z*L*M, F + z*L*L, E + z*L*L and writes out + z*stride_out (X, X2 shared).
+ * Limits: 1 <= M <= 80 (the scaled coordinates of a 64 x 256 strip are staged in shared memory), L*N <= 65535*64. */
 int rc_gram(const double* X, int N, const double* X2, int N2, int M, const double* ls, int L, const double* F, const double* E,
             double* out, long ld_out, long stride_out, int rows_pad, int cols_pad, int lower_only, int pad_identity, int batch,
             rc_stream_t stream);

@@ -182,3 +182,37 @@ def test_closed_sobol_calibrator_attributes(small_repo):
         assert_close(subs[0]['V'].numpy(), sobol.subset_V(X, ls, F, KiY, [0, 2], diag)['V'], rtol=1e-7, atol=1e-9, what='subset {0,2}')
     # default is_F_diagonal: True unless the GP's meta says the kernel covariance was trained (quirk Q3)
     assert ClosedSobol(gpm).is_F_diagonal is True
+
+
+def test_mogp_shares_one_factorisation_until_the_hyperparameters_change(small_repo):
+    """MOGP keeps ONE Cholesky factor (and K^-1 y) per set of hyper-parameters for predict / K_cho / K_inv_Y / the Sobol calibrators, where
+    the reference factorises in each of them; the cache must follow the parameters: same numbers as a fresh model before and after a
+    change, and a different factor object after it."""
+    from romcomma.data.storage import Fold
+    from romcomma.gpr.models import MOGP
+    fold = Fold(small_repo, 0)
+    model = MOGP('cache.c.a', fold, is_read=False, is_covariant=True, is_isotropic=False)
+    xs = fold.test_x.values[:5]
+    fac0 = model._factorize()[0]
+    m0, s0 = model.predict(xs)
+    assert model._factorize()[0] is fac0, 'unchanged hyper-parameters: the factor is reused'
+    kiy0 = model.K_inv_Y.numpy().copy()
+    assert np.array_equal(model.K_inv_Y.numpy(), kiy0)
+    X, Y = fold.X.values, fold.Y.values
+    impl = model.implementation[0]
+    ls, F, E = impl.kernel.lengthscales_neat.numpy(), impl.kernel.variance.value.numpy(), impl.likelihood.variance.value.numpy()
+    rm, rv = gp.predict_mo(X, Y, ls, F, E, xs)
+    assert_close(m0, rm, what='mean (cached factor)')
+    assert_close(s0, np.sqrt(rv), what='std (cached factor)')
+    # change a hyper-parameter in place, as the optimiser does
+    v = impl.likelihood.variance._cholesky_diagonal
+    v.unconstrained_variable = np.asarray(v.unconstrained_variable) + 0.3
+    fac1 = model._factorize()[0]
+    assert fac1 is not fac0, 'changed hyper-parameters: a new factorisation'
+    E1 = impl.likelihood.variance.value.numpy()
+    assert not np.allclose(E1, E)
+    m1, s1 = model.predict(xs)
+    rm1, rv1 = gp.predict_mo(X, Y, ls, F, E1, xs)
+    assert_close(m1, rm1, what='mean after the change')
+    assert_close(s1, np.sqrt(rv1), what='std after the change')
+    assert_close(model.K_inv_Y.numpy(), gp.k_inv_y_mo(X, Y, ls, F, E1), rtol=1e-7, atol=1e-8, what='K_inv_Y after the change')

@@ -54,7 +54,7 @@ def test_gram_variant_batch_matches_gpflow_form(C):
 
 
 # ---- factorisation ----------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('n', [5, 128, 200, 384, 700])
+@pytest.mark.parametrize('n', [5, 128, 200, 384, 700, 1100])
 def test_potrf_solves_and_inverse(C, n):
     rng = np.random.default_rng(n)
     A = rng.normal(size=(n, n))
@@ -78,6 +78,41 @@ def test_potrf_solves_and_inverse(C, n):
     assert_close(Bp[0, :n, :37].cpu().numpy(), np.linalg.solve(Lc, B), rtol=1e-8, atol=1e-10, what='L^-1 B')
     Kinv = C.extract_lower(fac.inverse_(), n, symmetrize=True)[0].cpu().numpy()
     assert_close(Kinv, np.linalg.inv(K), rtol=1e-8, atol=1e-10, what='K^-1')
+
+
+@pytest.mark.parametrize('group', [1, 2, 3, 4, 8])
+def test_potrf_group_widths(C, group, monkeypatch):
+    """RC_POTRF_GROUP block columns are factored between two trailing updates (default 4: rank-512 updates); every width, with a ragged
+    last group (n_pad = 1408 = 11 blocks), must give the same factor to rounding."""
+    monkeypatch.setenv('RC_POTRF_GROUP', str(group))
+    n = 1400
+    rng = np.random.default_rng(group)
+    A = rng.normal(size=(n, n))
+    K = A @ A.T / n + np.eye(n)
+    fac = C.Factorization(C.pad_identity(C.dev(K)))
+    fac.raise_if_failed()
+    assert_close(fac.lower(n)[0].cpu().numpy(), np.linalg.cholesky(K), rtol=1e-8, atol=1e-10, what=f'L (group {group})')
+
+
+@pytest.mark.parametrize('n,nrhs,sb', [(1300, 1152, None), (1300, 1152, 1), (1300, 1152, 3), (900, 2000, None), (300, 1100, None), (1300, 300, 8)])
+def test_trsm_wide_right_hand_sides(C, n, nrhs, sb, monkeypatch):
+    """B <- L^-1 B.  More than 1024 columns take the two-level form (K = 1024 updates below an 8-block super-block, RC_TRSM_SB overrides);
+    all super-block sizes, ragged last super-blocks and narrow/wide cases against LAPACK."""
+    if sb is not None:
+        monkeypatch.setenv('RC_TRSM_SB', str(sb))
+    rng = np.random.default_rng(n + nrhs)
+    A = rng.normal(size=(n, n))
+    K = A @ A.T / n + np.eye(n)
+    fac = C.Factorization(C.pad_identity(C.dev(K)))
+    fac.raise_if_failed()
+    B = rng.normal(size=(n, nrhs))
+    Bp = torch.zeros((1, fac.n_pad, C.padded(nrhs)), dtype=torch.float64, device='cuda')
+    Bp[0, :n, :nrhs] = C.dev(B)
+    fac.trsm_fwd_(Bp)
+    import scipy.linalg
+    ref = scipy.linalg.solve_triangular(np.linalg.cholesky(K), B, lower=True)
+    assert_close(Bp[0, :n, :nrhs].cpu().numpy(), ref, rtol=1e-8, atol=1e-10, what='L^-1 B')
+    assert float(Bp[0, n:, :].abs().sum()) == 0.0 and float(Bp[0, :, nrhs:].abs().sum()) == 0.0, 'padding must stay zero'
 
 
 def test_potrf_batched(C):
