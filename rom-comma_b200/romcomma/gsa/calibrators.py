@@ -133,11 +133,28 @@ class ClosedSobolWithError(ClosedSobol):
         self._fac = self.gp._factorize()[0]                              # K_cho with its solve workspace, resident for the whole sweep
         self._Lam_d, self._F_d = _capi.dev(self.Lambda.numpy()), _capi.dev(self.F.numpy().reshape(-1))
         self._g0_d = self.g0.as_subclass(torch.Tensor).reshape(self.L, self.N).contiguous()
-        self.W = HostTensor(self._VW_many([_capi.slice_mask(0, self.M)])[1][0])
+        self._W_full = None
+
+    @property
+    def W(self) -> HostTensor:
+        """ The covariance W of the full model (reference calibrators.py: computed eagerly in ``_calibrate``).  Here it is evaluated on first
+        use, and for free when a ``marginalize_*`` call comes first: the full-model subset rides along in that call's single triangular
+        solve (16 more right-hand sides) instead of paying for a launch-latency-bound solve of its own."""
+        if self._W_full is None:
+            self._W_full = HostTensor(self._VW_many([_capi.slice_mask(0, self.M)])[1][0])
+        return self._W_full
 
     def _VW_many(self, masks: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+        masks = [int(m) for m in masks]
+        ride_along = self._W_full is None             # rc_sobol_error chunks long lists itself
+        if ride_along:
+            masks = masks + [_capi.slice_mask(0, self.M)]
         V, W = _capi.sobol_error(self._Xd, self._Lam_d, self._F_d, self._Phi_d, self._g0_d, self._g0KY_d, self._fac, masks)
-        return V.cpu().numpy(), W.cpu().numpy()
+        V, W = V.cpu().numpy(), W.cpu().numpy()
+        if ride_along:
+            self._W_full = HostTensor(W[-1])
+            V, W = V[:-1], W[:-1]
+        return V, W
 
     def _results(self, V: np.ndarray, W: np.ndarray) -> List[Dict[str, HostTensor]]:
         V2, V4 = self.V[2].numpy(), self.V[4].numpy()
