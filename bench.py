@@ -38,8 +38,10 @@ METRIC, UNIT = 'mogpr_lml_grad_evals_per_s', 'evals/s'
 # launch: the first rank-256 trailing update of potrf (profiles/r01_ncu_ws_syrk.md), the top level of trtri and the selected LAUUM
 # (profiles/r01_ncu_ws_trtri_lauum.md).  Algorithmic bytes of the same launches (operands once + C read/write): 2.1 GB, 1.6 GB, 0.8 GB - the
 # re-reads of the long-K launches are L2 capacity misses; at 1.1 TB/s (17 % of the HBM bandwidth) in the worst launch they are not the bound.
-NCU_TRAFFIC = {'syrk_rank256_first_launch_bytes': 2.230e9, 'trtri_top_level_launch_bytes': 18.02e9, 'lauum_selected_launch_bytes': 3.42e9,
-               'source': 'profiles/r01_ncu_ws_syrk.md, profiles/r01_ncu_ws_trtri_lauum.md'}
+NCU_TRAFFIC = {'syrk_rank512_first_launch_bytes': 3.473e9, 'syrk_rank512_first_launch_algorithmic_bytes': 2.08e9,
+               'trtri_top_level_launch_bytes': 18.02e9, 'lauum_selected_launch_bytes': 3.42e9,
+               'source': 'profiles/r01_ncu_ws_syrk512.md (DMMA pipe 89.7 % of active cycles, L2 hit rate 71 %: operand re-reads behind the streaming C '
+                         'tiles, 0.88 TB/s - not the bound), profiles/r01_ncu_ws_trtri_lauum.md'}
 
 
 def parse():
