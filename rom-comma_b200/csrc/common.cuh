@@ -87,8 +87,9 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // 2^k added into the exponent field.  Max relative error 1e-15.  Range: x below -708 is replaced by -708 with an INTEGER
 // compare of its high word and two selects (an FP64 fmin/fmax pair costs two DSETP on the FP64 pipe and four selects per call): the
 // result there is ~3e-308 instead of the true value below that - irrelevant to a sum of O(1) terms - however negative x gets (a line
-// search can make a lengthscale tiny).  x > 709 cannot occur (exponents are bounded by gamma (1-p) x^2 with |x| <= 7.04; gram and
-// gradient arguments are <= 0).
+// search can make a lengthscale tiny).  x > 709 is the CALLER's business: it cannot occur in the sweep kernels (single-input exponents are
+// bounded by gamma (1-p) x^2 with |x| <= 7.04) nor in the gram / gradient kernels (arguments <= 0); the general-subset kernels, which sum up to
+// M such exponents before the exp, pass fmin(e, 708).
 // (Constants as literals on purpose: from a __constant__ table the register-resident loop gains 12 %, but the sweep kernels, which are
 // out of registers, lose 7 % to the extra uniform-register loads.)
 __device__ __forceinline__ double exp_pairwise(double x) {

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(STHREADS) sobol_pair_kernel(SobolPairArgs p) {
     for (int u = 0; u < 4; ++u) {
       double rowacc = 0.0;
 #pragma unroll
-      for (int v = 0; v < 4; ++v) rowacc = fma(ccc[v], exp_pairwise(e[u][v]), rowacc);
+      for (int v = 0; v < 4; ++v) rowacc = fma(ccc[v], exp_pairwise(fmin(e[u][v], 708.0)), rowacc);
       acc = fma(crr[u], rowacc, acc);
     }
     acc = warp_sum(acc);

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(ETHREADS) sobol_error_matvec_kernel(ErrMatvecA
       for (int u = 0; u < 4; ++u) {
         const double w = wl[rbase + u];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) colacc[v] = fma(w, exp_pairwise(e[u][v]), colacc[v]);
+        for (int v = 0; v < 4; ++v) colacc[v] = fma(w, exp_pairwise(fmin(e[u][v], 708.0)), colacc[v]);
       }
     }
 #pragma unroll
