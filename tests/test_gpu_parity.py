@@ -286,11 +286,13 @@ def test_sobol_golden(C, golden):
 
 
 # ---- properties at benchmark scale (oracle too slow / too large there) ---------------------------------------------------
-def test_full_size_properties_cfg3(C):
-    """n = 16384 (cfg3): K K^-1 v = v, L L^T v = K v, symmetric V, bitwise run-to-run reproducibility."""
+@pytest.mark.parametrize('cfg', ['cfg3', 'cfg5'])
+def test_full_size_properties(C, cfg):
+    """Full benchmark sizes (cfg3: n = 16384, cfg5: n = 24576): K K^-1 v = v, L L^T v = K v, the LML and gradient identities from the
+    explicit inverse, bitwise run-to-run reproducibility."""
     from romcomma import synthetic
-    w = synthetic.config('cfg3')
-    N, M, L = 4096, 8, 4
+    w = synthetic.config(cfg)
+    (N, M), L = w.X.shape, w.Y.shape[1]
     n = N * L
     dX, dY, dls, dF, dE = C.dev(w.X), C.dev(w.Y), C.dev(w.lengthscales), C.dev(w.F[None]), C.dev(w.E[None])
     K = C.gram(dX, None, dls, dF, dE)[0]
@@ -319,6 +321,40 @@ def test_full_size_properties_cfg3(C):
     for l in range(L):
         ref = 0.5 * ((ky[l * N:(l + 1) * N] ** 2).sum() - Kinv[l * N:(l + 1) * N, l * N:(l + 1) * N].diagonal().sum()).item()
         assert_close(a[0, 1 + L * L + l * L + l].item(), ref, rtol=1e-8, atol=1e-6, what=f'dE[{l},{l}]')
+
+
+@pytest.mark.parametrize('cfg', ['cfg3', 'cfg5'])
+def test_full_size_sobol_properties(C, cfg):
+    """Size-independent properties of the Sobol contractions at full benchmark size: V symmetric in the outputs; the sweep form and the
+    general-subset kernel agree (a non-structured subset equals a prefix after permuting the inputs); the row-tile parts that the ranks
+    of a multi-GPU sweep own add up to the whole; run-to-run bitwise reproducibility."""
+    from romcomma import synthetic
+    w = synthetic.config(cfg)
+    (N, M), L = w.X.shape, w.Y.shape[1]
+    dX, Lam, Fd = C.dev(w.X), w.lengthscales, np.diag(w.F).copy()
+    KiY = torch.randn(L, N, dtype=torch.float64, device='cuda', generator=torch.Generator('cuda').manual_seed(11)) * 0.1
+    Phi, g0, g0KY = C.sobol_prepare(dX, C.dev(Lam), C.dev(Fd), KiY, True)
+    slices = [(m, m + 1) for m in range(M)] + [(0, m + 1) for m in range(M)] + [(m + 1, M) for m in range(M)] + [(0, M)]
+    masks = [C.slice_mask(*sl) for sl in slices]
+    V = C.sobol_contract(dX, Phi, g0KY, L, True, masks)
+    V2 = C.sobol_contract(dX, Phi, g0KY, L, True, masks)
+    assert torch.equal(V, V2), 'sweep is not bitwise reproducible'
+    Vh = V.cpu().numpy()
+    scale = np.abs(Vh).max()
+    assert np.abs(Vh - Vh.transpose(0, 2, 1)).max() <= 1e-12 * scale, 'V is not symmetric in the outputs'
+    assert_close(Vh[2 * M - 1], Vh[3 * M], rtol=1e-12, what='closed [0:M] equals the full slice')
+    assert_close(Vh[M], Vh[0], rtol=1e-12, what='closed [0:1] equals first-order [0:1]')
+    assert np.abs(Vh[3 * M - 1]).max() <= 1e-9 * scale, 'the empty slice [M:M] must vanish (up to cancellation)'
+    # general-subset kernel vs sweep form: {1, 2} is not a prefix/suffix/single; with inputs reordered (1, 2, 0, 3, ...) it is the prefix [0:2]
+    perm = [1, 2, 0] + list(range(3, M))
+    Vg = C.sobol_contract(dX, Phi, g0KY, L, True, [0b110])
+    dXp = C.dev(np.ascontiguousarray(w.X[:, perm]))
+    Phip, g0p, g0KYp = C.sobol_prepare(dXp, C.dev(np.ascontiguousarray(Lam[:, perm])), C.dev(Fd), KiY, True)
+    Vp = C.sobol_contract(dXp, Phip, g0KYp, L, True, [C.slice_mask(0, 2)])
+    assert_close(Vg.cpu().numpy(), Vp.cpu().numpy(), rtol=1e-9, atol=1e-12 * scale, what='general-subset kernel vs sweep form')
+    # pair-space parts (what each rank of a 3-GPU sweep would compute) add up
+    parts = sum(C.sobol_contract(dX, Phi, g0KY, L, True, masks, part=r, nparts=3) for r in range(3))
+    assert_close(parts.cpu().numpy(), Vh, rtol=1e-11, atol=1e-13 * scale, what='row-tile parts add up')
 
 
 # ---- Sobol errors (ClosedSobolWithError) -----------------------------------------------------------------------------------
