@@ -39,13 +39,12 @@ METRIC, UNIT = 'mogpr_lml_grad_evals_per_s', 'evals/s'
 # (profiles/r01_ncu_ws_trtri_lauum.md).  Algorithmic bytes of the same launches (operands once + C read/write): 2.1 GB, 1.6 GB, 0.8 GB - the
 # re-reads of the long-K launches are L2 capacity misses; at 1.1 TB/s (17 % of the HBM bandwidth) in the worst launch they are not the bound.
 NCU_TRAFFIC = {'syrk_rank512_first_launch_bytes': 3.473e9, 'syrk_rank512_first_launch_algorithmic_bytes': 2.08e9,
-               'trtri_top_level_launch_bytes': 18.02e9, 'trtri_top_level_launch_algorithmic_bytes': 1.34e9,
-               'trtri_top_level_note': 'tiles are ordered by decreasing K for load balance (DMMA pipe 96 % active), so the 128-row operand panels of the '
-                                       '8192^3 triangular product are re-read from DRAM once per tile column: 18 GB in 16.3 ms = 1.1 TB/s = 17 % of the '
-                                       'HBM peak - wasteful but far from the bound of this launch; an L2-blocked raster would cut it to ~3 GB',
-               'lauum_selected_launch_bytes': 3.42e9,
+               'trtri_top_level_launch_bytes': 4.83e9, 'trtri_top_level_launch_algorithmic_bytes': 1.34e9,
+               'trtri_top_level_note': 'L2-blocked 12 x 12 tile raster: 4.8 GB in 15.96 ms (18.0 GB in 16.29 ms with column-major tile order); DMMA pipe '
+                                       '94.6 % active, L2 hit rate 78 %',
+               'lauum_selected_launch_bytes': 3.42e9, 'lauum_selected_launch_algorithmic_bytes': 1.34e9,
                'source': 'profiles/r01_ncu_ws_syrk512.md (DMMA pipe 89.7 % of active cycles, L2 hit rate 71 %: operand re-reads behind the streaming C '
-                         'tiles, 0.88 TB/s - not the bound), profiles/r01_ncu_ws_trtri_lauum.md'}
+                         'tiles, 0.88 TB/s - not the bound), profiles/r01_ncu_trtri_top_lauum_raster.csv'}
 
 
 def parse():

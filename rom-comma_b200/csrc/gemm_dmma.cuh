@@ -59,6 +59,8 @@ __device__ __forceinline__ void gemm_load_operand(double* __restrict__ dst, cons
   }
 }
 
+constexpr int G_RASTER = 12;   // super-tile edge of the L2-blocked tile order (12 x 12 = 144 tiles ~ one wave of 148 SMs)
+
 struct GemmTile {
   int m0, n0, kb, nk;   // nk == 0: nothing to do for this tile (skipped by sel_block)
   const double* A; const double* B; double* C;
@@ -75,11 +77,25 @@ __device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p, long til
     while ((long)tm * (tm + 1) / 2 > idx) --tm;
     tn = (int)(idx - (long)tm * (tm + 1) / 2);
   } else {
-    const int tiles_m = p.M / G_BM;
-    tm = (int)(idx % tiles_m);
-    tn = (int)(idx / tiles_m);
-    if (p.kmode == K_LT_M1) tm = tiles_m - 1 - tm;   // longest K ranges first
-    if (p.kmode == K_LE_N1) tn = p.N / G_BN - 1 - tn;
+    // L2-blocked raster: the ~148 tiles in flight at any time form a G_RASTER x G_RASTER super-tile, so they share G_RASTER row panels
+    // of A and G_RASTER column panels of B and walk k almost in step - each operand panel comes from DRAM about once per super-tile
+    // instead of once per tile (column-major order re-read the 128 x K row panels for every tile column: 18 GB for the 8192^3
+    // triangular product of trtri's top level against 1.3 GB algorithmic).  Super-tiles are ordered along the dimension the K range
+    // depends on, longest K first, and so are the tiles inside one: the dynamic scheduler's load balance is unchanged.
+    const int tiles_m = p.M / G_BM, tiles_n = p.N / G_BN;
+    const bool k_by_row = p.kmode == K_LT_M1 || p.kmode == K_GE_M0;
+    const int slow_n = k_by_row ? tiles_m : tiles_n, fast_n = k_by_row ? tiles_n : tiles_m;    // slow: the dimension K depends on
+    const long per_slow_band = (long)G_RASTER * fast_n;
+    const int sb = (int)(idx / per_slow_band);                         // band along the slow dimension (only the last one is narrower)
+    const int slow_w = min(G_RASTER, slow_n - sb * G_RASTER);
+    const long r1 = idx - (long)sb * per_slow_band;
+    const int fb = (int)(r1 / ((long)G_RASTER * slow_w));              // band along the fast dimension
+    const int fast_w = min(G_RASTER, fast_n - fb * G_RASTER);
+    const int r2 = (int)(r1 - (long)fb * G_RASTER * slow_w);
+    int slow = sb * G_RASTER + r2 / fast_w, fast = fb * G_RASTER + r2 % fast_w;
+    if (p.kmode == K_LT_M1 || p.kmode == K_LE_N1) slow = slow_n - 1 - slow;   // K grows with the index: start from the far end
+    tm = k_by_row ? slow : fast;
+    tn = k_by_row ? fast : slow;
   }
   GemmTile t;
   t.m0 = tm * G_BM;
