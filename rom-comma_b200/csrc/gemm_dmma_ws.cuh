@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
         }
       }
     } else {
-      // Read-modify-write of C, W_EPI_ROWS fragment rows at a time: all their loads are issued before the first store.  Written as
+      // Read-modify-write of C with streaming (evict-first) loads and stores - every C element is touched once per launch, the operand
+      // panels are what should stay in L2 -, W_EPI_ROWS fragment rows at a time: all their loads are issued before the first store.  Written as
       // load / fma / store per element the compiler may not move a load above an earlier store (same array, run-time ldc), which made
       // the epilogue eight dependent L2 round trips per warp - most of what a K = 256 trailing-update tile lost against a long-K tile.
 #pragma unroll
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
         for (int i = 0; i < W_EPI_ROWS; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            o[i][j] = *reinterpret_cast<const double2*>(T.C + (long)(T.m0 + wm * 64 + (i0 + i) * 8 + g) * p.ldc + T.n0 + wn * 32 + j * 8 + t * 2);
+            o[i][j] = __ldcs(reinterpret_cast<const double2*>(T.C + (long)(T.m0 + wm * 64 + (i0 + i) * 8 + g) * p.ldc + T.n0 + wn * 32 + j * 8 + t * 2));
 #pragma unroll
         for (int i = 0; i < W_EPI_ROWS; ++i)
 #pragma unroll
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
             double2 v;
             v.x = fma(alpha, acc[i0 + i][j][0], beta * o[i][j].x);
             v.y = fma(alpha, acc[i0 + i][j][1], beta * o[i][j].y);
-            *reinterpret_cast<double2*>(T.C + (long)(T.m0 + wm * 64 + (i0 + i) * 8 + g) * p.ldc + T.n0 + wn * 32 + j * 8 + t * 2) = v;
+            __stcs(reinterpret_cast<double2*>(T.C + (long)(T.m0 + wm * 64 + (i0 + i) * 8 + g) * p.ldc + T.n0 + wn * 32 + j * 8 + t * 2), v);
           }
       }
     }
