@@ -397,11 +397,18 @@ size_t potrf_workspace_bytes(int n, int batch) {
 // The factorisation proper.  `after_panel(done)` (optional) is called once the panel solve of block `done - 1` has been enqueued, i.e. when
 // block columns [0, done) of L are final for ALL rows in stream order - the hook the overlapped inverse below forks its side work from.
 // `invert_all`: finish with the batched launch of the 128 x 128 inverses (off the critical path).
-// Block columns factored between two trailing updates (rank 128 * group).  RC_POTRF_GROUP overrides (1..8).
-static int potrf_group() {
+// Block columns factored between two trailing updates (rank 128 * group).  Four while the trailing matrix is large (its K = 512 tiles
+// amortise the read-modify-write epilogue; cfg3 117.6 -> 116.8 ms against two), two once the trailing update is down to a wave or two
+// of tiles and the longer column updates of a wide group are pure chain latency (n = 2048: 2.86 -> 2.72 ms).  RC_POTRF_GROUP (1..8)
+// fixes the width.
+static int potrf_group_env() {
   const char* e = getenv("RC_POTRF_GROUP");
-  const int v = e ? atoi(e) : 4;
-  return v < 1 ? 1 : (v > 8 ? 8 : v);
+  const int v = e ? atoi(e) : 0;
+  return v < 1 ? 0 : (v > 8 ? 8 : v);
+}
+static int potrf_group(int blocks_left) {
+  const int v = potrf_group_env();
+  return v ? v : (blocks_left >= 40 ? 4 : 2);
 }
 
 template <typename Hook>
@@ -413,9 +420,8 @@ static int potrf_core(double* A, int n, long ld, long strideA, int batch, double
   const long strideD = (long)nblk * DB * DB;
   RC_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
   int rc;
-  const int W = potrf_group();
-  for (int b0 = 0; b0 < nblk; b0 += W) {
-    const int w = std::min(W, nblk - b0);
+  for (int b0 = 0, w = 0; b0 < nblk; b0 += w) {
+    w = std::min(potrf_group(nblk - b0), nblk - b0);
     for (int j = 0; j < w; ++j) {
       const long r0 = (long)(b0 + j) * DB;
       if (j > 0) {   // block column b0+j, rows from block b0+j down:  A -= P[:, b0:b0+j] * P[b0+j, b0:b0+j]^T
@@ -711,7 +717,7 @@ int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_pa
   if (panels > OV_MAX_PANELS) panels = OV_MAX_PANELS;
   int dev = 0;
   RC_CUDA_OK(cudaGetDevice(&dev));
-  const bool aligned = (8 % potrf_group()) == 0;      // panel boundaries (multiples of 8 blocks) must fall on group boundaries
+  const bool aligned = potrf_group_env() == 0 || (8 % potrf_group_env()) == 0;      // panel boundaries (multiples of 8 blocks) must fall on group boundaries
   OverlapCtx* cx = (aligned && panels >= 2 && nblk >= 2 * panels && potrf_trtri_tmp_doubles(n, panels) <= tmp_doubles) ? overlap_ctx(dev, st) : nullptr;
   if (!cx) {   // small problem (nothing to hide) or no scratch: plain sequence
     RC_REQUIRE(tmp_doubles >= (size_t)n * n / 4, -2, "potrf_trtri_lower: scratch too small");

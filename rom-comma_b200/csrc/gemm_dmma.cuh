@@ -85,13 +85,14 @@ __device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p, long til
     const int tiles_m = p.M / G_BM, tiles_n = p.N / G_BN;
     const bool k_by_row = p.kmode == K_LT_M1 || p.kmode == K_GE_M0;
     const int slow_n = k_by_row ? tiles_m : tiles_n, fast_n = k_by_row ? tiles_n : tiles_m;    // slow: the dimension K depends on
-    const long per_slow_band = (long)G_RASTER * fast_n;
-    const int sb = (int)(idx / per_slow_band);                         // band along the slow dimension (only the last one is narrower)
+    const int idx32 = (int)idx;                                        // tiles of ONE matrix: < 2^31, 32-bit divisions
+    const int per_slow_band = G_RASTER * fast_n;
+    const int sb = idx32 / per_slow_band;                              // band along the slow dimension (only the last one is narrower)
     const int slow_w = min(G_RASTER, slow_n - sb * G_RASTER);
-    const long r1 = idx - (long)sb * per_slow_band;
-    const int fb = (int)(r1 / ((long)G_RASTER * slow_w));              // band along the fast dimension
+    const int r1 = idx32 - sb * per_slow_band;
+    const int fb = r1 / (G_RASTER * slow_w);                           // band along the fast dimension
     const int fast_w = min(G_RASTER, fast_n - fb * G_RASTER);
-    const int r2 = (int)(r1 - (long)fb * G_RASTER * slow_w);
+    const int r2 = r1 - fb * G_RASTER * slow_w;
     int slow = sb * G_RASTER + r2 / fast_w, fast = fb * G_RASTER + r2 % fast_w;
     if (p.kmode == K_LT_M1 || p.kmode == K_LE_N1) slow = slow_n - 1 - slow;   // K grows with the index: start from the far end
     tm = k_by_row ? slow : fast;

@@ -43,18 +43,18 @@ __device__ __forceinline__ void stage_scaled(double* __restrict__ s, int* __rest
 // One CTA per 64-row x (GSTRIP * 64)-column strip: the scaled coordinates of the rows are staged once and the prologue (global loads,
 // the divisions by the lengthscales, one barrier) is paid once per GSTRIP tiles; with one tile per CTA the prologue latency was ~60 % of
 // the kernel (0.72 ms for the 1.07 GB lower triangle at n = 16384; FP64 issue and HBM both far from busy).
-constexpr int GSTRIP = 4;
+constexpr int GSTRIP = 4;   // upper limit; GramArgs::strip is what a launch uses
 __global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
   extern __shared__ __align__(16) double sm[];
   double* sr = sm;                              // [M][64]
-  double* sc = sm + GT * p.M;                   // [GSTRIP][M][64]
-  int* li = reinterpret_cast<int*>(sm + (1 + GSTRIP) * GT * p.M);
+  double* sc = sm + GT * p.M;                   // [strip][M][64]
+  int* li = reinterpret_cast<int*>(sm + (1 + p.strip) * GT * p.M);
   int* ni = li + GT;
-  int* lj = ni + GT;                            // [GSTRIP][64]
-  int* nj = lj + GSTRIP * GT;                   // [GSTRIP][64]
+  int* lj = ni + GT;                            // [strip][64]
+  int* nj = lj + p.strip * GT;                  // [strip][64]
 
-  const int ti = blockIdx.y, tj0 = blockIdx.x * GSTRIP;
-  int ntj = min(GSTRIP, p.cols_pad / GT - tj0);
+  const int ti = blockIdx.y, tj0 = blockIdx.x * p.strip;
+  int ntj = min(p.strip, p.cols_pad / GT - tj0);
   if (p.lower_only) ntj = min(ntj, ti - tj0 + 1);
   if (ntj <= 0) return;                         // strip entirely above the diagonal
   const int z = blockIdx.z;
@@ -133,19 +133,24 @@ __global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
   }
 }
 
-int gram(const GramArgs& a, int batch, cudaStream_t st) {
+int gram(const GramArgs& a_in, int batch, cudaStream_t st) {
+  GramArgs a = a_in;
   RC_REQUIRE(a.M >= 1 && a.M <= 80, -2, "gram: M=%d out of range [1,80]", a.M);
   RC_REQUIRE(a.rows_pad % GT == 0 && a.cols_pad % GT == 0 && a.ld_out % 2 == 0, -2, "gram: padded sizes must be multiples of 64");
   RC_REQUIRE(!a.lower_only || a.rows_pad == a.cols_pad, -2, "gram: lower_only needs a square output");
   const long tr = a.rows_pad / GT, tc = a.cols_pad / GT;
   RC_REQUIRE(tr <= 65535 && batch <= 65535, -2, "gram: %ld row tiles / %d problems exceed the grid limits", tr, batch);
-  const size_t smem = (size_t)(1 + GSTRIP) * GT * a.M * sizeof(double) + (size_t)(2 + 2 * GSTRIP) * GT * sizeof(int);
+  // Strips amortise the prologue over several tiles, which only pays once there are more tiles than the GPU holds at a time
+  // (~5 CTAs x 148 SMs); below that one tile per CTA keeps every tile in flight at once (N = 256: 20 -> 6 us).
+  const long tiles = (a.lower_only ? tr * (tr + 1) / 2 : tr * tc) * batch;
+  a.strip = tiles >= 3000 ? GSTRIP : 1;
+  const size_t smem = (size_t)(1 + a.strip) * GT * a.M * sizeof(double) + (size_t)(2 + 2 * a.strip) * GT * sizeof(int);
   static size_t configured = 48 * 1024;
   if (smem > configured) {
     RC_CUDA_OK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  gram_kernel<<<dim3((unsigned)((tc + GSTRIP - 1) / GSTRIP), (unsigned)tr, batch), GTHREADS, smem, st>>>(a);
+  gram_kernel<<<dim3((unsigned)((tc + a.strip - 1) / a.strip), (unsigned)tr, batch), GTHREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
   return 0;
 }

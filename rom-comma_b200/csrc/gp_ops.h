@@ -16,6 +16,7 @@ struct GramArgs {
   int rows_pad, cols_pad;              // multiples of 64; indices >= L*N (L*N2) are padding
   int lower_only;                      // only 64-tiles on or below the diagonal
   int pad_identity;                    // padding gets the identity (square factorisation input) instead of zeros
+  int strip;                           // set by gram(): 64-column tiles per CTA (1 for small problems, 4 once the grid exceeds a few waves)
 };
 int gram(const GramArgs& a, int batch, cudaStream_t st);
 
