@@ -400,15 +400,21 @@ size_t potrf_workspace_bytes(int n, int batch) {
 // Block columns factored between two trailing updates (rank 128 * group).  Four while the trailing matrix is large (its K = 512 tiles
 // amortise the read-modify-write epilogue; cfg3 117.6 -> 116.8 ms against two), two once the trailing update is down to a wave or two
 // of tiles and the longer column updates of a wide group are pure chain latency (n = 2048: 2.86 -> 2.72 ms).  RC_POTRF_GROUP (1..8)
-// fixes the width.
+// fixes the width.  Eight while 160+ blocks remain (n >= 20480; cfg4 933 -> 927 ms); thresholds: RC_POTRF_T4 / RC_POTRF_T8.
 static int potrf_group_env() {
   const char* e = getenv("RC_POTRF_GROUP");
   const int v = e ? atoi(e) : 0;
   return v < 1 ? 0 : (v > 8 ? 8 : v);
 }
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 static int potrf_group(int blocks_left) {
   const int v = potrf_group_env();
-  return v ? v : (blocks_left >= 40 ? 4 : 2);
+  if (v) return v;
+  static const int t4 = env_int("RC_POTRF_T4", 40), t8 = env_int("RC_POTRF_T8", 160);
+  return blocks_left >= t8 ? 8 : (blocks_left >= t4 ? 4 : 2);
 }
 
 template <typename Hook>
