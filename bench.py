@@ -38,13 +38,13 @@ METRIC, UNIT = 'mogpr_lml_grad_evals_per_s', 'evals/s'
 # launch: the first rank-256 trailing update of potrf (profiles/r01_ncu_ws_syrk.md), the top level of trtri and the selected LAUUM
 # (profiles/r01_ncu_ws_trtri_lauum.md).  Algorithmic bytes of the same launches (operands once + C read/write): 2.1 GB, 1.6 GB, 0.8 GB - the
 # re-reads of the long-K launches are L2 capacity misses; at 1.1 TB/s (17 % of the HBM bandwidth) in the worst launch they are not the bound.
-NCU_TRAFFIC = {'syrk_rank512_first_launch_bytes': 3.200e9, 'syrk_rank512_first_launch_algorithmic_bytes': 2.08e9,
+NCU_TRAFFIC = {'syrk_rank512_first_launch_bytes': 2.401e9, 'syrk_rank512_first_launch_algorithmic_bytes': 2.08e9,
                'trtri_top_level_launch_bytes': 4.83e9, 'trtri_top_level_launch_algorithmic_bytes': 1.34e9,
                'trtri_top_level_note': 'L2-blocked 12 x 12 tile raster: 4.8 GB in 15.96 ms (18.0 GB in 16.29 ms with column-major tile order); DMMA pipe '
                                        '94.6 % active, L2 hit rate 78 %',
                'lauum_selected_launch_bytes': 3.42e9, 'lauum_selected_launch_algorithmic_bytes': 1.34e9,
-               'source': 'profiles/r01_ncu_ws_syrk512.md (DMMA pipe 89.7 % of active cycles, L2 hit rate 71 %: operand re-reads behind the streaming C '
-                         'tiles, 0.88 TB/s - not the bound), profiles/r01_ncu_trtri_top_lauum_raster.csv'}
+               'source': 'profiles/r01_ncu_syrk512_raster.csv (L2-blocked raster + streaming C accesses: 2.40 GB, DMMA pipe 90.6 % of active cycles; '
+                         '3.47 GB before, profiles/r01_ncu_ws_syrk512.md), profiles/r01_ncu_trtri_top_lauum_raster.csv'}
 
 
 def parse():

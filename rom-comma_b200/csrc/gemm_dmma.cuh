@@ -67,15 +67,49 @@ struct GemmTile {
 };
 
 // tile index (over all matrices of the batch) -> coordinates, K range and base pointers
+// LOWER: -1 = decide at run time from p.lower_only (the cp.async kernel), 0 / 1 = known at compile time (the warp-specialised kernel is
+// instantiated per case so that each copy carries only its own index arithmetic).
+template <int LOWER = -1>
 __device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p, long tile, long tiles_per_matrix) {
+  const bool lower = LOWER < 0 ? (p.lower_only != 0) : (LOWER != 0);
   const int z = (int)(tile / tiles_per_matrix);
   const long idx = tile - (long)z * tiles_per_matrix;
   int tm, tn;
-  if (p.lower_only) {
+  if (lower && p.kmode != K_FULL) {
+    // row-major over the lower triangle: tile row tm has the longest K of what is left (K_GE_M0: LAUUM, where the raster below costs 2 % -
+    // the selected tile lists leave it too few tiles per super-tile - and saves no traffic)
     tm = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
     while ((long)(tm + 1) * (tm + 2) / 2 <= idx) ++tm;
     while ((long)tm * (tm + 1) / 2 > idx) --tm;
     tn = (int)(idx - (long)tm * (tm + 1) / 2);
+  } else if (lower) {
+    // Lower triangle in the same L2-blocked raster (rank-k updates: first rank-512 trailing update 3.2 -> 2.4 GB of DRAM traffic, 2.1 GB algorithmic): super-rows of G_RASTER tile rows (top first: longest K for K_GE_M0), inside one
+    // the full G_RASTER-wide super-tiles left to right, then the triangular one on the diagonal; rows first inside a super-tile.
+    // C(s) = tiles above super-row s = 72 s^2 + 6 s for G_RASTER = 12 (every super-row above the last one is full).
+    constexpr int R = G_RASTER, FULL = R * R, DIAG = R * (R + 1) / 2;
+    const int tiles_m = p.M / G_BM, i32 = (int)idx;
+    int si = (int)((sqrt((double)DIAG * DIAG + 2.0 * FULL * (double)i32) - DIAG) / FULL);     // root of FULL s^2/2 + (DIAG - FULL/2) s = idx ...
+    auto above = [&](int s_) { return FULL * (s_ * (s_ - 1) / 2) + DIAG * s_; };
+    while (above(si + 1) <= i32) ++si;
+    while (above(si) > i32) --si;
+    const int h = min(R, tiles_m - si * R);
+    int r = i32 - above(si);
+    int tml, tnl, sj;
+    if (r < si * h * R) {
+      sj = r / (h * R);
+      r -= sj * h * R;
+      tml = r / R;
+      tnl = r - tml * R;
+    } else {
+      sj = si;
+      r -= si * h * R;
+      tml = (int)((sqrt(8.0 * (double)r + 1.0) - 1.0) * 0.5);
+      while ((tml + 1) * (tml + 2) / 2 <= r) ++tml;
+      while (tml * (tml + 1) / 2 > r) --tml;
+      tnl = r - tml * (tml + 1) / 2;
+    }
+    tm = si * R + tml;
+    tn = sj * R + tnl;
   } else {
     // L2-blocked raster: the ~148 tiles in flight at any time form a G_RASTER x G_RASTER super-tile, so they share G_RASTER row panels
     // of A and G_RASTER column panels of B and walk k almost in step - each operand panel comes from DRAM about once per super-tile

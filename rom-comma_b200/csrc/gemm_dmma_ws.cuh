@@ -86,7 +86,7 @@ __device__ __forceinline__ void ws_load_operand(double* dst, const double* src, 
   }
 }
 
-template <bool TA, bool TB>
+template <bool TA, bool TB, bool LOWER>
 __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, long tiles_per_matrix, long total_tiles, int* __restrict__ sched,
                                                                     int tiles_per_cta, const __grid_constant__ CUtensorMap mapA,
                                                                     const __grid_constant__ CUtensorMap mapB) {
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
         if (lane == 0) t = atomicAdd(sched, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= total_tiles) break;
-        T = gemm_decode_tile(p, t, tiles_per_matrix);
+        T = gemm_decode_tile<LOWER ? 1 : 0>(p, t, tiles_per_matrix);
         if (T.nk >= 0) {
           tile = t;
           ++drawn;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
       tphase ^= 1u;
     }
     if (tile < 0) break;
-    const GemmTile T = gemm_decode_tile(p, tile, tiles_per_matrix);
+    const GemmTile T = gemm_decode_tile<LOWER ? 1 : 0>(p, tile, tiles_per_matrix);
     if (p.beta != 0.0) {   // pull this warp's 64 x 32 part of C (64 rows x 256 B) towards L2 while the main loop runs
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -313,15 +313,15 @@ int* gemm_sched_slot(int device);   // defined in chol.cu
 // tiles_per_cta = 0: persistent grid (one CTA per SM draws tiles until the list is empty).  tiles_per_cta = k > 0: a YIELDING launch of
 // ceil(tiles / k) CTAs that retire after k tiles each - for background work on a low-priority stream: the SMs return to the block
 // scheduler every few tiles, so pending CTAs of a higher-priority stream never wait longer than that.
-template <bool TA, bool TB>
-inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream, int tiles_per_cta = 0) {
+template <bool TA, bool TB, bool LOWER>
+inline int launch_gemm_ws_impl(const GemmArgs& a, int batch, cudaStream_t stream, int tiles_per_cta) {
   using S = GemmWsSmem<TA, TB>;
   static bool configured = false;
   static int num_sms = 0;
   int dev = 0;
   RC_CUDA_OK(cudaGetDevice(&dev));
   if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_ws_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
+    RC_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_ws_kernel<TA, TB, LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
     RC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
@@ -343,10 +343,15 @@ inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream, int
   if (prof) profile_gemm_begin(stream);
   int* sched = gemm_sched_slot(dev);
   RC_REQUIRE(sched != nullptr, -3, "gemm_dmma_ws: could not allocate the tile-scheduler scratch");
-  gemm_dmma_ws_kernel<TA, TB><<<grid, W_THREADS, S::BYTES, stream>>>(a, tiles, total, sched, tiles_per_cta, mapA, mapB);
+  gemm_dmma_ws_kernel<TA, TB, LOWER><<<grid, W_THREADS, S::BYTES, stream>>>(a, tiles, total, sched, tiles_per_cta, mapA, mapB);
   if (prof) profile_gemm_end(stream, gemm_tile_flops(a, batch));
   RC_LAUNCH_OK();
   return 0;
+}
+
+template <bool TA, bool TB>
+inline int launch_gemm_ws(const GemmArgs& a, int batch, cudaStream_t stream, int tiles_per_cta = 0) {
+  return a.lower_only ? launch_gemm_ws_impl<TA, TB, true>(a, batch, stream, tiles_per_cta) : launch_gemm_ws_impl<TA, TB, false>(a, batch, stream, tiles_per_cta);
 }
 
 }  // namespace rc
