@@ -26,7 +26,12 @@
 
 namespace rc {
 
-constexpr int W_STAGES = 6, W_CONSUMERS = 8, W_THREADS = 32 * (W_CONSUMERS + 1), W_RING = 4, W_EPI_ROWS = 2;
+// Three warpgroups: two of consumers (8 warps) and one for the producer (one working warp).  The launch gives every thread 168 registers
+// (65536 / 384); setmaxnreg then moves registers from the producer's warpgroup to the consumers (W_REGS_PRODUCER / W_REGS_CONSUMER:
+// 128 x 56 + 256 x 224 = 64512), whose 128 accumulator registers plus fragments, tile state and the batched C loads of the epilogue do not
+// fit 168 without spilling.
+constexpr int W_STAGES = 6, W_CONSUMERS = 8, W_THREADS = 32 * (W_CONSUMERS + 4), W_RING = 4, W_EPI_ROWS = 4;
+constexpr int W_REGS_PRODUCER = 56, W_REGS_CONSUMER = 224;
 
 template <bool TA, bool TB>
 struct GemmWsSmem {
@@ -117,6 +122,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
+
+  if (warp >= W_CONSUMERS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(W_REGS_PRODUCER));
+    if (warp != W_CONSUMERS) return;          // the other three warps of the producer's warpgroup only give their registers away
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(W_REGS_CONSUMER));
+  }
 
   if (warp == W_CONSUMERS) {
     // ---------------------------------------------------------------- producer
