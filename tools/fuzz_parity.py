@@ -1,0 +1,72 @@
+"""Randomised parity sweep on the GPU (not part of the test suite; test infrastructure, it imports the oracle): random shapes around the
+block / tile / strip boundaries, every flag combination of rc_lml_grad, predict, and Sobol subsets, against oracle/ on identical inputs.
+    python tools/fuzz_parity.py [seconds] [seed]"""
+import sys, time
+from pathlib import Path
+import numpy as np, torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / 'rom-comma_b200'))
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / 'tests'))
+from romcomma import _capi as C, gf_compat as gf
+from oracle import gp, sobol
+from conftest import random_problem, assert_close
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+edges = [1, 2, 3, 31, 32, 33, 63, 64, 65, 127, 128, 129, 191, 192, 193, 255, 256, 257, 300, 383, 384, 385, 511, 512, 513, 640, 700]
+t0, cases = time.time(), 0
+while time.time() - t0 < budget:
+    L = int(rng.integers(1, 5))
+    N = int(rng.choice(edges)) if rng.random() < 0.7 else int(rng.integers(1, 700))
+    N = max(N, 2)                                   # Y is standardised per column
+    if L * N > 1500:
+        N = 1500 // L
+    M = int(rng.integers(1, 13))
+    full_F = bool(rng.random() < 0.5) and L > 1
+    X, Y, ls, F, E = random_problem(N, M, L, seed=int(rng.integers(1 << 30)), full_F=full_F)
+    dX, dY = C.dev(X), C.dev(Y)
+    args = (C.dev(ls), C.dev(F[None]), C.dev(E[None]))
+    ref = gp.lml_grad_mo(X, Y, ls, F, E)
+    tag = f'N={N} M={M} L={L} full_F={full_F}'
+    for flags in (C.RC_GRAD_NONE, C.RC_GRAD_VARIANCE, C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES) + ((C.RC_GRAD_VARIANCE | C.RC_GRAD_F_DIAGONAL,) if not full_F else ()):
+        plan = C.LmlGradPlan(dX, dY, L, 1, flags)
+        res = plan.unpack(plan(*args).cpu().numpy())[0]
+        assert plan.info.cpu().tolist() == [0], tag
+        assert_close(res['lml'], ref['lml'], what=f'{tag} flags={flags} lml')
+        if flags & C.RC_GRAD_VARIANCE:
+            dF, rF = (np.diag(res['dF']), np.diag(ref['dF'])) if flags & C.RC_GRAD_F_DIAGONAL else (res['dF'], ref['dF'])
+            assert_close(dF, rF, atol=1e-10 * L * N, what=f'{tag} flags={flags} dF')
+            assert_close(res['dE'], ref['dE'], atol=1e-10 * L * N, what=f'{tag} flags={flags} dE')
+        if flags & C.RC_GRAD_LENGTHSCALES:
+            assert_close(res['dls'], ref['dls'], atol=1e-10 * L * N, what=f'{tag} dls')
+    ns = int(rng.integers(1, 40))
+    xs = rng.normal(size=(ns, M))
+    mean, var = gf.predict_core(dX, dY, args[0], F[None], E[None], C.dev(xs), L, 1, True)
+    rm, rv = gp.predict_mo(X, Y, ls, F, E, xs)
+    assert_close(mean[0].cpu().numpy(), rm, rtol=1e-7, atol=1e-9, what=f'{tag} predict mean')
+    assert_close(var[0].cpu().numpy(), rv, rtol=1e-7, atol=1e-9, what=f'{tag} predict var')
+    if not full_F:
+        Fd = np.diag(F).copy()
+        KiY = gp.k_inv_y_mo(X, Y, ls, F, E)
+        Phi, g0, g0KY = C.sobol_prepare(dX, C.dev(ls), C.dev(Fd), C.dev(KiY.reshape(L, N)), True)
+        masks = [int(rng.integers(1, 1 << M)) for _ in range(int(rng.integers(1, 4)))] + [C.slice_mask(0, M), C.slice_mask(0, 1), C.slice_mask(M - 1, M)]
+        V = C.sobol_contract(dX, Phi, g0KY, L, True, masks).cpu().numpy()
+        scale = np.abs(V).max() + 1e-300
+        for v, m in zip(V, masks):
+            idx = [i for i in range(M) if (m >> i) & 1]
+            # V is a sum of N^2 terms of either sign: the comparison can only be as tight as the conditioning of the sum allows - the float64
+            # oracle itself is 8 eps sum|terms| away from an extended-precision evaluation in the worst cases this sweep generates
+            perm = idx + [i for i in range(M) if i not in idx]
+            cal = sobol.ClosedSobol(X[:, perm], ls[:, perm], F, KiY, True)
+            absum = np.zeros((L, L))
+            for l in range(L):
+                for j in range(L):
+                    H = sobol.H_block(cal.X, cal.Phi[l, 0], cal.Phi[j, 0], 0, len(idx))
+                    absum[l, j] = np.abs(cal.g0KY[l, 0]) @ (np.abs(H) @ np.abs(cal.g0KY[j, 0]))
+            ref_v = cal.marginalize((0, len(idx)))['V']
+            err = np.abs(v - ref_v)
+            bound = 1e-10 + 1e-8 * np.abs(ref_v) + 8 * np.finfo(float).eps * absum
+            assert np.all(err <= bound), f'{tag} sobol mask={m:b}: max err/bound {np.max(err / bound):.2f}, max abs err {err.max():.3e}'
+    cases += 1
+print(f'fuzz ok: {cases} random cases in {time.time() - t0:.0f} s')
