@@ -177,6 +177,8 @@ diag_potrf_inv_kernel(double* __restrict__ A, long ld, long strideA, double* __r
   double* Ab = A + (long)z * strideA + (long)blk * DB * (ld + 1);
   double* Db = dinv + (long)z * strideD + (long)blk * DB * DB;
 
+  pdl_launch_dependents();
+  pdl_wait();
   double a[8][8], dr[8], dc[8];
 #pragma unroll
   for (int ia = 0; ia < 8; ++ia) {
@@ -258,7 +260,7 @@ static int launch_diag_factor(double* A, long ld, long strideA, double* dinv, lo
     RC_CUDA_OK(cudaFuncSetAttribute(diag_potrf_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
     configured = true;
   }
-  diag_potrf_inv_kernel<1><<<batch, DB_THREADS, DB_SMEM, st>>>(A, ld, strideA, dinv, strideD, blk, logdet_parts, nblk, info);
+  RC_CUDA_OK(launch_pdl(diag_potrf_inv_kernel<1>, dim3(batch), dim3(DB_THREADS), DB_SMEM, st, A, ld, strideA, dinv, strideD, blk, logdet_parts, nblk, info));
   RC_LAUNCH_OK();
   return 0;
 }
@@ -298,6 +300,8 @@ panel_trsm_kernel(double* __restrict__ A, long ld, long strideA, int blk) {
   double* Az = A + (long)z * strideA;
   const double* Lb = Az + (long)blk * DB * (ld + 1);
   double* Pt = Az + ((long)(blk + 1 + blockIdx.x) * DB + warp * 16) * ld + (long)blk * DB;    // this warp's 16 rows
+  pdl_launch_dependents();
+  pdl_wait();
   // accumulators: acc[h][c][e] = P[8h + g][8c + 2t + e]
   double acc[2][16][2];
 #pragma unroll
@@ -380,7 +384,7 @@ static int launch_panel_trsm(double* A, int n, long ld, long strideA, int blk, i
     RC_CUDA_OK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
     configured = true;
   }
-  panel_trsm_kernel<<<dim3(tiles, batch), 256, PT_SMEM, st>>>(A, ld, strideA, blk);
+  RC_CUDA_OK(launch_pdl(panel_trsm_kernel, dim3(tiles, batch), dim3(256), PT_SMEM, st, A, ld, strideA, blk));
   RC_LAUNCH_OK();
   return 0;
 }
@@ -472,6 +476,8 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __rest
   const double* Az = A + (long)z * strideA;
   const double* Dk = dinv + (long)z * strideD + (long)k * DB * DB;
   double* wz = w + (long)z * strideV;
+  pdl_launch_dependents();
+  pdl_wait();
   if (tid < DB) wk[tid] = wz[(long)k * DB + tid];
   __syncthreads();
   for (int r = warp; r < DB; r += 8) {     // x_k[r] = sum_c Dinv[r][c] w_k[c]
@@ -505,6 +511,8 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __rest
   const double* Az = A + (long)z * strideA;
   const double* Dk = dinv + (long)z * strideD + (long)k * DB * DB;
   double* wz = w + (long)z * strideV;
+  pdl_launch_dependents();
+  pdl_wait();
   if (tid < DB) wk[tid] = wz[(long)k * DB + tid];
   __syncthreads();
   {
@@ -536,13 +544,13 @@ int trsv_lower(const double* A, int n, long ld, long strideA, int batch, const d
   if (!transpose) {
     for (int k = 0; k < nblk; ++k) {
       dim3 grid(nblk - k, batch);
-      trsv_fwd_step_kernel<<<grid, 256, 0, st>>>(A, ld, strideA, dinv, strideD, w, x, strideV, k);
+      RC_CUDA_OK(launch_pdl(trsv_fwd_step_kernel, grid, dim3(256), 0, st, A, ld, strideA, dinv, strideD, w, x, strideV, k));
     }
     count_launches(nblk - 1);
   } else {
     for (int k = nblk - 1; k >= 0; --k) {
       dim3 grid(k + 1, batch);
-      trsv_bwd_step_kernel<<<grid, 256, 0, st>>>(A, ld, strideA, dinv, strideD, w, x, strideV, k);
+      RC_CUDA_OK(launch_pdl(trsv_bwd_step_kernel, grid, dim3(256), 0, st, A, ld, strideA, dinv, strideD, w, x, strideV, k));
     }
     count_launches(nblk - 1);
   }

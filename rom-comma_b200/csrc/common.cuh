@@ -115,6 +115,27 @@ __device__ __forceinline__ double exp_pairwise(double x) {
   return __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
 }
 
+// Programmatic dependent launch: a kernel launched through launch_pdl may start (CTA scheduling, barrier / register set-up, descriptor
+// prefetch) while its predecessor in the stream drains; it must execute pdl_wait() before its first access to global memory, which also
+// makes the predecessor's writes visible.  pdl_launch_dependents() at the top of a kernel lets ITS successor do the same.  Kernels
+// launched the ordinary way after one of these still wait for full completion.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace rc

@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  pdl_launch_dependents();
   __syncthreads();
+  pdl_wait();                                   // everything above overlaps the tail of the previous kernel in the stream
 
   if (warp >= W_CONSUMERS) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(W_REGS_PRODUCER));
@@ -355,7 +357,7 @@ inline int launch_gemm_ws_impl(const GemmArgs& a, int batch, cudaStream_t stream
   if (prof) profile_gemm_begin(stream);
   int* sched = gemm_sched_slot(dev);
   RC_REQUIRE(sched != nullptr, -3, "gemm_dmma_ws: could not allocate the tile-scheduler scratch");
-  gemm_dmma_ws_kernel<TA, TB, LOWER><<<grid, W_THREADS, S::BYTES, stream>>>(a, tiles, total, sched, tiles_per_cta, mapA, mapB);
+  RC_CUDA_OK(launch_pdl(gemm_dmma_ws_kernel<TA, TB, LOWER>, dim3(grid), dim3(W_THREADS), S::BYTES, stream, a, tiles, total, sched, tiles_per_cta, mapA, mapB));
   if (prof) profile_gemm_end(stream, gemm_tile_flops(a, batch));
   RC_LAUNCH_OK();
   return 0;
