@@ -224,3 +224,35 @@ def test_world_size_2_gloo_gather(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert 'rank 0 ok' in outs[0] and 'rank 1 ok' in outs[1]
+
+
+def test_exp_pairwise_polynomial_constants():
+    """The device exp of the pairwise kernels (csrc/common.cuh: exp_pairwise) evaluates a degree-10 polynomial on |r| <= ln2/2 whose
+    coefficients come from tools/exp_poly.py.  Re-derive them and check (a) the literals in the CUDA source are those numbers, (b) the
+    polynomial with double-rounded coefficients is within 1e-15 of exp on the reduced range, (c) the Cody-Waite split of ln 2 is exact
+    enough: hi has 21 trailing zero bits, i.e. 32 significant ones (k * hi is exact for |k| < 2^21), and hi + lo = ln 2 to 1e-18."""
+    import re
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    src = (root / 'rom-comma_b200' / 'csrc' / 'common.cuh').read_text()
+    body = src[src.index('__device__ __forceinline__ double exp_pairwise'):]
+    body = body[:body.index('inline int round_up')]
+    lits = [float(v) for v in re.findall(r'fma\(p, r, ([0-9.e+-]+)\)', body)]
+    lead = float(re.search(r'double p = ([0-9.e+-]+);', body).group(1))
+    coef_src = [lead] + lits                                  # c10 ... c0
+    assert len(coef_src) == 11
+    out = subprocess.run([sys.executable, str(root / 'tools' / 'exp_poly.py'), '10'], capture_output=True, text=True, check=True).stdout
+    line = [ln for ln in out.splitlines() if ln.startswith('   ')][0]
+    coef_fit = [float(v) for v in line.split(',')]            # c0 ... c10
+    assert coef_src[::-1] == coef_fit, 'common.cuh does not hold the coefficients tools/exp_poly.py derives'
+    r = np.linspace(-0.34658, 0.34658, 20001).astype(np.longdouble)
+    p = np.full_like(r, np.longdouble(coef_src[0]))
+    for c in coef_src[1:]:
+        p = p * r + np.longdouble(c)
+    assert float(np.max(np.abs(p / np.exp(r) - 1))) < 1e-15
+    hi = -float(re.search(r'fma\(k, (-[0-9.e+-]+), x\)', body).group(1))
+    lo = -float(re.search(r'fma\(k, (-[0-9.e+-]+), r\)', body).group(1))
+    assert (int(np.float64(hi).view(np.uint64)) & ((1 << 21) - 1)) == 0
+    assert abs((np.longdouble(hi) + np.longdouble(lo)) - np.log(np.longdouble(2))) < 1e-18
