@@ -14,7 +14,7 @@
 //     operations: results are bitwise independent of the schedule.
 //
 // Operand staging, by storage order of the operand:
-//   * k-contiguous operands ([m][k], "non-transposed"): ONE cp.async.bulk.tensor (TMA tiled load, SASS UTMALDG) per stage through a
+//   * k-contiguous operands ([m][k], "non-transposed"): ONE cp.async.bulk.tensor (TMA tiled load, SASS UTMALDG) per k-slice through a
 //     CUtensorMap built per launch, box 16 (k) x 128 (rows) doubles, SWIZZLE_128B: the 16-byte chunk index of a 128-byte row is
 //     XORed with (row & 7), which makes every warp fragment read (8 rows x 4 k) hit all 32 banks twice = the 2-wavefront minimum,
 //     without padding.  (128 separate 128-byte bulk copies per stage are TMA-issue bound: measured 10.5 TFLOP/s.)
@@ -30,7 +30,10 @@ namespace rc {
 // (65536 / 384); setmaxnreg then moves registers from the producer's warpgroup to the consumers (W_REGS_PRODUCER / W_REGS_CONSUMER:
 // 128 x 56 + 256 x 224 = 64512), whose 128 accumulator registers plus fragments, tile state and the batched C loads of the epilogue do not
 // fit 168 without spilling.
-constexpr int W_STAGES = 6, W_CONSUMERS = 8, W_THREADS = 32 * (W_CONSUMERS + 4), W_RING = 4, W_EPI_ROWS = 4;
+// A pipeline stage holds W_SUB k-slices of 16 (two TMA boxes per operand: the 128-byte swizzle limits a box to 16 doubles along k) behind ONE
+// full/empty barrier pair: half the barrier waits, proxy fences and arrivals per flop of a 16-wide stage.
+constexpr int W_SUB = 2;
+constexpr int W_STAGES = 3, W_CONSUMERS = 8, W_THREADS = 32 * (W_CONSUMERS + 4), W_RING = 4, W_EPI_ROWS = 4;
 constexpr int W_REGS_PRODUCER = 56, W_REGS_CONSUMER = 224;
 
 template <bool TA, bool TB>
@@ -38,10 +41,10 @@ struct GemmWsSmem {
   static constexpr int A_STAGE = TA ? G_BK * (G_BM + G_PAD) : G_BM * G_BK;   // doubles; k-contiguous operands are dense + swizzled
   static constexpr int B_STAGE = TB ? G_BK * (G_BN + G_PAD) : G_BN * G_BK;
   static constexpr size_t up1k(size_t b) { return (b + 1023) / 1024 * 1024; }
-  static constexpr size_t A_BYTES = up1k((size_t)W_STAGES * A_STAGE * sizeof(double));
-  static constexpr size_t B_BYTES = up1k((size_t)W_STAGES * B_STAGE * sizeof(double));
+  static constexpr size_t A_BYTES = up1k((size_t)W_STAGES * W_SUB * A_STAGE * sizeof(double));
+  static constexpr size_t B_BYTES = up1k((size_t)W_STAGES * W_SUB * B_STAGE * sizeof(double));
   static constexpr size_t BYTES = 1024 + A_BYTES + B_BYTES + (2 * W_STAGES + 2 * W_RING) * sizeof(unsigned long long) + W_RING * sizeof(int);
-  static constexpr unsigned STAGE_TX = 2u * G_BM * G_BK * sizeof(double);   // bytes landing per stage
+  static constexpr unsigned STAGE_TX = 2u * W_SUB * G_BM * G_BK * sizeof(double);   // bytes landing per stage
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -163,12 +166,15 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
       }
       if (tile < 0) break;
       const int z = (int)(tile / tiles_per_matrix);
-      for (int kt = 0; kt < T.nk; ++kt) {
+      for (int kt = 0; kt < T.nk; kt += W_SUB) {   // K ranges are multiples of 128: nk is a multiple of W_SUB
         mbar_wait(empty + stage, phase ^ 1u);
         if (lane == 0) mbar_arrive_expect_tx(full + stage, S::STAGE_TX);
         __syncwarp();
-        ws_load_operand<TA>(As + stage * S::A_STAGE, T.A, p.lda, &mapA, z, T.m0, T.kb + kt * G_BK, lane, full + stage);
-        ws_load_operand<TB>(Bs + stage * S::B_STAGE, T.B, p.ldb, &mapB, z, T.n0, T.kb + kt * G_BK, lane, full + stage);
+#pragma unroll
+        for (int sub = 0; sub < W_SUB; ++sub) {
+          ws_load_operand<TA>(As + (stage * W_SUB + sub) * S::A_STAGE, T.A, p.lda, &mapA, z, T.m0, T.kb + (kt + sub) * G_BK, lane, full + stage);
+          ws_load_operand<TB>(Bs + (stage * W_SUB + sub) * S::B_STAGE, T.B, p.ldb, &mapB, z, T.n0, T.kb + (kt + sub) * G_BK, lane, full + stage);
+        }
         if (++stage == W_STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -218,11 +224,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kt = 0; kt < T.nk; ++kt) {
+    for (int kt = 0; kt < T.nk; kt += W_SUB) {
       mbar_wait(full + stage, phase);
       __syncwarp();
-      const double* as = As + stage * S::A_STAGE;
-      const double* bs = Bs + stage * S::B_STAGE;
+#pragma unroll
+      for (int sub = 0; sub < W_SUB; ++sub) {
+      const double* as = As + (stage * W_SUB + sub) * S::A_STAGE;
+      const double* bs = Bs + (stage * W_SUB + sub) * S::B_STAGE;
 #pragma unroll
       for (int kk = 0; kk < G_BK / 4; ++kk) {
         double a[8], b[4];
@@ -236,6 +244,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
       }
       // Release the stage to the producer.  The fragment loads above are generic-proxy reads, the refill is an async-proxy (TMA) write:
       // without a cross-proxy fence ptxas may schedule the arrive right after the last LDS is *issued* and the bulk copy of the next
@@ -340,7 +349,7 @@ inline int launch_gemm_ws_impl(const GemmArgs& a, int batch, cudaStream_t stream
     configured = true;
   }
   if (a.M <= 0 || a.N <= 0 || batch <= 0) return 0;
-  RC_REQUIRE(a.M % G_BM == 0 && a.N % G_BN == 0 && a.K % G_BK == 0, -2, "gemm_dmma_ws: M,N must be multiples of 128 and K of 16 (got %d,%d,%d)", a.M,
+  RC_REQUIRE(a.M % G_BM == 0 && a.N % G_BN == 0 && a.K % (G_BK * W_SUB) == 0, -2, "gemm_dmma_ws: M,N must be multiples of 128 and K of 32 (got %d,%d,%d)", a.M,
              a.N, a.K);
   RC_REQUIRE(a.lda % 2 == 0 && a.ldb % 2 == 0 && a.ldc % 2 == 0, -2, "gemm_dmma_ws: leading dimensions must be even (16-byte rows)");
   const long tm = a.M / G_BM, tn = a.N / G_BN;
