@@ -40,6 +40,13 @@ int rc_measure_exp_gexps(double* scratch, double* gexps_host);
  * roofline: between rc_profile_begin() and rc_profile_end() every GEMM launch is bracketed by CUDA events on its own stream.
  * rc_profile_end synchronises on them and returns the summed launch durations (ms), the flops those launches executed
  * (2*128*128*K per tile actually computed) and their count.  Diagnostic, process-global, not thread-safe. */
+/* Test hook, host only (no GPU needed): the order in which the tile scheduler of the GEMM hands out the 128 x 128 tiles of an M x N x K
+ * product - kmode 0 full K, 1 k >= n0, 2 k < m0+128, 3 k >= m0, 4 k < n0+128; lower_only: tiles on or below the diagonal; sel_block > 0:
+ * tiles whose row block lies above the column block get k steps = -1.  out_host: 4 ints per tile { m0, n0, k begin, k steps of 16 },
+ * M/128 * N/128 (or the triangular count) tiles.  Returns the tile count (< 0: bad argument).  The L2-blocked raster must visit every tile
+ * exactly once (tests/test_capi_symbols.py). */
+int rc_debug_tile_order(int M, int N, int K, int lower_only, int kmode, int sel_block, int* out_host);
+
 int rc_profile_begin(void);
 int rc_profile_end(double* gemm_ms_host, double* gemm_flops_host, long* gemm_launches_host);
 

@@ -166,6 +166,10 @@ int rc_apply_variance_noise(const double* Kunit, long ldu, const double* F, cons
   return apply_variance_noise(Kunit, ldu, F, E, L, N, n_pad, out, ld_out, lower_only, (cudaStream_t)stream);
 }
 
+int rc_debug_tile_order(int M, int N, int K, int lower_only, int kmode, int sel_block, int* out_host) {
+  return debug_tile_order(M, N, K, lower_only, kmode, sel_block, out_host);
+}
+
 size_t rc_potrf_bufsize(int n_pad, int batch) { return align256(potrf_workspace_bytes(n_pad, batch)); }
 
 int rc_potrf(double* A, int n_pad, long ld, long strideA, int batch, void* work, int* info, rc_stream_t stream) {

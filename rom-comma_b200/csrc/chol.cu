@@ -980,4 +980,20 @@ int pad_identity(const double* src, int n, long strideS, double* dst, int n_pad,
   return 0;
 }
 
+// Host mirror of the device tile order (gemm_decode_tile is __host__ __device__): what rc_debug_tile_order reports.
+int debug_tile_order(int M, int N, int K, int lower_only, int kmode, int sel_block, int* out) {
+  RC_REQUIRE(M > 0 && N > 0 && K > 0 && M % G_BM == 0 && N % G_BN == 0 && K % G_BK == 0 && out, -2, "rc_debug_tile_order: bad shape");
+  RC_REQUIRE(kmode >= K_FULL && kmode <= K_LE_N1, -2, "rc_debug_tile_order: kmode %d", kmode);
+  RC_REQUIRE(!lower_only || M == N, -2, "rc_debug_tile_order: lower_only needs M == N");
+  GemmArgs p{};
+  p.M = M; p.N = N; p.K = K; p.lower_only = lower_only; p.kmode = kmode; p.sel_block = sel_block;
+  const long tm = M / G_BM, tn = N / G_BN;
+  const long tiles = lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  for (long t = 0; t < tiles; ++t) {
+    const GemmTile T = lower_only ? gemm_decode_tile<1>(p, t, tiles) : gemm_decode_tile<0>(p, t, tiles);
+    out[4 * t + 0] = T.m0; out[4 * t + 1] = T.n0; out[4 * t + 2] = T.kb; out[4 * t + 3] = T.nk;
+  }
+  return (int)tiles;
+}
+
 }  // namespace rc

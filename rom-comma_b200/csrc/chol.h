@@ -42,6 +42,9 @@ size_t tri_gemv_workspace_bytes(int n, int batch);
 int tri_gemv_lower(const double* Z, int n, long ld, long strideZ, int batch, const double* v, double* out, long strideV, int transpose,
                    double* parts, cudaStream_t st);
 
+// Host-side: the order in which a tile list is handed out (m0, n0, k begin, k steps of 16 per tile); returns the tile count.
+int debug_tile_order(int M, int N, int K, int lower_only, int kmode, int sel_block, int* out);
+
 int sum_parts(const double* parts, int count, int batch, double* out, double scale, cudaStream_t st);
 int dot_batched(const double* a, const double* b, long n, long stride, int batch, double* out, cudaStream_t st);
 int extract_lower(const double* src, long lds, long strideS, double* dst, int n, long strideDst, int batch, int symmetrize, cudaStream_t st);

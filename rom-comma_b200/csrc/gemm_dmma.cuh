@@ -69,8 +69,10 @@ struct GemmTile {
 // tile index (over all matrices of the batch) -> coordinates, K range and base pointers
 // LOWER: -1 = decide at run time from p.lower_only (the cp.async kernel), 0 / 1 = known at compile time (the warp-specialised kernel is
 // instantiated per case so that each copy carries only its own index arithmetic).
+__host__ __device__ __forceinline__ int gemm_imin(int a, int b) { return a < b ? a : b; }
+
 template <int LOWER = -1>
-__device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p, long tile, long tiles_per_matrix) {
+__host__ __device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p, long tile, long tiles_per_matrix) {
   const bool lower = LOWER < 0 ? (p.lower_only != 0) : (LOWER != 0);
   const int z = (int)(tile / tiles_per_matrix);
   const long idx = tile - (long)z * tiles_per_matrix;
@@ -92,7 +94,7 @@ __device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p, long til
     auto above = [&](int s_) { return FULL * (s_ * (s_ - 1) / 2) + DIAG * s_; };
     while (above(si + 1) <= i32) ++si;
     while (above(si) > i32) --si;
-    const int h = min(R, tiles_m - si * R);
+    const int h = gemm_imin(R, tiles_m - si * R);
     int r = i32 - above(si);
     int tml, tnl, sj;
     if (r < si * h * R) {
@@ -122,10 +124,10 @@ __device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p, long til
     const int idx32 = (int)idx;                                        // tiles of ONE matrix: < 2^31, 32-bit divisions
     const int per_slow_band = G_RASTER * fast_n;
     const int sb = idx32 / per_slow_band;                              // band along the slow dimension (only the last one is narrower)
-    const int slow_w = min(G_RASTER, slow_n - sb * G_RASTER);
+    const int slow_w = gemm_imin(G_RASTER, slow_n - sb * G_RASTER);
     const int r1 = idx32 - sb * per_slow_band;
     const int fb = r1 / (G_RASTER * slow_w);                           // band along the fast dimension
-    const int fast_w = min(G_RASTER, fast_n - fb * G_RASTER);
+    const int fast_w = gemm_imin(G_RASTER, fast_n - fb * G_RASTER);
     const int r2 = r1 - fb * G_RASTER * slow_w;
     int slow = sb * G_RASTER + r2 / fast_w, fast = fb * G_RASTER + r2 % fast_w;
     if (p.kmode == K_LT_M1 || p.kmode == K_LE_N1) slow = slow_n - 1 - slow;   // K grows with the index: start from the far end
@@ -137,9 +139,9 @@ __device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p, long til
   t.n0 = tn * G_BN;
   int kb = 0, ke = p.K;
   if (p.kmode == K_GE_N0) kb = t.n0;
-  else if (p.kmode == K_LT_M1) ke = min(p.K, t.m0 + G_BM);
+  else if (p.kmode == K_LT_M1) ke = gemm_imin(p.K, t.m0 + G_BM);
   else if (p.kmode == K_GE_M0) kb = t.m0;
-  else if (p.kmode == K_LE_N1) ke = min(p.K, t.n0 + G_BN);
+  else if (p.kmode == K_LE_N1) ke = gemm_imin(p.K, t.n0 + G_BN);
   t.kb = kb;
   t.nk = (ke - kb) / G_BK;
   if (p.sel_block > 0 && t.m0 / p.sel_block > (t.n0 + G_BN - 1) / p.sel_block) t.nk = -1;   // row blocks all above the column blocks

@@ -26,6 +26,7 @@ _SIGNATURES = {
     'rc_launch_count': (ctypes.c_long, []),
     'rc_measure_dmma_tflops': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
     'rc_measure_exp_gexps': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
+    'rc_debug_tile_order': (ctypes.c_int, [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     'rc_profile_begin': (ctypes.c_int, []),
     'rc_profile_end': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'rc_gram': (ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p, c_double_p,
