@@ -1,7 +1,7 @@
 """Benchmark of the B200-native rom-comma hot path.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port), FULL size
 
 Workload (BASELINE.json metric): cfg3 = synthetic MOGPR N=4096, M=8, L=4 (n = 16384, 2.1 GB FP64 gram).
 A "step" is ONE evaluation of the covariant MOGPR log-marginal-likelihood plus its analytic gradient with respect to the kernel
@@ -11,9 +11,17 @@ all inputs resident in HBM; `e2e` is the same evaluation through the public API 
 buffers, copies inside the timed region.  The second headline quantity, closed-form Sobol index sweeps per second on the same
 configuration, is reported in the "sobol" object of the same JSON line.
 
-N > 1 (torchrun, one process per GPU): a single dense factorisation does not shard ("replicas only"), so every rank
-evaluates its own hyper-parameter point of the same shape (multi-start / fold-parallel fitting) - weak scaling, no data-path
-collective; the Sobol sweep is sharded by marginal subset and gathered with one NCCL all_gather.
+N > 1 (torchrun, one process per GPU): a single dense factorisation does not shard ("replicas only"), so for the headline
+metric every rank evaluates its own hyper-parameter point of the same shape (multi-start / fold-parallel fitting) - weak scaling, no
+data-path collective.  The workloads that DO shard are timed in the same run and reported per world size under "sharded":
+  sobol_sweep        cfg3's 25-slice sweep, the (N, n) sample-pair space split by 64-row tile over the ranks, ONE NCCL all-reduce of the
+                     (slices, L, L) partial sums (the "sobol" object);
+  sobol_all_subsets  cfg5 (N=8192, M=12, L=3): closed V for all 2^12 - 1 input subsets, subset blocks round-robin over the ranks, ONE
+                     NCCL all_gather of the (L, L) results;
+  folds              cfg2 (Sobol-G, N=2048, M=10): user.run.gpr + user.run.gsa over the 10 folds + the improper fold through the public
+                     API (files included), fold k on rank k % world, csvs collected by rank 0.
+With --steps/--warmup the CPU leg of the N = 1 run also checks the GPU's full-size LML and gradient against the oracle's
+("parity_full_size").
 """
 from __future__ import annotations
 
@@ -35,9 +43,9 @@ for p in (ROOT, ROOT / 'rom-comma_b200'):
 
 METRIC, UNIT = 'mogpr_lml_grad_evals_per_s', 'evals/s'
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (gemm_dmma_ws_kernel) from the committed `ncu --set full` captures, per
-# launch: the first rank-256 trailing update of potrf (profiles/r01_ncu_ws_syrk.md), the top level of trtri and the selected LAUUM
-# (profiles/r01_ncu_ws_trtri_lauum.md).  Algorithmic bytes of the same launches (operands once + C read/write): 2.1 GB, 1.6 GB, 0.8 GB - the
-# re-reads of the long-K launches are L2 capacity misses; at 1.1 TB/s (17 % of the HBM bandwidth) in the worst launch they are not the bound.
+# launch (constants from profiles/, NOT measured in this run): the first rank-512 trailing update of potrf, the top level of trtri and the
+# selected LAUUM.  Algorithmic bytes of the same launches (operands once + C read/write): 2.08 GB, 1.34 GB, 1.34 GB - the re-reads of
+# the long-K launches are L2 capacity misses; at <= 0.3 TB/s (5 % of the HBM bandwidth) they are not the bound.
 NCU_TRAFFIC = {'syrk_rank512_first_launch_bytes': 2.401e9, 'syrk_rank512_first_launch_algorithmic_bytes': 2.08e9,
                'trtri_top_level_launch_bytes': 4.83e9, 'trtri_top_level_launch_algorithmic_bytes': 1.34e9,
                'trtri_top_level_note': 'L2-blocked 12 x 12 tile raster: 4.8 GB in 15.96 ms (18.0 GB in 16.29 ms with column-major tile order); DMMA pipe '
@@ -56,6 +64,7 @@ def parse():
     ap.add_argument('--workload', default='cfg3')
     ap.add_argument('--N', type=int, default=None, help='override the number of samples (debugging only; the JSON line names it)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sharded', action='store_true', help='skip the sharded legs (cfg5 all-subsets sweep, cfg2 folds)')
     ap.add_argument('--cpu-sample-N', type=int, default=None, help='rows used by the CPU baseline sample (default: all for cpu_baseline, 2048 for --impl reference)')
     return ap.parse_args()
 
@@ -118,7 +127,9 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port = the reference algorithm through LAPACK; the reference itself needs TensorFlow/GPflow, absent here)
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_eval_seconds(w, L, rows, repeats=1):
+def cpu_eval_seconds(w, L, rows, repeats=1, keep=None):
+    """Seconds of ONE LML+gradient evaluation of the first `rows` samples through the oracle port (dpotrf + dpotri, all host threads).
+    keep: a dict that receives the oracle's numbers of the last evaluation (the N = 1 run compares the GPU's against them)."""
     from threadpoolctl import threadpool_limits
     from oracle import gp
     cores = os.cpu_count() or 1
@@ -127,8 +138,10 @@ def cpu_eval_seconds(w, L, rows, repeats=1):
     with threadpool_limits(limits=cores):
         for _ in range(repeats):
             t0 = time.perf_counter()
-            gp.lml_grad_mo_lapack(X, Y, w.lengthscales, w.F, w.E)
+            res = gp.lml_grad_mo_lapack(X, Y, w.lengthscales, w.F, w.E)
             best = min(best, time.perf_counter() - t0)
+    if keep is not None:
+        keep.update(res)
     return best, cores
 
 
@@ -161,26 +174,35 @@ def cpu_sobol_seconds(w, L, rows, n_slices):
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm on the host cores.  Under torchrun only rank 0 works."""
+    """--impl reference: the reference algorithm on the host cores, every timed step ONE evaluation of the FULL configuration (no
+    extrapolation: `same config` as the GPU arm).  Under torchrun only rank 0 works.
+
+    Warm-up: W - 1 small evaluations (thread pools, BLAS initialisation) and one full-size one, which is also the probe for the time
+    budget: if K full-size steps would not fit RC_REF_BUDGET_S (default 1500 s, the driver allows 1800 s per arm), the steps fall back to
+    the largest sample that does and the line says so (`same_config: false`, time scaled by (N/N_s)^3)."""
     if int(os.environ.get('RANK', '0')) != 0:
         return
     from romcomma import synthetic
     w = synthetic.config(args.workload, N=args.N)
     N, M = w.X.shape
     L = w.Y.shape[1]
-    rows = min(N, args.cpu_sample_N or 2048)
-    scale = (N / rows) ** 3
-    for _ in range(args.warmup):
-        cpu_eval_seconds(w, L, min(rows, 512))
-    times = [cpu_eval_seconds(w, L, rows)[0] for _ in range(args.steps)]
     cores = os.cpu_count() or 1
+    budget = float(os.environ.get('RC_REF_BUDGET_S', '1500'))
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_eval_seconds(w, L, min(N, 512))
+    rows = min(N, args.cpu_sample_N or N)
+    probe, _ = cpu_eval_seconds(w, L, rows)                       # the last warm-up step: full size
+    if probe * args.steps > budget and args.cpu_sample_N is None:
+        rows = max(128, int(N * (budget / (probe * args.steps)) ** (1.0 / 3.0)) // 128 * 128)
+    scale = (N / rows) ** 3
+    times = [cpu_eval_seconds(w, L, rows)[0] for _ in range(args.steps)]
     per_step = float(np.mean(times)) * scale
     value = 1.0 / per_step
-    sample = (f'{args.steps} evaluations at N={rows} (n={L * rows}) of the same workload through LAPACK dpotrf+dpotri (OpenBLAS, {cores} threads); '
-              f'time scaled by (N/N_sample)^3 = {scale:g} to the full-size unit (the n^3 factorisation+inverse dominates)')
+    sample = (f'{args.steps} evaluations at N={rows} (n={L * rows}) through LAPACK dpotrf+dpotri (OpenBLAS, {cores} threads), {np.mean(times):.1f} s each'
+              + (', full size, no scaling' if rows == N else f'; full-size probe {probe:.1f} s did not fit the {budget:.0f} s budget: time scaled by (N/N_sample)^3 = {scale:g}'))
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'impl': 'reference', 'config': {'workload': workload_description(w, L, M)},
+            'impl': 'reference', 'config': {'workload': workload_description(w, L, M)}, 'same_config': rows == N,
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -235,7 +257,8 @@ def run_b200(args):
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
     info = int(plan.info.cpu()[0])
-    lml = float(plan.out[0, 0].item())
+    gpu_result = plan.unpack(plan.out.cpu().numpy())[0]          # { lml, dF, dE, dls } of this rank's last evaluation
+    lml = float(gpu_result['lml'])
     assert info == 0 and np.isfinite(lml), f'evaluation failed: info={info}, lml={lml}'
 
     # ---- dominant-kernel profile + stage breakdown (outside the timed region) ---------------------------------------------
@@ -403,11 +426,24 @@ def run_b200(args):
         torch.cuda.empty_cache()
 
     # ---- CPU baseline on this box's host cores (rank 0, single-GPU runs only) -------------------------------------------
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rows = min(N, args.cpu_sample_N or N)
-        secs, cores = cpu_eval_seconds(w, L, rows)
+        oracle_result = {}
+        secs, cores = cpu_eval_seconds(w, L, rows, keep=oracle_result)
         scale = (N / rows) ** 3
+        if rows == N:
+            # the same evaluation on both sides: GPU (selected inverse, default trainables) against the oracle port
+            def worst(a, b, atol):
+                a, b = np.asarray(a, float), np.asarray(b, float)
+                return float(np.max(np.abs(a - b) / (atol + 1e-8 * np.abs(b))))
+            parity = {'lml_rel': abs(gpu_result['lml'] - oracle_result['lml']) / abs(oracle_result['lml']),
+                      'lml': [gpu_result['lml'], oracle_result['lml']],
+                      'dF_diag_worst_err_over_tol': worst(np.diag(gpu_result['dF']), np.diag(oracle_result['dF']), 1e-10 * n),
+                      'dE_worst_err_over_tol': worst(gpu_result['dE'], oracle_result['dE'], 1e-10 * n),
+                      'tolerance': f'rtol 1e-8, atol 1e-10 * n = {1e-10 * n:.2e} for the gradients (sums of n^2 signed terms); <= 1 passes',
+                      'against': 'oracle.gp.lml_grad_mo_lapack (numpy/LAPACK float64) on the same inputs and hyper-parameters, full size'}
+            parity['ok'] = bool(parity['lml_rel'] <= 1e-8 and parity['dF_diag_worst_err_over_tol'] <= 1 and parity['dE_worst_err_over_tol'] <= 1)
         cpu = {'value': 1.0 / (secs * scale), 'unit': UNIT, 'cores': cores, 'kind': 'port',
                'sample': f'1 evaluation at N={rows} (n={L * rows}) through LAPACK dpotrf+dpotri (OpenBLAS, {cores} threads), {secs:.1f} s'
                          + (f', scaled by {scale:g}' if scale != 1 else ', full size, no scaling')}
@@ -417,6 +453,16 @@ def run_b200(args):
         cpu['sobol'] = {'value': 1.0 / full, 'unit': 'sweeps/s',
                         'sample': f'{nsl} closed slices x {L * L} output pairs on N={srows} rows, blocked numpy exp+dgemm on {cores} threads, {ssecs:.1f} s; '
                                   f'scaled by (N/N_s)^2 x slices = {(N / srows) ** 2 * len(masks) / nsl:g}'}
+
+    # ---- the sharded workloads, at this world size --------------------------------------------------------------------------
+    sharded = {}
+    if not args.no_sharded:
+        torch.cuda.empty_cache()
+        sharded['sobol_all_subsets'] = leg_sobol_all_subsets(C, distributed, torch, rank, world)
+        torch.cuda.empty_cache()
+        sharded['folds'] = leg_folds(C, distributed, torch, rank, world)
+        sharded['sobol_sweep'] = {'see': 'the "sobol" object of this line (cfg3 25-slice sweep, pair space split over the ranks)', 'scaling': 'strong',
+                                  'n_gpus': world, 'value': 1e3 / sobol_ms, 'unit': 'sweeps/s'}
 
     if rank == 0:
         achieved = prof.tflops
@@ -437,13 +483,98 @@ def run_b200(args):
                                      'register-resident DMMA loop (MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 is ~37-40 TFLOP/s); '
                                      'traffic = ncu dram bytes (read+write) of the launch with the most traffic (top level of trtri, 16.4 ms); see traffic_detail for the other captured launches',
                              'stages': stages},
-                'cpu_baseline': cpu,
+                'cpu_baseline': cpu, 'parity_full_size': parity,
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                         'ms_per_step': 1e3 * e2e_s / args.steps,
                         'path': 'romcomma.gpf.models.MOGPR(data=(pinned host X, Y), ...)._loss_and_grad: H2D of X, Y and hyper-parameters, D2H of LML+gradient'},
-                'gpu_launches': int(launches), 'concurrent_streams': concurrent, 'sobol': sobol, 'sobol_with_error': sobol_err, 'clocks': clocks.summary(), 'lml': lml}
+                'gpu_launches': int(launches), 'concurrent_streams': concurrent, 'sharded': sharded, 'sobol': sobol, 'sobol_with_error': sobol_err, 'clocks': clocks.summary(), 'lml': lml}
         emit(line)
     distributed.barrier()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the workloads that shard (BASELINE.json north_star: folds, per-input-subset Sobol sweep): timed at the current world size
+# ----------------------------------------------------------------------------------------------------------------------
+def leg_sobol_all_subsets(C, distributed, torch, rank, world):
+    """cfg5: closed V for every non-empty subset of the 12 inputs (4095 masks) - blocks of the subset lattice round-robin over the ranks
+    (romcomma.distributed.shard on the mask list), ONE all_gather of the (L, L) results on the device.  Strong scaling."""
+    from romcomma import synthetic
+    w = synthetic.config('cfg5')
+    N, M = w.X.shape
+    L = w.Y.shape[1]
+    dX = C.dev(w.X)
+    KiY = torch.randn(L, N, dtype=torch.float64, device='cuda', generator=torch.Generator('cuda').manual_seed(7)) * 0.1
+    Phi, g0, g0KY = C.sobol_prepare(dX, C.dev(w.lengthscales), C.dev(np.diag(w.F).copy()), KiY, True)
+    masks = list(range(2 ** M))             # mask 0 (the empty subset) rides along so that the lattice splits into equal blocks of 64
+    mine = distributed.shard_blocks(masks, 64, rank, world)
+    out = {}
+
+    def run():
+        V = C.sobol_contract(dX, Phi, g0KY, L, True, mine)
+        out['V'] = distributed.all_gather_rows_tensor(V, len(masks), 64)
+    run()
+    distributed.barrier()
+    torch.cuda.synchronize()
+    reps = 2
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        run()
+    b.record()
+    distributed.barrier()
+    torch.cuda.synchronize()
+    ms = distributed.all_reduce_max(a.elapsed_time(b) / reps)
+    V = out['V'].cpu().numpy()
+    return {'workload': f'cfg5 N={N} M={M} L={L}: closed Sobol V of all {len(masks) - 1} non-empty input subsets', 'scaling': 'strong', 'n_gpus': world,
+            'ms': ms, 'value': 1e3 / ms, 'unit': 'all-subset sweeps/s', 'subsets_per_s': (len(masks) - 1) / (ms * 1e-3), 'subsets': len(masks) - 1,
+            'collective': 'one all_gather_into_tensor of the (L, L) blocks' if world > 1 else 'none',
+            'checksum': float(np.sum(V)), 'V_full_model_00': float(V[-1, 0, 0])}
+
+
+def leg_folds(C, distributed, torch, rank, world, maxiter=50):
+    """cfg2 through the public API, files included: user.run.gpr (fit + test) and user.run.gsa (three kinds) over the 10 folds + the
+    improper fold, fold k on rank k % world, rank 0 collects the csvs.  Wall clock (host + device + files), max over ranks.  Strong."""
+    import random
+    import shutil
+    import tempfile
+    from romcomma.data.storage import Repository
+    from romcomma.user import functions, run, sample
+    # one directory that every rank of THIS launch sees (single node): keyed by the rendezvous port, or the pid of a lone process
+    root = Path(os.environ.get('RC_SCALING_ROOT', tempfile.gettempdir())) / ('rc_bench_folds_' + (os.environ.get('MASTER_PORT', '0') if world > 1 else f'pid{os.getpid()}'))
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+        root.mkdir(parents=True)
+        np.random.seed(2)
+        random.seed(2)
+        fn = sample.Function(root, lambda N, M: sample.DOE.latin_hypercube(N, M, seed=2), functions.SOBOL_G.subVector('sobol_g', ['weak5_2']), N=2048, M=10,
+                             noise_variance=sample.GaussianNoise.Variance(1, 0.04, False, False), overwrite_existing=True)
+        fn.repo.into_K_folds(10)
+    distributed.barrier()
+    repo = Repository(next(p for p in root.iterdir() if p.is_dir()))
+    distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    names = run.gpr('gpr', repo, is_read=False, is_covariant=False, is_isotropic=False, maxiter=maxiter)
+    torch.cuda.synchronize()
+    distributed.barrier()
+    t1 = time.perf_counter()
+    run.gsa('gpr', repo, is_covariant=False, is_isotropic=False)
+    torch.cuda.synchronize()
+    distributed.barrier()
+    t2 = time.perf_counter()
+    fit_s, gsa_s = distributed.all_reduce_max(t1 - t0), distributed.all_reduce_max(t2 - t1)
+    rec = None
+    if rank == 0:
+        import pandas as pd
+        S = pd.read_csv(repo.folder / 'gpr.v.a' / 'gsa' / 'closed' / 'S.csv', index_col=[0, 1])
+        lm = pd.read_csv(repo.folder / 'gpr.v.a' / 'likelihood' / 'log_marginal.csv', index_col=0)
+        rec = {'workload': f'cfg2 Sobol-G N=2048 M=10 L=1: user.run.gpr (L-BFGS-B maxiter={maxiter}, test) + user.run.gsa (3 kinds) over {len(repo.folds)} folds',
+               'scaling': 'strong', 'n_gpus': world, 'fit_test_s': fit_s, 'gsa_s': gsa_s, 'value': len(repo.folds) / (fit_s + gsa_s), 'unit': 'folds/s',
+               'folds': len(repo.folds), 'models': names, 'mean_log_marginal': float(np.mean(lm.values)),
+               'closed_S_last_column_mean': float(S.values[:, -1].mean())}
+        shutil.rmtree(root, ignore_errors=True)
+    distributed.barrier()
+    return rec
 
 
 def emit(line: dict):

@@ -196,8 +196,10 @@ def lml_rbf(X, y, ls, variance, noise):
     return lml_from_K(K, np.asarray(y, float).reshape(-1))[0]
 
 
-def lml_grad_rbf(X, y, ls, variance, noise):
-    """LML and d/d(ls[m]), d/d(variance), d/d(noise) for one gpflow GPR (variant)."""
+def lml_grad_rbf(X, y, ls, variance, noise, gemm_form=False):
+    """LML and d/d(ls[m]), d/d(variance), d/d(noise) for one gpflow GPR (variant).
+    gemm_form: sum_ab WK[a,b] (x_a - x_b)^2 = 2 sum_a x_a (rowsum(WK)[a] x_a - (WK X)[a]) for symmetric WK - the same sum without the
+    (N,N,M) tensor, for N in the thousands (the cfg2 folds)."""
     X, y, ls = np.asarray(X, float), np.asarray(y, float).reshape(-1), np.broadcast_to(np.asarray(ls, float), (np.shape(X)[1],))
     Kf = gram_rbf(X, None, ls, variance)
     K = Kf.copy()
@@ -207,9 +209,11 @@ def lml_grad_rbf(X, y, ls, variance, noise):
     a = Kinv @ y
     W = np.outer(a, a) - Kinv
     WK = W * Kf
-    d2 = (X[:, None, :] - X[None, :, :]) ** 2
-    return {'lml': lml, 'dls': 0.5 * np.einsum('ab,abm->m', WK, d2) / ls ** 3,
-            'dvariance': 0.5 * WK.sum() / variance, 'dnoise': 0.5 * np.trace(W)}
+    if gemm_form:
+        s = 2.0 * np.einsum('am,am->m', X, WK.sum(axis=1)[:, None] * X - WK @ X)
+    else:
+        s = np.einsum('ab,abm->m', WK, (X[:, None, :] - X[None, :, :]) ** 2)
+    return {'lml': lml, 'dls': 0.5 * s / ls ** 3, 'dvariance': 0.5 * WK.sum() / variance, 'dnoise': 0.5 * np.trace(W)}
 
 
 def predict_rbf(X, y, ls, variance, noise, Xs, y_instead_of_f=True):
@@ -271,9 +275,29 @@ def predict_gradient_rbf(X, Y, ls, variance, noise, xs):
 # ----------------------------------------------------------------------------------------------------------------
 # the timed CPU unit: one LML + gradient evaluation through LAPACK (potrf + potri), blocked gram
 # ----------------------------------------------------------------------------------------------------------------
-def lml_grad_mo_lapack(X, Y, ls, F, E, with_lengthscales=False):
-    """Same numbers as lml_grad_mo, organised the way a tuned CPU code would run it (dpotrf + dpotri through OpenBLAS,
-    gram built block by block); used as bench.py's cpu_baseline.  Memory: 2 n^2 doubles."""
+def dls_gemm_form(X, ls, F, W4, U4):
+    """d LML / d ls[l,m] of lml_grad_mo in GEMM form (no (N,N,M) tensor), for sizes where the broadcast form does not fit:
+         G_lj = W_lj * F[l,j] * U_lj,   dls[l,m] = sum_j sum_a X[a,m] ( rowsum(G_lj)[a] X[a,m]/ls[l,m] - (G_lj Xs_j)[a,m] ) / ls[l,m]^2
+    with Xs_j = X / ls[j] - the same sum as 'ab,abm,am->m' over d = Xs_l[a] - Xs_j[b] (gpf/kernels.py:82 differentiated)."""
+    L, N = W4.shape[0], W4.shape[1]
+    Xs = X[None, :, :] / ls[:, None, :]
+    dls = np.zeros_like(ls)
+    for l in range(L):
+        for j in range(L):
+            if F[l, j] == 0.0:
+                continue
+            G = W4[l, :, j, :] * (F[l, j] * U4[l, :, j, :])
+            dls[l] += np.einsum('am,am->m', X, G.sum(axis=1)[:, None] * Xs[l] - G @ Xs[j]) / ls[l] ** 2
+    return dls
+
+
+def lml_grad_mo_lapack(X, Y, ls, F, E, with_lengthscales=False, predict_at=None, want_kinvy=False):
+    """Same numbers as lml_grad_mo (and predict_mo / k_inv_y_mo), organised the way a tuned CPU code would run it: ONE dpotrf shared by
+    the LML, the predictions and K^-1 y, dpotri for the explicit inverse (OpenBLAS), gram built block by block.  bench.py's cpu_baseline
+    (default arguments) and the full-size parity tests (tests/test_gpu_baseline_sizes.py).  Memory: ~4 n^2 doubles.
+
+    predict_at: optional (n*, M) inputs -> out['mean'], out['var_f'] (n*, L) as predict_mo(y_instead_of_f=False).
+    want_kinvy: out['KiY'] (L,1,N) as k_inv_y_mo."""
     X, Y, ls, F, E = (np.asarray(a, float) for a in (X, Y, np.atleast_2d(ls), F, E))
     N, M = X.shape
     L = Y.shape[1]
@@ -294,11 +318,57 @@ def lml_grad_mo_lapack(X, Y, ls, F, E, with_lengthscales=False):
     alpha = sla.solve_triangular(c, y, lower=True)
     lml = float(-0.5 * alpha @ alpha - 0.5 * n * LOG2PI - np.log(np.diag(c)).sum())
     a = sla.solve_triangular(c, alpha, lower=True, trans='T')
+    out = {'lml': lml}
+    if want_kinvy:
+        out['KiY'] = a.reshape(L, 1, N).copy()
+    if predict_at is not None:
+        Xn = np.asarray(predict_at, float)
+        ns = Xn.shape[0]
+        Kmn = gram_mo(X, Xn, ls, F)
+        A = sla.solve_triangular(c, Kmn, lower=True)
+        out['var_f'] = (np.repeat(np.diag(F), ns) - np.einsum('ki,ki->i', A, A)).reshape(L, ns).T
+        out['mean'] = (Kmn.T @ a).reshape(L, ns).T
     Kinv, info = sla.lapack.dpotri(c, lower=1, overwrite_c=1)
     Kinv = np.tril(Kinv) + np.tril(Kinv, -1).T
     W = np.outer(a, a) - Kinv
     W4, U4 = W.reshape(L, N, L, N), U.reshape(L, N, L, N)
-    out = {'lml': lml, 'dF': 0.5 * np.einsum('anbm,anbm->ab', W4, U4), 'dE': 0.5 * np.einsum('anbn->ab', W4)}
+    out |= {'dF': 0.5 * np.einsum('anbm,anbm->ab', W4, U4), 'dE': 0.5 * np.einsum('anbn->ab', W4)}
     if with_lengthscales:
-        out['dls'] = lml_grad_mo(X, Y, ls, F, E)['dls']
+        out['dls'] = dls_gemm_form(X, ls, F, W4, U4)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# variant fit: what gf.optimizers.Scipy().minimize(gp.training_loss, gp.trainable_variables, options=...) does per output
+# (gpr/models.py:359-361) - L-BFGS-B on the unconstrained variables in tf.Module order (kernel.lengthscales, kernel.variance,
+# likelihood.variance), softplus transforms, noise floor 1e-6 (gpflow.likelihoods.Gaussian)
+# ----------------------------------------------------------------------------------------------------------------
+def fit_rbf(X, y, ls0, variance0, noise0, train_lengthscales=True, noise_floor=1e-6, **options):
+    """-> dict(ls (M,), variance, noise, lml, nit, nfev).  ls0 of size 1 = isotropic kernel (one shared lengthscale)."""
+    import scipy.optimize
+    X, y = np.asarray(X, float), np.asarray(y, float).reshape(-1)
+    M = X.shape[1]
+    ls0 = np.atleast_1d(np.asarray(ls0, float))
+    k = ls0.size
+
+    def unpack(u):
+        ls = softplus(u[:k]) if train_lengthscales else ls0
+        off = k if train_lengthscales else 0
+        return ls, float(softplus(u[off])), float(softplus(u[off + 1]) + noise_floor)
+
+    def fun(u):
+        ls, var, noise = unpack(u)
+        r = lml_grad_rbf(X, y, np.broadcast_to(ls, (M,)), var, noise, gemm_form=X.shape[0] > 600)
+        g = []
+        if train_lengthscales:
+            dls = r['dls'] if k == M else np.array([r['dls'].sum()])
+            g.append(dls * sigmoid(u[:k]))
+        off = k if train_lengthscales else 0
+        g.append([r['dvariance'] * sigmoid(u[off])])
+        g.append([r['dnoise'] * sigmoid(u[off + 1])])
+        return -r['lml'], -np.concatenate([np.reshape(v, -1) for v in g])
+
+    u0 = np.concatenate(([softplus_inverse(ls0)] if train_lengthscales else []) + [[softplus_inverse(variance0)], [softplus_inverse(noise0 - noise_floor)]])
+    res = scipy.optimize.minimize(fun, np.asarray(u0, float).reshape(-1), jac=True, method='L-BFGS-B', options=options)
+    ls, var, noise = unpack(res.x)
+    return {'ls': np.broadcast_to(ls, (M,)).copy() if k == M else ls, 'variance': var, 'noise': noise, 'lml': -float(res.fun), 'nit': res.nit, 'nfev': res.nfev}

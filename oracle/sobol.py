@@ -34,24 +34,34 @@ def H_block(X, p, q, m0, m1, rows=slice(None)):
     return np.exp(e) / np.sqrt(np.prod(psi))
 
 
-def V_bilinear(X, Phi, c_left, c_right, m0, m1, block=1024):
-    """sum_{L',J'} c_left[l,L',:]^T H c_right[j,J',:]  ->  (L,L).  Phi (L,L',M); c (L,L',N)."""
+def V_bilinear(X, Phi, c_left, c_right, m0, m1, block=1024, workers=1):
+    """sum_{L',J'} c_left[l,L',:]^T H c_right[j,J',:]  ->  (L,L).  Phi (L,L',M); c (L,L',N).
+    workers > 1: the (pair, row block) terms are evaluated by a thread pool (numpy releases the GIL in exp and matmul) and added in
+    the same fixed order as the serial loop - the full-size parity tests need seconds, not minutes."""
     L, Lp, _ = Phi.shape
     N = X.shape[0]
+    tasks = [(l, a, j, b, r0) for l, a, j, b in itertools.product(range(L), range(Lp), range(L), range(Lp)) for r0 in range(0, N, block)]
+
+    def term(t):
+        l, a, j, b, r0 = t
+        rows = slice(r0, min(N, r0 + block))
+        return c_left[l, a, rows] @ (H_block(X, Phi[l, a], Phi[j, b], m0, m1, rows) @ c_right[j, b])
+    if workers > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            terms = list(ex.map(term, tasks))
+    else:
+        terms = [term(t) for t in tasks]
     V = np.zeros((L, L))
-    for l, a, j, b in itertools.product(range(L), range(Lp), range(L), range(Lp)):
-        acc = 0.0
-        for r0 in range(0, N, block):
-            rows = slice(r0, min(N, r0 + block))
-            acc += c_left[l, a, rows] @ (H_block(X, Phi[l, a], Phi[j, b], m0, m1, rows) @ c_right[j, b])
-        V[l, j] += acc
+    for (l, a, j, b, r0), v in zip(tasks, terms):
+        V[l, j] += v
     return V
 
 
 class ClosedSobol:
     """gsa/calibrators.py:31-143.  Public attributes as in the reference: V (dict 0,1,2), S, G, Phi, g0, g0KY, Lambda2."""
 
-    def __init__(self, X, Lambda, F, K_inv_Y, is_F_diagonal=True, block=1024, centre=True):
+    def __init__(self, X, Lambda, F, K_inv_Y, is_F_diagonal=True, block=1024, centre=True, workers=1):
         X = np.asarray(X, float)
         self.N, self.M = X.shape
         self.X = X
@@ -60,7 +70,7 @@ class ClosedSobol:
         self.L = K_inv_Y.shape[0]
         L, M = self.L, self.M
         self.is_F_diagonal = is_F_diagonal
-        self.block = block
+        self.block, self.workers = block, workers
         # calibrators.py:134-138
         if is_F_diagonal:
             F = np.atleast_2d(F)
@@ -89,7 +99,7 @@ class ClosedSobol:
         self.S = self.V[0] / self.V[2]
 
     def _V(self, m0, m1):
-        return V_bilinear(self.X, self.Phi, self.g0KY, self.g0KY, m0, m1, self.block)
+        return V_bilinear(self.X, self.Phi, self.g0KY, self.g0KY, m0, m1, self.block, self.workers)
 
     def marginalize(self, m: Tuple[int, int]) -> Dict[str, np.ndarray]:
         """calibrators.py:49-58"""

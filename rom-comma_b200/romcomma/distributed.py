@@ -76,6 +76,32 @@ def all_gather_rows(local: np.ndarray, total_rows: int) -> np.ndarray:
     return out
 
 
+def shard_blocks(items: Sequence[Any], block: int, r: int | None = None, w: int | None = None) -> List[Any]:
+    """ Round-robin shard of consecutive blocks of ``block`` items (block b goes to rank b % w): what keeps the subsets that share their
+    high mask bits - and so their partial products in the all-subsets Sobol kernel - on one rank."""
+    r = rank() if r is None else r
+    w = world_size() if w is None else w
+    return [item for i, item in enumerate(items) if (i // block) % w == r]
+
+
+def all_gather_rows_tensor(local: torch.Tensor, total_rows: int, block: int = 1) -> torch.Tensor:
+    """ ``all_gather_rows`` for a tensor that already lives where the collective runs (CUDA for NCCL): no host hop, one
+    all_gather_into_tensor on the current stream, rows put back in order on the device.  Rank r holds, in order, the rows of the
+    blocks b (of ``block`` consecutive rows) with b % world == r (``shard`` for block = 1, ``shard_blocks`` otherwise)."""
+    w = world_size()
+    if w == 1:
+        return local
+    nblocks = (total_rows + block - 1) // block
+    per = (nblocks + w - 1) // w * block
+    mine = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    mine[:local.shape[0]] = local
+    gathered = torch.empty((w * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, mine)
+    i = torch.arange(total_rows, device=local.device)
+    b = i // block
+    return gathered[(b % w) * per + (b // w) * block + i % block]
+
+
 def all_reduce_max(value: float) -> float:
     if not is_initialized():
         return float(value)

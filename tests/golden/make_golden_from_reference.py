@@ -47,7 +47,7 @@ def load_reference() -> SimpleNamespace:
     import torch
     from romcomma.data.storage import Fold, Repository
     from romcomma.gpr.models import MOGP
-    from romcomma.gsa.calibrators import ClosedSobol
+    from romcomma.gsa.calibrators import ClosedSobol, ClosedSobolWithError
     from romcomma.gsa.models import GSA, Sobol
 
     for mod in (pkg.gpf.models, pkg.gsa.calibrators, pkg.gpr.models):
@@ -74,8 +74,8 @@ def load_reference() -> SimpleNamespace:
         grads = torch.autograd.grad(loss, [p.unconstrained_variable for p in params])
         return float(loss.detach()), [g.detach().as_subclass(torch.Tensor).numpy() for g in grads]
 
-    def sobol_results(gp, kind, is_error_calculated):
-        gsa = Sobol(gp, kind, m=-1, is_error_calculated=is_error_calculated)
+    def sobol_results(gp, kind, is_error_calculated, **kwargs):
+        gsa = Sobol(gp, kind, m=-1, is_error_calculated=is_error_calculated, **kwargs)
         captured = {}
         original = gsa._compose_and_save
 
@@ -87,7 +87,7 @@ def load_reference() -> SimpleNamespace:
         gsa.calibrate()
         return captured
 
-    return SimpleNamespace(Repository=Repository, Fold=Fold, MOGP=MOGP, ClosedSobol=ClosedSobol, GSA=GSA, to_np=to_np,
+    return SimpleNamespace(Repository=Repository, Fold=Fold, MOGP=MOGP, ClosedSobol=ClosedSobol, ClosedSobolWithError=ClosedSobolWithError, GSA=GSA, to_np=to_np,
                            variable_order=variable_order, loss_and_grads=loss_and_grads, sobol_results=sobol_results,
                            slice_arg=lambda s: tf.constant(list(s), dtype=tf.int32))
 

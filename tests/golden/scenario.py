@@ -189,6 +189,16 @@ def run(api: SimpleNamespace, name: str, root: Path) -> Dict[str, np.ndarray]:
         for kind in api.GSA.ALL_KINDS:
             for key, value in api.sobol_results(gp, kind, is_error_calculated=True).items():
                 out[f'gsa_err.{kind.name.lower()}.{key}'] = value
+        # is_T_partial=False - what installation_test.py, csv_script.py and benchmark_script.py run (the MIXED rank equation, W[Mm], Q and the
+        # full-model T; gsa/calibrators.py:169-170,342-346,358-372,388-402; T post-processed by gsa/models.py:211-213)
+        for kind in api.GSA.ALL_KINDS:
+            for key, value in api.sobol_results(gp, kind, is_error_calculated=True, is_T_partial=False).items():
+                out[f'gsa_err_full.{kind.name.lower()}.{key}'] = value
+        cal = api.ClosedSobolWithError(gp, is_T_partial=False)
+        out['sobol_err_full.W_DIAGONAL'], out['sobol_err_full.W_MIXED'] = to_np(cal.W.DIAGONAL), to_np(cal.W.MIXED)
+        out['sobol_err_full.Q'], out['sobol_err_full.T'] = to_np(cal.Q), to_np(cal.T)
+        r = cal.marginalize(api.slice_arg((1, M)))
+        out['sobol_err_full.marginalize.1.M.W'], out['sobol_err_full.marginalize.1.M.T'] = to_np(r['W']), to_np(r['T'])
 
     # ---- a6 through the optimizer: a short L-BFGS-B run from the given start (maxiter small; compared loosely) ------------------------
     meta = gp.calibrate(method='L-BFGS-B', maxiter=6)

@@ -286,9 +286,10 @@ def test_sobol_golden(C, golden):
 
 
 # ---- properties at benchmark scale (oracle too slow / too large there) ---------------------------------------------------
-@pytest.mark.parametrize('cfg', ['cfg3', 'cfg5'])
+@pytest.mark.parametrize('cfg', ['cfg3', 'cfg5', 'cfg4'])
 def test_full_size_properties(C, cfg):
-    """Full benchmark sizes (cfg3: n = 16384, cfg5: n = 24576): K K^-1 v = v, L L^T v = K v, the LML and gradient identities from the
+    """Full benchmark sizes (cfg3: n = 16384, cfg5: n = 24576, cfg4: n = 32768 = 256 blocks, the only size at which the factorisation
+    takes its 8-block-column groups): K K^-1 v = v, L L^T v = K v, the LML and gradient identities from the
     explicit inverse, bitwise run-to-run reproducibility."""
     from romcomma import synthetic
     w = synthetic.config(cfg)
@@ -323,7 +324,7 @@ def test_full_size_properties(C, cfg):
         assert_close(a[0, 1 + L * L + l * L + l].item(), ref, rtol=1e-8, atol=1e-6, what=f'dE[{l},{l}]')
 
 
-@pytest.mark.parametrize('cfg', ['cfg3', 'cfg5'])
+@pytest.mark.parametrize('cfg', ['cfg3', 'cfg5', 'cfg4'])
 def test_full_size_sobol_properties(C, cfg):
     """Size-independent properties of the Sobol contractions at full benchmark size: V symmetric in the outputs; the sweep form and the
     general-subset kernel agree (a non-structured subset equals a prefix after permuting the inputs); the row-tile parts that the ranks

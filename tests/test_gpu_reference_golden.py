@@ -29,7 +29,7 @@ def api():
     _capi.lib()
     from romcomma.data.storage import Fold, Repository
     from romcomma.gpr.models import MOGP
-    from romcomma.gsa.calibrators import ClosedSobol
+    from romcomma.gsa.calibrators import ClosedSobol, ClosedSobolWithError
     from romcomma.gsa.models import GSA, Sobol
     scenario = _scenario()
 
@@ -44,12 +44,12 @@ def api():
     def loss_and_grads(model, params):
         return model._loss_and_grad(params)
 
-    def sobol_results(gp, kind, is_error_calculated):
-        gsa = Sobol(gp, kind, m=-1, is_error_calculated=is_error_calculated)
+    def sobol_results(gp, kind, is_error_calculated, **kwargs):
+        gsa = Sobol(gp, kind, m=-1, is_error_calculated=is_error_calculated, **kwargs)
         gsa.calibrate()
         return {key: np.asarray(value, dtype=np.float64) for key, value in gsa.results.items()}
 
-    return SimpleNamespace(Repository=Repository, Fold=Fold, MOGP=MOGP, ClosedSobol=ClosedSobol, GSA=GSA, to_np=to_np,
+    return SimpleNamespace(Repository=Repository, Fold=Fold, MOGP=MOGP, ClosedSobol=ClosedSobol, ClosedSobolWithError=ClosedSobolWithError, GSA=GSA, to_np=to_np,
                            variable_order=variable_order, loss_and_grads=loss_and_grads, sobol_results=sobol_results,
                            slice_arg=tuple, with_error=True, scenario=scenario)
 

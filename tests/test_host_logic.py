@@ -210,6 +210,18 @@ WORKER = textwrap.dedent('''
     part = torch.from_numpy(tiles[[t for t in range(6) if t % w == r]].sum(axis=0))
     distributed.all_reduce_sum_tensor(part)
     assert np.array_equal(part.numpy(), tiles.sum(axis=0)), part
+    # the all-subsets sweep: blocks of consecutive masks round-robin over the ranks, one all_gather on the tensor's own device
+    masks = list(range(20))
+    mine = distributed.shard_blocks(masks, 4)
+    assert mine == [m for m in masks if (m // 4) % w == r]
+    local_t = torch.tensor([[float(m), -float(m)] for m in mine], dtype=torch.float64)
+    full_t = distributed.all_gather_rows_tensor(local_t, len(masks), 4)
+    assert full_t.shape == (20, 2) and np.array_equal(full_t[:, 0].numpy(), np.arange(20.0)), full_t
+    ragged = distributed.shard_blocks(list(range(11)), 4)                     # a short last block
+    rag_t = distributed.all_gather_rows_tensor(torch.tensor([[float(m)] for m in ragged], dtype=torch.float64), 11, 4)
+    assert np.array_equal(rag_t[:, 0].numpy(), np.arange(11.0)), rag_t
+    one = distributed.all_gather_rows_tensor(torch.tensor([[float(m)] for m in distributed.shard(list(range(7)))], dtype=torch.float64), 7)
+    assert np.array_equal(one[:, 0].numpy(), np.arange(7.0)), one
     distributed.barrier()
     print('rank', r, 'ok')
 ''')
