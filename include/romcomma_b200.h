@@ -149,18 +149,29 @@ int rc_sobol_contract(const double* X, int N, int M, const double* Phi, const do
 int rc_sobol_contract_part(const double* X, int N, int M, const double* Phi, const double* c, int L, int is_F_diagonal,
                            const unsigned long long* masks_host, int nslices, int part, int nparts, void* parts, double* V, rc_stream_t stream);
 
-/* rc_sobol_error: ClosedSobolWithError.marginalize / _calibrate (romcomma/gsa/calibrators.py:146-402) for a list of marginal subsets,
- * in the only configuration the reference supports: diagonal F (:380-381) and is_T_partial (META, :149-157).  Evaluates the
- * _psi_factor (:290-309), _UpsilonGaussian (:244-257), _OmegaGaussian (:214-242) and _mu_phi_mu (:259-288) chains as fused pairwise
- * kernels, runs the triangular solve of :307 as one TRSM over all (subset, l, i) right-hand sides, and returns
+/* rc_sobol_error: ClosedSobolWithError.marginalize / _calibrate (romcomma/gsa/calibrators.py:146-402) for a list of marginal subsets, with the
+ * diagonal F the reference requires (:380-381), in the is_T_partial form (META, :149-157): evaluates the _psi_factor (:290-309),
+ * _UpsilonGaussian (:244-257), _OmegaGaussian (:214-242) and _mu_phi_mu (:259-288) chains under the DIAGONAL rank equations (:167-168) as fused
+ * pairwise kernels, runs the triangular solve of :307 as one TRSM over all (subset, l, i) right-hand sides, and returns
  *   V[s][l][i]  (ClosedSobol._V, a by-product)   and   W[s][l][i] = (mu_phi_mu - mu_psi_mu) + transpose  (:324-333).
- * T = sqrt(|W| / V[2]^2) (:335-346) is L x L host work.  Phi, g0, g0KY: outputs of rc_sobol_prepare (diagonal F, P = L); Lam (L,M); F (L).
+ * Phi, g0, g0KY: outputs of rc_sobol_prepare (diagonal F, P = L); Lam (L,M); F (L).
  * Achol / potrf_work: a factor from rc_potrf - chol_batch = 1 for a covariant GP (n_pad = rc_padded(L*N), K_cho of
- * romcomma/gpr/models.py:427-432) or chol_batch = L for a variant GP (one rc_padded(N) factor per output, :433-439). */
+ * romcomma/gpr/models.py:427-432) or chol_batch = L for a variant GP (one rc_padded(N) factor per output, :433-439).
+ *
+ * rc_sobol_error_mixed: the same plus the MIXED rank equation (:169-170) that is_T_partial = False needs - the default of all three reference
+ * scripts (installation_test.py:51, csv_script.py:48, benchmark_script.py:144):
+ *   WMm[s][l][i] = (mu_phi_mu_MIXED - mu_psi_mu_MIXED) + transpose  (:358-372), the covariance between the FULL model and the marginal s
+ * (one more family of pairwise kernels whose Upsilon factor comes from the full model, and the dots psi^FULL_ii . psi^s_li of the solved columns).
+ * From W, WMm and V the host forms Q (:400-401) and T = sqrt(|W - 2 V WMm / V[1] + V^2 Q| / V[2]^2) (:335-346): L x L work. */
 size_t rc_sobol_error_bufsize(int N, int M, int L, int nslices, int n_pad, int chol_batch);
 int rc_sobol_error(const double* X, int N, int M, const double* Lam, const double* F, const double* Phi, const double* g0, const double* g0KY,
                    int L, const double* Achol, int n_pad, long ld, long strideA, int chol_batch, const void* potrf_work,
                    const unsigned long long* masks_host, int nslices, void* work, size_t work_bytes, double* V, double* W, rc_stream_t stream);
+size_t rc_sobol_error_mixed_bufsize(int N, int M, int L, int nslices, int n_pad, int chol_batch);
+int rc_sobol_error_mixed(const double* X, int N, int M, const double* Lam, const double* F, const double* Phi, const double* g0, const double* g0KY,
+                         int L, const double* Achol, int n_pad, long ld, long strideA, int chol_batch, const void* potrf_work,
+                         const unsigned long long* masks_host, int nslices, void* work, size_t work_bytes, double* V, double* W, double* WMm,
+                         rc_stream_t stream);
 
 #ifdef __cplusplus
 }

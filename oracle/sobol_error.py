@@ -100,10 +100,13 @@ class ClosedSobolWithError(ClosedSobol):
             self.W = self._W(0, self.M)
         else:
             self.psi_full = [self._psi(i, i, 0, self.M)[1] for i in range(self.L)]
-            self.W_DIAGONAL, self.W_MIXED = self._W(0, self.M), self._W_mixed(0, self.M)
+            self.W_DIAGONAL = self._W(0, self.M)
+            self.W_MIXED, mixed_scale = self._W_mixed(0, self.M, True)
             self.W = (self.W_DIAGONAL, self.W_MIXED)
             q = np.diag(self.W_MIXED) / (4.0 * self.V[1] * self.V[1])
             self.Q = q[None, :] + q[:, None] + 2.0 * np.diag(q)
+            qs = np.diag(mixed_scale) / (4.0 * self.V[1] * self.V[1])
+            self.Q_scale = qs[None, :] + qs[:, None] + 2.0 * np.diag(qs)
             self.T = self._T(self.W_DIAGONAL, self.W_MIXED, self.V[0])
 
     def _psi(self, l, i, m0, m1):
@@ -132,14 +135,19 @@ class ClosedSobolWithError(ClosedSobol):
             acc += self.g0KY[l, 0, rows] @ (pair_kernel(Xs, A, B, C, logk, rows) @ self.g0KY[l, 0])
         return self.pre_factor[i] * acc
 
-    def _W(self, m0, m1):
+    def _W(self, m0, m1, with_scale=False):
+        """W[mm]; with_scale also |mu_phi_mu| + |mu_psi_mu| (+ transpose): W is the difference of two nearly equal terms, and the rounding
+        error of any float64 evaluation scales with THEM (times eps cond(K), through K^-1 y), not with |W| - tests on fitted (ill-conditioned)
+        models state their tolerance against this scale."""
         L = self.L
-        W = np.zeros((L, L))
+        W, S = np.zeros((L, L)), np.zeros((L, L))
         for l in range(L):
             for i in range(L):
                 _, psi = self._psi(l, i, m0, m1)
-                W[l, i] = (self._phi(l, i, m0, m1) - psi @ psi) * (2.0 if l == i else 1.0)
-        return W + W.T
+                phi, twice = self._phi(l, i, m0, m1), (2.0 if l == i else 1.0)
+                W[l, i] = (phi - psi @ psi) * twice
+                S[l, i] = (abs(phi) + psi @ psi) * twice
+        return (W + W.T, S + S.T) if with_scale else W + W.T
 
     def _phi_mixed(self, l, i, m0, m1):
         s = slice(m0, m1)
@@ -152,14 +160,16 @@ class ClosedSobolWithError(ClosedSobol):
             acc += left[rows] @ (pair_kernel(Xs, A, B, C, logk, rows) @ self.g0KY[l, 0])
         return self.pre_factor[i] * acc
 
-    def _W_mixed(self, m0, m1):
+    def _W_mixed(self, m0, m1, with_scale=False):
         L = self.L
-        W = np.zeros((L, L))
+        W, S = np.zeros((L, L)), np.zeros((L, L))
         for l in range(L):
             for i in range(L):
                 _, psi = self._psi(l, i, m0, m1)
-                W[l, i] = (self._phi_mixed(l, i, m0, m1) - self.psi_full[i] @ psi) * (2.0 if l == i else 1.0)
-        return W + W.T
+                phi, dot, twice = self._phi_mixed(l, i, m0, m1), self.psi_full[i] @ psi, (2.0 if l == i else 1.0)
+                W[l, i] = (phi - dot) * twice
+                S[l, i] = (abs(phi) + abs(dot)) * twice
+        return (W + W.T, S + S.T) if with_scale else W + W.T
 
     def _T(self, Wmm, WMm=None, Vm=None):
         """calibrators.py:335-346."""
@@ -168,11 +178,14 @@ class ClosedSobolWithError(ClosedSobol):
 
     def marginalize(self, m: Tuple[int, int]) -> Dict[str, np.ndarray]:
         result = super().marginalize(m)
-        W = self._W(int(m[0]), int(m[1]))
+        W, W_scale = self._W(int(m[0]), int(m[1]), True)
         if self.is_T_partial:
-            return result | {'W': W, 'T': self._T(W)}
-        WMm = self._W_mixed(int(m[0]), int(m[1]))
-        return result | {'W': W, 'WMm': WMm, 'T': self._T(W, WMm, result['V'])}
+            return result | {'W': W, 'T': self._T(W), 'W_scale': W_scale}
+        WMm, WMm_scale = self._W_mixed(int(m[0]), int(m[1]), True)
+        # Q_m = W[mm] - 2 V W[Mm]/V1 + V^2 Q, and the size of what cancels in it (for tolerances)
+        V = result['V']
+        Q_scale = W_scale + 2.0 * np.abs(V) * WMm_scale / self.V[1] + V * V * self.Q_scale
+        return result | {'W': W, 'WMm': WMm, 'T': self._T(W, WMm, V), 'W_scale': W_scale, 'WMm_scale': WMm_scale, 'Q_scale': Q_scale}
 
 
 def sobol_kind_with_error(cal: ClosedSobolWithError, kind: int, m: int = -1) -> Dict[str, np.ndarray]:

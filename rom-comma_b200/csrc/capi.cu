@@ -257,7 +257,8 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
   RC_REQUIRE(X && Y && ls && F && E && work && out && info, -2, "rc_lml_grad: null pointer");
   RC_REQUIRE(N > 0 && M > 0 && L > 0 && batch > 0, -2, "rc_lml_grad: non-positive size");
   RC_REQUIRE(!Kunit || batch == 1, -2, "rc_lml_grad: a cached unit gram is only supported for batch == 1");
-  const bool overlap = !(flags & RC_NO_OVERLAP) && batch == 1 && (flags & ~RC_NO_OVERLAP) != RC_GRAD_NONE;
+  const bool one_stream = (flags & RC_NO_OVERLAP) != 0;       // keep every kernel on `stream`: no look-ahead, no overlapped inverse
+  const bool overlap = !one_stream && batch == 1 && (flags & ~RC_NO_OVERLAP) != RC_GRAD_NONE;
   flags &= ~RC_NO_OVERLAP;
   const LmlLayout lay = lml_layout(N, M, L, batch, flags);
   RC_REQUIRE(work_bytes >= lay.total, -2, "rc_lml_grad: workspace too small (%zu < %zu)", work_bytes, lay.total);
@@ -289,8 +290,8 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
   }
   // 2. factor, log-determinant (gradient of one matrix: Z = L^-1 is produced as well, its independent part inside the factorisation)
   if (overlap) {
-    if ((rc = potrf_trtri_lower(A, n_pad, n_pad, pw.dinv, pw.logdet_parts, info, Kinv, (size_t)mat, overlap_panels(), st))) return rc;
-  } else if ((rc = potrf_lower(A, n_pad, n_pad, mat, batch, pw.dinv, pw.logdet_parts, info, st))) {
+    if ((rc = potrf_trtri_lower(A, n_pad, n_pad, pw.dinv, pw.logdet_parts, info, Kinv, (size_t)mat, overlap_panels(), st, true))) return rc;
+  } else if ((rc = potrf_lower(A, n_pad, n_pad, mat, batch, pw.dinv, pw.logdet_parts, info, st, !one_stream))) {
     return rc;
   }
   if ((rc = sum_parts(pw.logdet_parts, n_pad / TILE, batch, logdet, 1.0, st))) return rc;
@@ -362,20 +363,41 @@ int rc_sobol_contract_part(const double* X, int N, int M, const double* Phi, con
 }
 
 size_t rc_sobol_error_bufsize(int N, int M, int L, int nslices, int n_pad, int chol_batch) {
-  return align256(sobol_error_workspace_bytes(N, M, L, nslices, n_pad, chol_batch));
+  return align256(sobol_error_workspace_bytes(N, M, L, nslices, n_pad, chol_batch, 0));
+}
+size_t rc_sobol_error_mixed_bufsize(int N, int M, int L, int nslices, int n_pad, int chol_batch) {
+  return align256(sobol_error_workspace_bytes(N, M, L, nslices, n_pad, chol_batch, 1));
+}
+
+static int sobol_error_entry(const char* who, const double* X, int N, int M, const double* Lam, const double* F, const double* Phi, const double* g0,
+                             const double* g0KY, int L, const double* Achol, int n_pad, long ld, long strideA, int chol_batch, const void* potrf_work,
+                             const unsigned long long* masks_host, int nslices, void* work, size_t work_bytes, double* V, double* W, double* WMm,
+                             rc_stream_t stream) {
+  RC_REQUIRE(X && Lam && F && Phi && g0 && g0KY && Achol && potrf_work && masks_host && work && V && W && nslices > 0, -2,
+             "%s: null pointer or empty subset list", who);
+  RC_REQUIRE(N > 0 && L > 0, -2, "%s: non-positive size", who);
+  RC_REQUIRE(chol_batch == 1 || chol_batch == L, -2, "%s: chol_batch must be 1 (covariant) or L (variant)", who);
+  RC_REQUIRE(n_pad > 0 && n_pad % TILE == 0, -2, "%s: n_pad must be a positive multiple of 128", who);
+  RC_REQUIRE(work_bytes >= sobol_error_workspace_bytes(N, M, L, nslices, n_pad, chol_batch, WMm != nullptr), -2, "%s: workspace too small", who);
+  PotrfWork w = split_potrf_work(const_cast<void*>(potrf_work), n_pad, chol_batch);
+  return sobol_error(X, N, M, Lam, F, Phi, g0, g0KY, L, Achol, n_pad, ld, strideA, chol_batch, w.dinv, masks_host, nslices, work, V, W, WMm,
+                     (cudaStream_t)stream);
 }
 
 int rc_sobol_error(const double* X, int N, int M, const double* Lam, const double* F, const double* Phi, const double* g0, const double* g0KY,
                    int L, const double* Achol, int n_pad, long ld, long strideA, int chol_batch, const void* potrf_work,
                    const unsigned long long* masks_host, int nslices, void* work, size_t work_bytes, double* V, double* W, rc_stream_t stream) {
-  RC_REQUIRE(X && Lam && F && Phi && g0 && g0KY && Achol && potrf_work && masks_host && work && V && W && nslices > 0, -2,
-             "rc_sobol_error: null pointer or empty subset list");
-  RC_REQUIRE(chol_batch == 1 || chol_batch == L, -2, "rc_sobol_error: chol_batch must be 1 (covariant) or L (variant)");
-  RC_REQUIRE(n_pad % TILE == 0, -2, "rc_sobol_error: n_pad must be a multiple of 128");
-  RC_REQUIRE(work_bytes >= sobol_error_workspace_bytes(N, M, L, nslices, n_pad, chol_batch), -2, "rc_sobol_error: workspace too small");
-  PotrfWork w = split_potrf_work(const_cast<void*>(potrf_work), n_pad, chol_batch);
-  return sobol_error(X, N, M, Lam, F, Phi, g0, g0KY, L, Achol, n_pad, ld, strideA, chol_batch, w.dinv, masks_host, nslices, work, V, W,
-                     (cudaStream_t)stream);
+  return sobol_error_entry("rc_sobol_error", X, N, M, Lam, F, Phi, g0, g0KY, L, Achol, n_pad, ld, strideA, chol_batch, potrf_work, masks_host, nslices,
+                           work, work_bytes, V, W, nullptr, stream);
+}
+
+int rc_sobol_error_mixed(const double* X, int N, int M, const double* Lam, const double* F, const double* Phi, const double* g0, const double* g0KY,
+                         int L, const double* Achol, int n_pad, long ld, long strideA, int chol_batch, const void* potrf_work,
+                         const unsigned long long* masks_host, int nslices, void* work, size_t work_bytes, double* V, double* W, double* WMm,
+                         rc_stream_t stream) {
+  RC_REQUIRE(WMm, -2, "rc_sobol_error_mixed: null pointer");
+  return sobol_error_entry("rc_sobol_error_mixed", X, N, M, Lam, F, Phi, g0, g0KY, L, Achol, n_pad, ld, strideA, chol_batch, potrf_work, masks_host,
+                           nslices, work, work_bytes, V, W, WMm, stream);
 }
 
 }  // extern "C"

@@ -10,6 +10,8 @@
 #include "gemm_dmma_ws.cuh"
 
 #include <algorithm>
+#include <vector>
+#include <utility>
 #include <cstdlib>
 #include <atomic>
 #include <mutex>
@@ -255,22 +257,14 @@ diag_potrf_inv_kernel(double* __restrict__ A, long ld, long strideA, double* __r
 
 static int launch_diag_factor(double* A, long ld, long strideA, double* dinv, long strideD, int blk, double* logdet_parts, int nblk, int* info,
                               int batch, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(diag_potrf_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
-    configured = true;
-  }
+  RC_ENSURE_SMEM(diag_potrf_inv_kernel<1>, DB_SMEM);
   RC_CUDA_OK(launch_pdl(diag_potrf_inv_kernel<1>, dim3(batch), dim3(DB_THREADS), DB_SMEM, st, A, ld, strideA, dinv, strideD, blk, logdet_parts, nblk, info));
   RC_LAUNCH_OK();
   return 0;
 }
 
 static int launch_diag_invert_all(double* A, long ld, long strideA, double* dinv, long strideD, int nblk, int batch, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(diag_potrf_inv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM));
-    configured = true;
-  }
+  RC_ENSURE_SMEM(diag_potrf_inv_kernel<2>, DB_SMEM);
   diag_potrf_inv_kernel<2><<<dim3(nblk, batch), DB_THREADS, DB_SMEM, st>>>(A, ld, strideA, dinv, strideD, 0, nullptr, nblk, nullptr);
   RC_LAUNCH_OK();
   return 0;
@@ -379,11 +373,7 @@ panel_trsm_kernel(double* __restrict__ A, long ld, long strideA, int blk) {
 static int launch_panel_trsm(double* A, int n, long ld, long strideA, int blk, int batch, cudaStream_t st) {
   const int tiles = n / DB - blk - 1;
   if (tiles <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
-    configured = true;
-  }
+  RC_ENSURE_SMEM(panel_trsm_kernel, PT_SMEM);
   RC_CUDA_OK(launch_pdl(panel_trsm_kernel, dim3(tiles, batch), dim3(256), PT_SMEM, st, A, ld, strideA, blk));
   RC_LAUNCH_OK();
   return 0;
@@ -461,9 +451,6 @@ static int potrf_core(double* A, int n, long ld, long strideA, int batch, double
   return 0;
 }
 
-int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st) {
-  return potrf_core(A, n, ld, strideA, batch, dinv, logdet_parts, info, st, [](int) { return 0; }, true);
-}
 
 // ----------------------------------------------------------------------------------------------------------------
 // Vector triangular solves (one right-hand side per matrix), one launch per block step, no atomics.
@@ -713,6 +700,145 @@ OverlapCtx* overlap_ctx(int device, cudaStream_t user) {
 }
 }  // namespace
 
+// ----------------------------------------------------------------------------------------------------------------
+// potrf with LOOK-AHEAD (one matrix).
+//
+// Right-looking order leaves the GPU idle along the chain  diagonal factor (1 CTA, ~41 us) -> panel solve (~25 us) -> column update
+// of the next block column: 128 x 66 us + 87 tall-skinny updates = 12 of the 52.7 ms of a 16384 factorisation (round-1 launch list).
+// With groups g of block columns C_g (the same widths potrf_core uses) and P_g = L[:, C_g]:
+//     F_g        factor group g (diagonal factors, panel solves, column updates inside the group)        needs every update of C_g
+//     U_g        A[c_g+1:, C_g+1] -= P_g P_g[C_g+1]^T      the NEXT group's columns only (column-limited lower tile list)
+//     B_g        A[c_g+2:, c_g+2:] -= P_g P_g^T            the rest of the trailing update, lower tiles
+// the CHAIN  F_0 U_0 F_1 U_1 F_2 ...  runs on an internal high-priority stream and the BULK  B_0 B_1 ...  on an internal low-priority one as
+// YIELDING launches (each CTA retires after RC_POTRF_YIELD tiles, default 2): B_g only needs F_g, and U_g+1 only needs B_g (both write
+// C_g+2, always in this order), so while B_g runs the chain of group g+1 is scheduled onto every SM a bulk CTA gives back - the block
+// scheduler serves the higher-priority stream first.  The chain's work still costs SM time, but no SM waits for it any more.
+// Same tiles, same K ranges, same order of updates per tile as potrf_core: the factor is bit-for-bit the same.  Capturable (fork/join by
+// events).  The last groups (fewer than LA_TAIL blocks left, where a bulk update is a fraction of a wave) run the plain sequence on the
+// chain stream.  RC_POTRF_LOOKAHEAD=0 switches it off.
+// ----------------------------------------------------------------------------------------------------------------
+static bool lookahead_env() {
+  static const int v = env_int("RC_POTRF_LOOKAHEAD", 1);
+  return v != 0;
+}
+
+static int potrf_lookahead(double* A, int n, long ld, double* dinv, double* logdet_parts, int* info, cudaStream_t st, OverlapCtx* cx) {
+  const int nblk = n / DB;
+  const long strideD = (long)nblk * DB * DB;
+  static const int LA_TAIL = env_int("RC_POTRF_LA_TAIL", 16), YIELD = std::max(1, env_int("RC_POTRF_YIELD", 2));
+  int start[DB * 4], G = 0;                      // group boundaries, as potrf_core chooses them
+  for (int b0 = 0, w = 0; b0 < nblk; b0 += w) {
+    w = std::min(potrf_group(nblk - b0), nblk - b0);
+    start[G++] = b0;
+    RC_REQUIRE(G < DB * 4 - 1, -2, "potrf_lookahead: too many block-column groups");
+  }
+  start[G] = nblk;
+  cudaStream_t hi = cx->hi, lo = cx->side;
+  RC_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int), st));
+  RC_CUDA_OK(cudaEventRecord(cx->fork0, st));
+  RC_CUDA_OK(cudaStreamWaitEvent(hi, cx->fork0, 0));
+  int rc;
+  auto factor_group = [&](int g) -> int {
+    const int b0 = start[g], w = start[g + 1] - b0;
+    for (int j = 0; j < w; ++j) {
+      const long r0 = (long)(b0 + j) * DB;
+      if (j > 0) {
+        GemmArgs u{};
+        u.A = A + r0 * ld + (long)b0 * DB; u.lda = ld;
+        u.B = u.A; u.ldb = ld;
+        u.C = A + r0 * ld + r0; u.ldc = ld;
+        u.M = n - (int)r0; u.N = DB; u.K = j * DB; u.alpha = -1.0; u.beta = 1.0; u.kmode = K_FULL;
+        if ((rc = launch_gemm_ws<false, false>(u, 1, hi))) return rc;
+      }
+      if ((rc = launch_diag_factor(A, ld, 0, dinv, strideD, b0 + j, logdet_parts, nblk, info, 1, hi))) return rc;
+      if ((rc = launch_panel_trsm(A, n, ld, 0, b0 + j, 1, hi))) return rc;
+    }
+    return 0;
+  };
+  // lower tiles of the square that starts at block `from`, rank = group g; col_tiles > 0: only its first col_tiles tile columns
+  auto update = [&](int g, int from, int col_tiles, cudaStream_t stream, int yield) -> int {
+    const long r0 = (long)from * DB;
+    if (r0 >= n) return 0;
+    GemmArgs u{};
+    u.A = A + r0 * ld + (long)start[g] * DB; u.lda = ld;
+    u.B = u.A; u.ldb = ld;
+    u.C = A + r0 * ld + r0; u.ldc = ld;
+    u.M = u.N = n - (int)r0; u.K = (start[g + 1] - start[g]) * DB; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1; u.kmode = K_FULL;
+    u.col_tiles = col_tiles;
+    return launch_gemm_ws<false, false>(u, 1, stream, yield);
+  };
+  cudaEvent_t evF[2] = {cx->fork[0], cx->fork[1]}, evB[2] = {cx->fork[2], cx->fork[3]};
+  bool bulk_pending = false;                     // a bulk update whose event the chain has not waited for yet
+  int last_bulk = -1;
+  // RC_POTRF_TIMELINE=1 (diagnostic, host-blocking): timestamps after every F_g / U_g on the chain and every B_g on the bulk stream
+  static const bool timeline = env_int("RC_POTRF_TIMELINE", 0) != 0;
+  std::vector<cudaEvent_t> tl_ev;
+  std::vector<std::pair<char, int>> tl_tag;
+  auto mark = [&](char what, int g, cudaStream_t stream) {
+    if (!timeline) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    tl_ev.push_back(e);
+    tl_tag.push_back({what, g});
+  };
+  mark('0', 0, hi);
+  for (int g = 0; g < G; ++g) {
+    if ((rc = factor_group(g))) return rc;
+    mark('F', g, hi);
+    if (g + 1 == G) break;
+    const bool split = g + 2 < G && nblk - start[g + 2] >= LA_TAIL;
+    if (split) {
+      RC_CUDA_OK(cudaEventRecord(evF[g & 1], hi));
+      RC_CUDA_OK(cudaStreamWaitEvent(lo, evF[g & 1], 0));
+    }
+    if (bulk_pending) {                          // B_(g-1) wrote the columns U_g / the plain update touches: keep the order
+      RC_CUDA_OK(cudaStreamWaitEvent(hi, evB[last_bulk & 1], 0));
+      bulk_pending = false;
+    }
+    if (split) {
+      if ((rc = update(g, start[g + 2], 0, lo, YIELD))) return rc;
+      RC_CUDA_OK(cudaEventRecord(evB[g & 1], lo));
+      mark('B', g, lo);
+      bulk_pending = true;
+      last_bulk = g;
+      if ((rc = update(g, start[g + 1], start[g + 2] - start[g + 1], hi, 0))) return rc;
+    } else if ((rc = update(g, start[g + 1], 0, hi, 0))) {
+      return rc;
+    }
+    mark('U', g, hi);
+  }
+  if ((rc = launch_diag_invert_all(A, ld, 0, dinv, strideD, nblk, 1, hi))) return rc;
+  RC_CUDA_OK(cudaEventRecord(cx->join_hi, hi));
+  RC_CUDA_OK(cudaStreamWaitEvent(st, cx->join_hi, 0));
+  if (last_bulk >= 0) {                          // every bulk update has been waited for by the chain already; join the stream itself for capture
+    RC_CUDA_OK(cudaEventRecord(cx->join, lo));
+    RC_CUDA_OK(cudaStreamWaitEvent(st, cx->join, 0));
+  }
+  if (timeline) {
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "potrf_lookahead timeline n=%d groups=%d (ms since start):", n, G);
+    for (size_t i = 1; i < tl_ev.size(); ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, tl_ev[0], tl_ev[i]);
+      fprintf(stderr, " %c%d=%.3f", tl_tag[i].first, tl_tag[i].second, t);
+    }
+    fprintf(stderr, "\n");
+    for (cudaEvent_t e : tl_ev) cudaEventDestroy(e);
+  }
+  return 0;
+}
+
+int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st, bool lookahead) {
+  static const int LA_MIN = env_int("RC_POTRF_LA_MIN_BLOCKS", 32);
+  if (lookahead && batch == 1 && lookahead_env() && n % DB == 0 && n / DB >= LA_MIN && ld >= n && ld % 2 == 0) {
+    int dev = 0;
+    RC_CUDA_OK(cudaGetDevice(&dev));
+    if (OverlapCtx* cx = overlap_ctx(dev, st)) return potrf_lookahead(A, n, ld, dinv, logdet_parts, info, st, cx);
+  }
+  return potrf_core(A, n, ld, strideA, batch, dinv, logdet_parts, info, st, [](int) { return 0; }, true);
+}
+
 size_t potrf_trtri_tmp_doubles(int n, int panels) {
   const long nblk = n / DB;
   if (panels < 2 || nblk < 2 * panels) return (size_t)n * n / 4;
@@ -724,7 +850,7 @@ size_t potrf_trtri_tmp_doubles(int n, int panels) {
 }
 
 int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_parts, int* info, double* tmp, size_t tmp_doubles, int panels,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool lookahead) {
   RC_REQUIRE(n > 0 && n % DB == 0, -2, "potrf_trtri_lower: n=%d must be a positive multiple of 128", n);
   const int nblk = n / DB;
   int rc;
@@ -735,7 +861,7 @@ int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_pa
   OverlapCtx* cx = (aligned && panels >= 2 && nblk >= 2 * panels && potrf_trtri_tmp_doubles(n, panels) <= tmp_doubles) ? overlap_ctx(dev, st) : nullptr;
   if (!cx) {   // small problem (nothing to hide) or no scratch: plain sequence
     RC_REQUIRE(tmp_doubles >= (size_t)n * n / 4, -2, "potrf_trtri_lower: scratch too small");
-    if ((rc = potrf_lower(A, n, ld, 0, 1, dinv, logdet_parts, info, st))) return rc;
+    if ((rc = potrf_lower(A, n, ld, 0, 1, dinv, logdet_parts, info, st, lookahead))) return rc;
     return trtri_lower(A, n, ld, 0, 1, dinv, tmp, 0, st);
   }
   int wblk = (nblk + panels - 1) / panels;
@@ -986,9 +1112,11 @@ int debug_tile_order(int M, int N, int K, int lower_only, int kmode, int sel_blo
   RC_REQUIRE(kmode >= K_FULL && kmode <= K_LE_N1, -2, "rc_debug_tile_order: kmode %d", kmode);
   RC_REQUIRE(!lower_only || M == N, -2, "rc_debug_tile_order: lower_only needs M == N");
   GemmArgs p{};
-  p.M = M; p.N = N; p.K = K; p.lower_only = lower_only; p.kmode = kmode; p.sel_block = sel_block;
-  const long tm = M / G_BM, tn = N / G_BN;
-  const long tiles = lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  p.M = M; p.N = N; p.K = K; p.lower_only = lower_only; p.kmode = kmode;
+  p.sel_block = sel_block > 0 ? sel_block : 0;
+  p.col_tiles = sel_block < 0 ? -sel_block : 0;      // negative sel_block: the column-limited lower list of the look-ahead panel update
+  RC_REQUIRE(p.col_tiles == 0 || (lower_only && kmode == K_FULL), -2, "rc_debug_tile_order: a column limit needs lower_only and kmode 0");
+  const long tiles = gemm_tile_count(p);
   for (long t = 0; t < tiles; ++t) {
     const GemmTile T = lower_only ? gemm_decode_tile<1>(p, t, tiles) : gemm_decode_tile<0>(p, t, tiles);
     out[4 * t + 0] = T.m0; out[4 * t + 1] = T.n0; out[4 * t + 2] = T.kb; out[4 * t + 3] = T.nk;

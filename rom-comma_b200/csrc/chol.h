@@ -10,7 +10,10 @@ size_t potrf_workspace_bytes(int n, int batch);
 // In-place lower Cholesky of `batch` n x n matrices (only the lower triangle is read; the strict upper triangle of
 // diagonal 128-tiles is clobbered). dinv: batch*(n/128) inverse diagonal blocks; logdet_parts: batch*(n/128) partial
 // sums of log L_ii; info[z] = 0 or the 1-based index of the first non-positive pivot.
-int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st);
+// lookahead: a single large matrix may be factorised with the serial diagonal/panel chain on an internal high-priority stream underneath
+// the trailing updates (chol.cu: potrf_lookahead; same bits); false keeps every kernel on `st` (per-kernel timing).
+int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st,
+                bool lookahead = true);
 
 // x = L^-1 w (transpose=0) or L^-T w (transpose=1); w is destroyed. Vectors of batch z start at z*strideV.
 int trsv_lower(const double* A, int n, long ld, long strideA, int batch, const double* dinv, double* w, double* x, long strideV, int transpose,
@@ -28,7 +31,7 @@ int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double
 // tmp: potrf_trtri_tmp_doubles(n, panels) doubles; panels < 2 (or a small n) selects the plain sequence.
 size_t potrf_trtri_tmp_doubles(int n, int panels);
 int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_parts, int* info, double* tmp, size_t tmp_doubles, int panels,
-                      cudaStream_t st);
+                      cudaStream_t st, bool lookahead = true);
 
 // Kinv(lower 128-tiles) = Z^T Z; sel_block > 0 restricts it to the tiles that intersect the diagonal blocks of that size.
 int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double* Kinv, long ldk, long strideK, int sel_block, cudaStream_t st);

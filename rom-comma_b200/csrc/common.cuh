@@ -138,4 +138,34 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember per (call site = kernel instantiation, device)
+// that it has been raised to `bytes`, so that a process which works on several devices configures each of them (round-1 advice: a
+// process-wide flag left every device but the first at the 48 KB default).  Idempotent, so the benign race between two threads is harmless.
+constexpr int RC_MAX_DEVICES = 64;
+#define RC_ENSURE_SMEM(kernel, bytes)                                                                              \
+  do {                                                                                                             \
+    static int _rc_have[rc::RC_MAX_DEVICES] = {};                                                                  \
+    int _rc_dev = 0;                                                                                               \
+    RC_CUDA_OK(cudaGetDevice(&_rc_dev));                                                                           \
+    const bool _rc_tracked = _rc_dev >= 0 && _rc_dev < rc::RC_MAX_DEVICES;                                         \
+    if (!_rc_tracked || _rc_have[_rc_dev] < (int)(bytes)) {                                                        \
+      RC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));         \
+      if (_rc_tracked) _rc_have[_rc_dev] = (int)(bytes);                                                           \
+    }                                                                                                              \
+  } while (0)
+
+// Number of SMs of the CURRENT device (cached per device): the size of every persistent grid.
+inline int device_sm_count() {
+  static int sms[RC_MAX_DEVICES] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev < 0 || dev >= RC_MAX_DEVICES) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }
+  if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
+}
+
 }  // namespace rc

@@ -32,7 +32,16 @@ struct GemmArgs {
   int lower_only;   // 1: only tiles with tile_m >= tile_n (requires M == N)
   int kmode;
   int sel_block;    // > 0 (with lower_only): compute only tiles that intersect the diagonal blocks of size sel_block ("selected" LAUUM)
+  int col_tiles;    // > 0 (with lower_only, K_FULL): only the first col_tiles tile columns of the lower triangle (look-ahead panel update)
 };
+
+// number of 128 x 128 tiles of one matrix in the list the arguments describe
+inline long gemm_tile_count(const GemmArgs& a) {
+  const long tm = a.M / 128, tn = a.N / 128;
+  if (!a.lower_only) return tm * tn;
+  if (a.col_tiles > 0 && a.col_tiles < tm) return (long)a.col_tiles * (a.col_tiles + 1) / 2 + (tm - a.col_tiles) * a.col_tiles;
+  return tm * (tm + 1) / 2;
+}
 
 constexpr int G_BM = 128, G_BN = 128, G_BK = 16, G_STAGES = 4, G_PAD = 4, G_THREADS = 256;
 
@@ -77,7 +86,21 @@ __host__ __device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p,
   const int z = (int)(tile / tiles_per_matrix);
   const long idx = tile - (long)z * tiles_per_matrix;
   int tm, tn;
-  if (lower && p.kmode != K_FULL) {
+  if (lower && p.col_tiles > 0 && p.col_tiles < p.M / G_BM) {
+    // the first col_tiles tile columns of the lower triangle, row-major: the triangle on the diagonal first, then full rows of col_tiles tiles
+    // (a strip of tiles shares one row panel of A and the same col_tiles panels of B, which stay in L2)
+    const int w = p.col_tiles, tri = w * (w + 1) / 2, i32 = (int)idx;
+    if (i32 < tri) {
+      tm = (int)((sqrt(8.0 * (double)i32 + 1.0) - 1.0) * 0.5);
+      while ((tm + 1) * (tm + 2) / 2 <= i32) ++tm;
+      while (tm * (tm + 1) / 2 > i32) --tm;
+      tn = i32 - tm * (tm + 1) / 2;
+    } else {
+      const int r = i32 - tri;
+      tm = w + r / w;
+      tn = r - (tm - w) * w;
+    }
+  } else if (lower && p.kmode != K_FULL) {
     // row-major over the lower triangle: tile row tm has the longest K of what is left (K_GE_M0: LAUUM, where the raster below costs 2 % -
     // the selected tile lists leave it too few tiles per super-tile - and saves no traffic)
     tm = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
@@ -270,7 +293,7 @@ inline double gemm_tile_flops(const GemmArgs& p, int batch) {
   const long tm_n = p.M / G_BM, tn_n = p.N / G_BN;
   double ksum = 0.0;
   for (long tm = 0; tm < tm_n; ++tm)
-    for (long tn = 0; tn < (p.lower_only ? tm + 1 : tn_n); ++tn) {
+    for (long tn = 0; tn < (p.lower_only ? (p.col_tiles > 0 && p.col_tiles < tm + 1 ? p.col_tiles : tm + 1) : tn_n); ++tn) {
       const long m0 = tm * G_BM, n0 = tn * G_BN;
       long kb = 0, ke = p.K;
       if (p.kmode == K_GE_N0) kb = n0;
@@ -286,19 +309,11 @@ inline double gemm_tile_flops(const GemmArgs& p, int batch) {
 template <bool TA, bool TB>
 inline int launch_gemm(const GemmArgs& a, int batch, cudaStream_t stream) {
   using S = GemmSmem<TA, TB>;
-  static bool configured = false;   // per instantiation; benign race (idempotent attribute set)
-  static int num_sms = 0;
-  if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
-    int dev = 0;
-    RC_CUDA_OK(cudaGetDevice(&dev));
-    RC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  RC_ENSURE_SMEM((gemm_dmma_kernel<TA, TB>), S::BYTES);
+  const int num_sms = device_sm_count();
   if (a.M <= 0 || a.N <= 0 || batch <= 0) return 0;
   RC_REQUIRE(a.M % G_BM == 0 && a.N % G_BN == 0 && a.K % G_BK == 0, -2, "gemm_dmma: M,N must be multiples of 128 and K of 16 (got %d,%d,%d)", a.M, a.N, a.K);
-  const long tm = a.M / G_BM, tn = a.N / G_BN;
-  const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  const long tiles = gemm_tile_count(a);
   const long total = tiles * batch;
   const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);   // persistent: one CTA per SM (160 KB smem each)
   const bool prof = profile_enabled();

@@ -339,21 +339,16 @@ int* gemm_sched_slot(int device);   // defined in chol.cu
 template <bool TA, bool TB, bool LOWER>
 inline int launch_gemm_ws_impl(const GemmArgs& a, int batch, cudaStream_t stream, int tiles_per_cta) {
   using S = GemmWsSmem<TA, TB>;
-  static bool configured = false;
-  static int num_sms = 0;
   int dev = 0;
   RC_CUDA_OK(cudaGetDevice(&dev));
-  if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_ws_kernel<TA, TB, LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
-    RC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  RC_ENSURE_SMEM((gemm_dmma_ws_kernel<TA, TB, LOWER>), S::BYTES);
+  const int num_sms = device_sm_count();
   if (a.M <= 0 || a.N <= 0 || batch <= 0) return 0;
   RC_REQUIRE(a.M % G_BM == 0 && a.N % G_BN == 0 && a.K % (G_BK * W_SUB) == 0, -2, "gemm_dmma_ws: M,N must be multiples of 128 and K of 32 (got %d,%d,%d)", a.M,
              a.N, a.K);
   RC_REQUIRE(a.lda % 2 == 0 && a.ldb % 2 == 0 && a.ldc % 2 == 0, -2, "gemm_dmma_ws: leading dimensions must be even (16-byte rows)");
-  const long tm = a.M / G_BM, tn = a.N / G_BN;
-  const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  RC_REQUIRE(a.col_tiles == 0 || (a.lower_only && a.kmode == K_FULL && a.sel_block == 0), -2, "gemm_dmma_ws: col_tiles needs a plain lower-triangular list");
+  const long tiles = gemm_tile_count(a);
   const long total = tiles * batch;
   const unsigned grid = tiles_per_cta > 0 ? (unsigned)((total + tiles_per_cta - 1) / tiles_per_cta) : (unsigned)(total < num_sms ? total : num_sms);
   alignas(64) CUtensorMap mapA, mapB;

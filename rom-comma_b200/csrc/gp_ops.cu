@@ -145,11 +145,7 @@ int gram(const GramArgs& a_in, int batch, cudaStream_t st) {
   const long tiles = (a.lower_only ? tr * (tr + 1) / 2 : tr * tc) * batch;
   a.strip = tiles >= 3000 ? GSTRIP : 1;
   const size_t smem = (size_t)(1 + a.strip) * GT * a.M * sizeof(double) + (size_t)(2 + 2 * a.strip) * GT * sizeof(int);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 48 * 1024) RC_ENSURE_SMEM(gram_kernel, smem);
   gram_kernel<<<dim3((unsigned)((tc + a.strip - 1) / a.strip), (unsigned)tr, batch), GTHREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
   return 0;

@@ -368,11 +368,7 @@ __global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs 
 template <int MAXM, int RU>
 static int launch_sweep(const SobolPairArgs& a, int npairs, cudaStream_t st) {
   const size_t smem = (size_t)(4 * a.M + 4 * a.M * ST + 2 * ST + 8 * 3 * MAXM + (size_t)a.M * 2 * RU * STHREADS) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(sobol_sweep_kernel<MAXM, RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
-  }
+  RC_ENSURE_SMEM((sobol_sweep_kernel<MAXM, RU>), 160 * 1024);
   RC_REQUIRE(smem <= 160 * 1024, -2, "sobol_contract: shared memory %zu too large", smem);
   sobol_sweep_kernel<MAXM, RU><<<dim3(a.T * a.T, npairs), STHREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
@@ -458,11 +454,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
   RC_REQUIRE(M >= 1 && M <= 64, -2, "sobol_contract: M=%d out of range [1,64]", M);
   RC_REQUIRE(nparts >= 1 && part >= 0 && part < nparts, -2, "sobol_contract: part %d of %d", part, nparts);
   const int P = L * Lp;
-  static bool configured = false;
-  if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(sobol_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  RC_ENSURE_SMEM(sobol_pair_kernel, 200 * 1024);
   const int T = (N + ST - 1) / ST;
   const int npairs = P * (P + 1) / 2;
   // Structured subsets (single inputs, prefixes, suffixes, full, empty: everything gsa.models.GSA asks for) go through the sweep form:

@@ -22,12 +22,13 @@ int sobol_sweep_index(unsigned long long mask, int M);
 int sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int Lp, const unsigned long long* masks, int nslices,
                    double* parts, double* V, int part, int nparts, cudaStream_t st);
 
-// ClosedSobolWithError (diagonal F, is_T_partial): V[s][l][i] and W[s][l][i] = (mu_phi_mu - mu_psi_mu) + transpose for every subset.
+// ClosedSobolWithError (diagonal F): V[s][l][i] and W[s][l][i] = (mu_phi_mu - mu_psi_mu) + transpose for every subset; with WMm != NULL
+// (is_T_partial = False) also the MIXED covariances WMm[s][l][i] between the full model and the marginal s.
 // Phi (L,M), g0 (L,N), g0KY (L,N) come from sobol_prepare; Achol/dinv from potrf_lower with chol_batch = 1 (covariant GP, n_pad >= L*N)
 // or L (variant GP, one N x N factor per output).
-size_t sobol_error_workspace_bytes(int N, int M, int L, int nslices, int n_pad, int chol_batch);
+size_t sobol_error_workspace_bytes(int N, int M, int L, int nslices, int n_pad, int chol_batch, int mixed);
 int sobol_error(const double* X, int N, int M, const double* Lam, const double* F, const double* Phi, const double* g0, const double* g0KY, int L,
                 const double* Achol, int n_pad, long ld, long strideA, int chol_batch, const double* dinv, const unsigned long long* masks,
-                int nslices, void* work, double* V, double* W, cudaStream_t st);
+                int nslices, void* work, double* V, double* W, double* WMm, cudaStream_t st);
 
 }  // namespace rc

@@ -1,5 +1,6 @@
-// Standard errors of the closed Sobol indices (FP64, sm_100a): ClosedSobolWithError.marginalize / _calibrate with diagonal F and
-// is_T_partial (romcomma/gsa/calibrators.py:146-402).
+// Standard errors of the closed Sobol indices (FP64, sm_100a): ClosedSobolWithError.marginalize / _calibrate with diagonal F
+// (romcomma/gsa/calibrators.py:146-402), for is_T_partial (W[mm] only) and for the non-partial form the reference's scripts run
+// (`mixed`: the MIXED rank equation W[Mm] as well, :169-170,358-372).
 //
 // With the size-one axes of a diagonal F removed, the reference's rank-8 Gaussian chains collapse to two families of pairwise
 // kernels over the (N, n) sample pairs, both of the form
@@ -8,6 +9,9 @@
 // job (kind 1; l,i):  Q_li - the Omega/Upsilon/G Gaussian ratio of _mu_phi_mu (:259-288)               w_li[n] = sum_N c_l[N] Q_li[N,n]
 // Then  V[l,i] = c_i . u_li,   psi_li = L_chol^-1 (g0_i * u_li)  (block i of an LN-vector for a covariant GP),
 //       W_raw[l,i] = ( pre_i * c_l . w_li  -  |psi_li|^2 ) * (1 + [l == i]),   W = W_raw + W_raw^T.
+// job (kind 2; i,l), `mixed` only:  Q'_il - the same ratio with the first output equated to i (MIXED) and its Upsilon factor, which the
+//       reference takes from the FULL model, folded into the left weights ct_i[N] = c_i[N] wx_i[N];   w'_il[n] = sum_N ct_i[N] Q'_il[N,n]
+//       WMm_raw[l,i] = ( pre_i * c_l . w'_il  -  psi^FULL_ii . psi_li ) * (1 + [l == i]),   W[Mm] = WMm_raw + WMm_raw^T.
 // The coefficient algebra is derived in oracle/sobol_error.py (checked against vectors produced by running the reference's file).
 // One fused mat-vec kernel evaluates every (job, subset) pair; nothing of size N^2 is ever stored.  Partial sums are combined in
 // a fixed order: bitwise reproducible, no atomics.
@@ -25,8 +29,8 @@ constexpr int ETHREADS = 256;   // 16 x 16 threads, 4 x 4 pairs each per 64 x 64
 // ---- per-job coefficients ------------------------------------------------------------------------------------------
 // coef layout: [4][J][M] = { cA, cB, cC, cK }, J = 2*L*L, job = kind*L*L + l*L + i.  pre[i] = F_i sqrt(prod_m Lam2/(Lam2+2)).
 __global__ void sobol_error_coeff_kernel(const double* __restrict__ Phi, const double* __restrict__ Lam, const double* __restrict__ F, int L, int M,
-                                         double* __restrict__ coef, double* __restrict__ pre) {
-  const int J = 2 * L * L;
+                                         int kinds, double* __restrict__ coef, double* __restrict__ pre) {
+  const int J = kinds * L * L;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < J * M; e += gridDim.x * blockDim.x) {
     const int job = e / M, m = e - job * M;
     const int kind = job / (L * L), li = job - kind * L * L, l = li / L, i = li - l * L;
@@ -35,7 +39,7 @@ __global__ void sobol_error_coeff_kernel(const double* __restrict__ Phi, const d
     if (kind == 0) {
       const double psi = 1.0 - pl * pi, g = pl * pi / psi;
       A = g * pl; B = g * pi; C = g; K = -0.5 * log(psi);
-    } else {
+    } else if (kind == 1) {
       const double lam2 = Lam[i * M + m] * Lam[i * M + m];
       const double ups = 1.0 / (lam2 + 2.0);
       const double gl = 1.0 - pl, gi = 1.0 - pi;
@@ -44,6 +48,16 @@ __global__ void sobol_error_coeff_kernel(const double* __restrict__ Phi, const d
       const double v = gl * pl + pl * pl * gi + pi * pi * pl * pl * r * gl;
       const double b = ups * pl * pl / (1.0 - ups * pl);
       A = a * a / v + b; B = pl * pl / v - pl; C = a * pl / v; K = -0.5 * log(v * (1.0 - ups * pl) / pl);
+    } else {
+      // MIXED: the job's first index is the x-side output (the reference's i, with l equated to it), the second the y-side output
+      const double px = pl, py = pi;
+      const double lam2 = Lam[l * M + m] * Lam[l * M + m];
+      const double ups = 1.0 / (lam2 + 2.0);
+      const double gx = 1.0 - px, gy = 1.0 - py;
+      const double r = (1.0 - ups) / (1.0 - px * ups);
+      const double a = px * px * py * r;
+      const double v = gy * py + py * py * gx + px * px * py * py * r * gx;
+      A = a * a / v; B = py * py / v - py; C = a * py / v; K = -0.5 * log(v / py);
     }
     coef[(0L * J + job) * M + m] = -0.5 * A;
     coef[(1L * J + job) * M + m] = -0.5 * B;
@@ -61,11 +75,28 @@ __global__ void sobol_error_coeff_kernel(const double* __restrict__ Phi, const d
   }
 }
 
+// MIXED left weights: ct[i][N] = c[i][N] * prod_{ALL m} (1 - ups phi)^-1/2 exp(-1/2 b x^2), b = ups phi^2 / (1 - ups phi): the Upsilon Gaussian of
+// the FULL model (calibrators.py:369 pairs the marginal Omega Gaussian with self.UpsilonGaussians.MIXED) as a per-sample factor.
+__global__ void sobol_error_mixed_weight_kernel(const double* __restrict__ X, int N, int M, const double* __restrict__ Phi, const double* __restrict__ Lam,
+                                                const double* __restrict__ c, double* __restrict__ ct) {
+  const int i = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double e = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const double lam2 = Lam[i * M + m] * Lam[i * M + m], ups = 1.0 / (lam2 + 2.0), ph = Phi[i * M + m];
+    const double q = 1.0 - ups * ph, x = X[(long)n * M + m];
+    e -= 0.5 * (ups * ph * ph / q * x * x + log(q));
+  }
+  ct[(long)i * N + n] = c[(long)i * N + n] * exp(e);
+}
+
 // ---- fused pairwise kernel + mat-vec -----------------------------------------------------------------------------------
 struct ErrMatvecArgs {
   const double* X; int N, M;
   const double* coef;     // [4][J][M]
   const double* c;        // [L][N] left weights g0KY; job (kind,l,i) uses row l
+  const double* c2;       // [L][N] left weights of the kind-2 (MIXED) jobs
   int L, J, T, RC, RCH;   // T column tiles of 64, RC row chunks of RCH rows
   int ns;
   double* parts;          // [J][RC][ns][T*64]
@@ -107,7 +138,7 @@ __global__ void __launch_bounds__(ETHREADS) sobol_error_matvec_kernel(ErrMatvecA
   }
   for (int r = tid; r < RCH; r += ETHREADS) {
     const int gi = row0 + r;
-    wl[r] = gi < p.N ? p.c[(long)l * p.N + gi] : 0.0;      // rows beyond N carry zero weight
+    wl[r] = gi < p.N ? (job >= 2 * p.L * p.L ? p.c2 : p.c)[(long)l * p.N + gi] : 0.0;      // rows beyond N carry zero weight
   }
   for (int e = tid; e < EC * M; e += ETHREADS) {
     const int r = e / M, m = e - r * M;
@@ -225,7 +256,7 @@ __global__ void __launch_bounds__(ETHREADS, 2) sobol_error_sweep_kernel(ErrMatve
   }
   for (int r = tid; r < RCH; r += ETHREADS) {
     const int gi = row0 + r;
-    wl[r] = gi < p.N ? p.c[(long)l * p.N + gi] : 0.0;
+    wl[r] = gi < p.N ? (job >= 2 * p.L * p.L ? p.c2 : p.c)[(long)l * p.N + gi] : 0.0;
   }
   for (int e = tid; e < SW_EC * M; e += ETHREADS) {
     const int r = e / M, m = e - r * M;
@@ -311,11 +342,7 @@ __global__ void __launch_bounds__(ETHREADS, 2) sobol_error_sweep_kernel(ErrMatve
 template <int MAXM>
 static int launch_error_sweep(const ErrMatvecArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(4 * a.M + (long)a.M * a.RCH + a.RCH + 2 * a.M * SW_EC + 16 * SW_EC + (long)a.M * 4 * ETHREADS) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(sobol_error_sweep_kernel<MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  RC_ENSURE_SMEM(sobol_error_sweep_kernel<MAXM>, 200 * 1024);
   RC_REQUIRE(smem <= 200 * 1024, -2, "sobol_error: shared memory %zu too large", smem);
   sobol_error_sweep_kernel<MAXM><<<dim3(a.T * a.RC, a.J), ETHREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
@@ -328,72 +355,93 @@ struct ErrMap {
   int dest[32];
 };
 
-// ---- gather: V, the Omega bilinear forms R, and the right-hand sides g0_i * u_li of the triangular solve -----------------------------
+// ---- gather: V, the Omega bilinear forms R (and Rm, MIXED), and the right-hand sides g0_i * u_li of the triangular solve --------------
 // grid (ns, L*L).  Covariant GP (chol_batch == 1): B is n_pad x ncol, column (s*L + l)*L + i, rows i*N + n.
 // Variant GP (chol_batch == L): problem i has its own N_pad x ncol block at B + i*strideB, column s*L + l, rows n.
 __global__ void sobol_error_gather_kernel(const double* __restrict__ parts, int L, int N, int RC, int nv, long ncols_u, const double* __restrict__ c,
                                           const double* __restrict__ g0, const double* __restrict__ pre, int chol_batch, double* __restrict__ B,
-                                          long ldb, long strideB, ErrMap map, double* __restrict__ V, double* __restrict__ R) {
+                                          long ldb, long strideB, ErrMap map, double* __restrict__ V, double* __restrict__ R, double* __restrict__ Rm) {
   __shared__ double red[32];
   const int s = blockIdx.x, li = blockIdx.y, l = li / L, i = li - l * L;
   const double* pu = parts + (((long)(0 * L * L + li) * RC) * nv + map.col[s]) * ncols_u;     // nv values per (job, row chunk)
   const double* pw = parts + (((long)(1 * L * L + li) * RC) * nv + map.col[s]) * ncols_u;
+  const double* pm = Rm ? parts + (((long)(2 * L * L + i * L + l) * RC) * nv + map.col[s]) * ncols_u : nullptr;   // MIXED job (x side i, y side l)
   const long rc_stride = (long)nv * ncols_u;
-  double vacc = 0.0, racc = 0.0;
+  double vacc = 0.0, racc = 0.0, macc = 0.0;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    double u = 0.0, w = 0.0;
+    double u = 0.0, w = 0.0, wm = 0.0;
     for (int r = 0; r < RC; ++r) {
       u += pu[r * rc_stride + n];
       w += pw[r * rc_stride + n];
+      if (pm) wm += pm[r * rc_stride + n];
     }
     vacc = fma(c[(long)i * N + n], u, vacc);
     racc = fma(c[(long)l * N + n], w, racc);
+    macc = fma(c[(long)l * N + n], wm, macc);
     const double f = g0[(long)i * N + n] * u;
     if (chol_batch == 1) B[((long)i * N + n) * ldb + ((long)s * L + l) * L + i] = f;
     else B[(long)i * strideB + (long)n * ldb + (long)s * L + l] = f;
   }
   vacc = block_sum(vacc, red);
   racc = block_sum(racc, red);
+  macc = block_sum(macc, red);
   if (threadIdx.x == 0) {
-    V[((long)map.dest[s] * L + l) * L + i] = vacc;
+    if (V) V[((long)map.dest[s] * L + l) * L + i] = vacc;
     R[((long)s * L + l) * L + i] = pre[i] * racc;
+    if (Rm) Rm[((long)s * L + l) * L + i] = pre[i] * macc;
   }
 }
 
-// partial[chunk][col] = sum over 128 rows of B[row][col]^2
-__global__ void colnorm_partial_kernel(const double* __restrict__ B, long ldb, long strideB, int ncols, double* __restrict__ partial, long stride_partial) {
+// partial[chunk][col] = sum over 128 rows of B[row][col]^2;  with psifull (MIXED) also partial2[chunk][col] = sum B[row][col] * psifull[i(col)][row],
+// i(col) = col % L for a covariant GP (column (s,l,i)), the problem index z for a variant one.
+__global__ void colnorm_partial_kernel(const double* __restrict__ B, long ldb, long strideB, int ncols, double* __restrict__ partial, long stride_partial,
+                                       const double* __restrict__ psifull, long n_pad, int L, int chol_batch, double* __restrict__ partial2) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x, chunk = blockIdx.y, z = blockIdx.z;
   if (col >= ncols) return;
   const double* b = B + (long)z * strideB + (long)chunk * 128 * ldb + col;
-  double acc = 0.0;
+  const double* pf = psifull ? psifull + (long)(chol_batch == 1 ? col % L : z) * n_pad + (long)chunk * 128 : nullptr;
+  double acc = 0.0, acc2 = 0.0;
 #pragma unroll 8
   for (int r = 0; r < 128; ++r) {
     const double v = b[(long)r * ldb];
     acc = fma(v, v, acc);
+    if (pf) acc2 = fma(v, pf[r], acc2);
   }
   partial[(long)z * stride_partial + (long)chunk * ncols + col] = acc;
+  if (pf) partial2[(long)z * stride_partial + (long)chunk * ncols + col] = acc2;
 }
 
-// W[s][l][i] = Wraw[l][i] + Wraw[i][l],  Wraw[l][i] = (R[s][l][i] - |psi_li|^2) * (1 + [l == i])
+// psifull[i][row] = solved column (s = 0, l = i, i) of B: the psi factor of the FULL model, kept for the MIXED dots of every later chunk
+__global__ void sobol_error_keep_psifull_kernel(const double* __restrict__ B, long ldb, long strideB, int L, long n_pad, int chol_batch,
+                                                double* __restrict__ psifull) {
+  const int i = blockIdx.y;
+  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_pad) return;
+  psifull[(long)i * n_pad + row] = chol_batch == 1 ? B[row * ldb + (long)i * L + i] : B[(long)i * strideB + row * ldb + i];
+}
+
+// W[s][l][i] = Wraw[l][i] + Wraw[i][l],  Wraw[l][i] = (R[s][l][i] - |psi_li|^2) * (1 + [l == i]);  WMm likewise from Rm and the psi^FULL . psi dots
 __global__ void sobol_error_W_kernel(const double* __restrict__ R, const double* __restrict__ partial, long stride_partial, int chunks, int ncols,
-                                     int L, int ns, int chol_batch, ErrMap map, double* __restrict__ W) {
+                                     int L, int ns, int chol_batch, ErrMap map, double* __restrict__ W, const double* __restrict__ Rm,
+                                     const double* __restrict__ partial2, double* __restrict__ WMm) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ns * L * L) return;
   const int s = e / (L * L), li = e - s * L * L, l = li / L, i = li - l * L;
-  auto raw = [&](int a, int b) {
+  auto raw = [&](const double* Rv, const double* part, int a, int b) {
     double psi2 = 0.0;
     const long col = chol_batch == 1 ? ((long)s * L + a) * L + b : (long)s * L + a;
-    const double* pp = partial + (chol_batch == 1 ? 0 : (long)b * stride_partial) + col;
+    const double* pp = part + (chol_batch == 1 ? 0 : (long)b * stride_partial) + col;
     for (int k = 0; k < chunks; ++k) psi2 += pp[(long)k * ncols];
-    return (R[((long)s * L + a) * L + b] - psi2) * (a == b ? 2.0 : 1.0);
+    return (Rv[((long)s * L + a) * L + b] - psi2) * (a == b ? 2.0 : 1.0);
   };
-  W[((long)map.dest[s] * L + l) * L + i] = raw(l, i) + raw(i, l);
+  if (W) W[((long)map.dest[s] * L + l) * L + i] = raw(R, partial, l, i) + raw(R, partial, i, l);
+  if (WMm) WMm[((long)map.dest[s] * L + l) * L + i] = raw(Rm, partial2, l, i) + raw(Rm, partial2, i, l);
 }
 
 namespace {
 struct ErrLayout {
-  size_t coef, pre, parts, B, partial, R, total;
-  int RCH, RC, T, chunk_slices, ncols;
+  size_t coef, pre, parts, B, partial, partial2, R, Rm, ct, psifull, total;
+  int RCH, RC, T, chunk_slices, ncols, kinds;
   long ldb, strideB;
 };
 inline size_t al(size_t b) { return (b + 255) / 256 * 256; }
@@ -404,13 +452,14 @@ int err_row_chunk(int N, int M) {
   const int n64 = (N + 63) / 64 * 64;
   return rch > n64 ? n64 : rch;
 }
-ErrLayout err_layout(int N, int M, int L, int nslices, int n_pad, int chol_batch) {
+ErrLayout err_layout(int N, int M, int L, int nslices, int n_pad, int chol_batch, bool mixed) {
   ErrLayout o{};
   o.RCH = err_row_chunk(N, M);
   o.RC = (N + o.RCH - 1) / o.RCH;
   o.T = (N + EC - 1) / EC;
   o.chunk_slices = nslices < 32 ? nslices : 32;
-  const int J = 2 * L * L;
+  o.kinds = mixed ? 3 : 2;
+  const int J = o.kinds * L * L;
   const int per_problem_cols = chol_batch == 1 ? o.chunk_slices * L * L : o.chunk_slices * L;
   o.ncols = round_up(per_problem_cols, TILE);
   o.ldb = o.ncols;
@@ -426,22 +475,29 @@ ErrLayout err_layout(int N, int M, int L, int nslices, int n_pad, int chol_batch
   o.B = off; off += al((size_t)chol_batch * o.strideB * sizeof(double));
   o.partial = off; off += al((size_t)chol_batch * (n_pad / 128) * o.ncols * sizeof(double));
   o.R = off; off += al((size_t)o.chunk_slices * L * L * sizeof(double));
+  if (mixed) {
+    o.partial2 = off; off += al((size_t)chol_batch * (n_pad / 128) * o.ncols * sizeof(double));
+    o.Rm = off; off += al((size_t)o.chunk_slices * L * L * sizeof(double));
+    o.ct = off; off += al((size_t)L * N * sizeof(double));
+    o.psifull = off; off += al((size_t)L * n_pad * sizeof(double));
+  }
   o.total = off;
   return o;
 }
 }  // namespace
 
-size_t sobol_error_workspace_bytes(int N, int M, int L, int nslices, int n_pad, int chol_batch) {
-  return err_layout(N, M, L, nslices, n_pad, chol_batch).total;
+size_t sobol_error_workspace_bytes(int N, int M, int L, int nslices, int n_pad, int chol_batch, int mixed) {
+  return err_layout(N, M, L, nslices, n_pad, chol_batch, mixed != 0).total;
 }
 
 int sobol_error(const double* X, int N, int M, const double* Lam, const double* F, const double* Phi, const double* g0, const double* g0KY, int L,
                 const double* Achol, int n_pad, long ld, long strideA, int chol_batch, const double* dinv, const unsigned long long* masks,
-                int nslices, void* work, double* V, double* W, cudaStream_t st) {
+                int nslices, void* work, double* V, double* W, double* WMm, cudaStream_t st) {
   RC_REQUIRE(M >= 1 && M <= 64, -2, "sobol_error: M=%d out of range [1,64]", M);
   RC_REQUIRE(chol_batch == 1 || chol_batch == L, -2, "sobol_error: chol_batch must be 1 (covariant) or L (variant)");
   RC_REQUIRE(n_pad >= (chol_batch == 1 ? L * N : N), -2, "sobol_error: n_pad too small");
-  const ErrLayout lay = err_layout(N, M, L, nslices, n_pad, chol_batch);
+  const bool mixed = WMm != nullptr;
+  const ErrLayout lay = err_layout(N, M, L, nslices, n_pad, chol_batch, mixed);
   char* base = static_cast<char*>(work);
   double* coef = reinterpret_cast<double*>(base + lay.coef);
   double* pre = reinterpret_cast<double*>(base + lay.pre);
@@ -449,18 +505,23 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
   double* B = reinterpret_cast<double*>(base + lay.B);
   double* partial = reinterpret_cast<double*>(base + lay.partial);
   double* R = reinterpret_cast<double*>(base + lay.R);
-  const int J = 2 * L * L;
-  static bool configured = false;
-  if (!configured) {
-    RC_CUDA_OK(cudaFuncSetAttribute(sobol_error_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured = true;
-  }
-  sobol_error_coeff_kernel<<<(J * M + 255) / 256, 256, 0, st>>>(Phi, Lam, F, L, M, coef, pre);
+  double* partial2 = mixed ? reinterpret_cast<double*>(base + lay.partial2) : nullptr;
+  double* Rm = mixed ? reinterpret_cast<double*>(base + lay.Rm) : nullptr;
+  double* ct = mixed ? reinterpret_cast<double*>(base + lay.ct) : nullptr;
+  double* psifull = mixed ? reinterpret_cast<double*>(base + lay.psifull) : nullptr;
+  const int J = lay.kinds * L * L;
+  RC_ENSURE_SMEM(sobol_error_matvec_kernel, 220 * 1024);
+  sobol_error_coeff_kernel<<<(J * M + 255) / 256, 256, 0, st>>>(Phi, Lam, F, L, M, lay.kinds, coef, pre);
   RC_LAUNCH_OK();
+  if (mixed) {
+    sobol_error_mixed_weight_kernel<<<dim3((N + 255) / 256, L), 256, 0, st>>>(X, N, M, Phi, Lam, g0KY, ct);
+    RC_LAUNCH_OK();
+  }
   const size_t smem = (size_t)(4 * M + (long)M * lay.RCH + lay.RCH + 2 * M * EC + lay.RCH + EC + 16 * EC) * sizeof(double);
   RC_REQUIRE(smem <= 220 * 1024, -2, "sobol_error: shared memory %zu too large", smem);
   const int chunks = n_pad / 128;
   const long stride_partial = (long)chunks * lay.ncols;
+  const unsigned long long full_mask = (M >= 64) ? ~0ull : ((1ull << M) - 1ull);
   // Structured slices (singles, prefixes, suffixes, full, empty) share ONE sweep-form launch; general subsets take the summed-exponent kernel.
   std::vector<int> structured, scol, general;
   for (int s = 0; s < nslices; ++s) {
@@ -472,40 +533,69 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
       general.push_back(s);
     }
   }
-  auto finish_chunk = [&](const ErrMap& map, int ns, int nv, int RC, long ncols_u) -> int {
+  // keep_full: this chunk is the internal one holding only the full model (MIXED): no V / W output, its psi_ii columns are kept
+  auto finish_chunk = [&](const ErrMap& map, int ns, int nv, int RC, long ncols_u, bool keep_full) -> int {
     RC_CUDA_OK(cudaMemsetAsync(B, 0, (size_t)chol_batch * lay.strideB * sizeof(double), st));
     sobol_error_gather_kernel<<<dim3(ns, L * L), 256, 0, st>>>(parts, L, N, RC, nv, ncols_u, g0KY, g0, pre, chol_batch, B, lay.ldb, lay.strideB, map,
-                                                               V, R);
+                                                               keep_full ? nullptr : V, R, keep_full ? nullptr : Rm);
     RC_LAUNCH_OK();
     int rc = trsm_lower_fwd(Achol, n_pad, ld, strideA, chol_batch, dinv, B, lay.ncols, lay.ldb, lay.strideB, st);
     if (rc) return rc;
-    colnorm_partial_kernel<<<dim3((lay.ncols + 127) / 128, chunks, chol_batch), 128, 0, st>>>(B, lay.ldb, lay.strideB, lay.ncols, partial,
-                                                                                                 stride_partial);
+    if (keep_full) {
+      sobol_error_keep_psifull_kernel<<<dim3((n_pad + 255) / 256, L), 256, 0, st>>>(B, lay.ldb, lay.strideB, L, n_pad, chol_batch, psifull);
+      RC_LAUNCH_OK();
+      return 0;
+    }
+    colnorm_partial_kernel<<<dim3((lay.ncols + 127) / 128, chunks, chol_batch), 128, 0, st>>>(B, lay.ldb, lay.strideB, lay.ncols, partial, stride_partial,
+                                                                                                 psifull, n_pad, L, chol_batch, partial2);
     RC_LAUNCH_OK();
-    sobol_error_W_kernel<<<(ns * L * L + 127) / 128, 128, 0, st>>>(R, partial, stride_partial, chunks, lay.ncols, L, ns, chol_batch, map, W);
+    sobol_error_W_kernel<<<(ns * L * L + 127) / 128, 128, 0, st>>>(R, partial, stride_partial, chunks, lay.ncols, L, ns, chol_batch, map, W, Rm, partial2,
+                                                                   WMm);
     RC_LAUNCH_OK();
     return 0;
   };
-  if (!structured.empty()) {
+  auto general_args = [&](int ns) {
     ErrMatvecArgs a{};
-    a.X = X; a.N = N; a.M = M; a.coef = coef; a.c = g0KY; a.L = L; a.J = J;
-    a.RCH = SW_RCH; a.RC = (N + SW_RCH - 1) / SW_RCH; a.T = (N + SW_EC - 1) / SW_EC; a.ns = 3 * M; a.parts = parts;
-    int rc = M <= 4 ? launch_error_sweep<4>(a, st) : M <= 8 ? launch_error_sweep<8>(a, st) : launch_error_sweep<12>(a, st);
+    a.X = X; a.N = N; a.M = M; a.coef = coef; a.c = g0KY; a.c2 = ct; a.L = L; a.J = J; a.T = lay.T; a.RC = lay.RC; a.RCH = lay.RCH; a.ns = ns; a.parts = parts;
+    return a;
+  };
+  const bool sweep_form = M <= 12 && (!structured.empty() || mixed);
+  ErrMatvecArgs sw{};
+  if (sweep_form) {
+    sw.X = X; sw.N = N; sw.M = M; sw.coef = coef; sw.c = g0KY; sw.c2 = ct; sw.L = L; sw.J = J;
+    sw.RCH = SW_RCH; sw.RC = (N + SW_RCH - 1) / SW_RCH; sw.T = (N + SW_EC - 1) / SW_EC; sw.ns = 3 * M; sw.parts = parts;
+    int rc = M <= 4 ? launch_error_sweep<4>(sw, st) : M <= 8 ? launch_error_sweep<8>(sw, st) : launch_error_sweep<12>(sw, st);
     if (rc) return rc;
-    for (size_t i0 = 0; i0 < structured.size(); i0 += lay.chunk_slices) {
-      const int ns = (int)std::min<size_t>(lay.chunk_slices, structured.size() - i0);
-      ErrMap map{};
-      for (int s = 0; s < ns; ++s) {
-        map.col[s] = scol[i0 + s];
-        map.dest[s] = structured[i0 + s];
-      }
-      if ((rc = finish_chunk(map, ns, 3 * M, a.RC, (long)a.T * SW_EC))) return rc;
+  }
+  if (mixed) {   // the full model first: psi^FULL_ii for the MIXED dots of every chunk below
+    ErrMap map{};
+    map.dest[0] = 0;
+    int rc;
+    if (sweep_form) {
+      map.col[0] = sobol_sweep_index(full_mask, M);
+      if ((rc = finish_chunk(map, 1, 3 * M, sw.RC, (long)sw.T * SW_EC, true))) return rc;
+    } else {
+      ErrMatvecArgs a = general_args(1);
+      a.masks[0] = full_mask;
+      map.col[0] = 0;
+      sobol_error_matvec_kernel<<<dim3(lay.T * lay.RC, J), ETHREADS, smem, st>>>(a);
+      RC_LAUNCH_OK();
+      if ((rc = finish_chunk(map, 1, 1, lay.RC, (long)lay.T * EC, true))) return rc;
     }
+  }
+  for (size_t i0 = 0; i0 < structured.size(); i0 += lay.chunk_slices) {
+    const int ns = (int)std::min<size_t>(lay.chunk_slices, structured.size() - i0);
+    ErrMap map{};
+    for (int s = 0; s < ns; ++s) {
+      map.col[s] = scol[i0 + s];
+      map.dest[s] = structured[i0 + s];
+    }
+    int rc = finish_chunk(map, ns, 3 * M, sw.RC, (long)sw.T * SW_EC, false);
+    if (rc) return rc;
   }
   for (size_t i0 = 0; i0 < general.size(); i0 += lay.chunk_slices) {
     const int ns = (int)std::min<size_t>(lay.chunk_slices, general.size() - i0);
-    ErrMatvecArgs a{};
-    a.X = X; a.N = N; a.M = M; a.coef = coef; a.c = g0KY; a.L = L; a.J = J; a.T = lay.T; a.RC = lay.RC; a.RCH = lay.RCH; a.ns = ns; a.parts = parts;
+    ErrMatvecArgs a = general_args(ns);
     ErrMap map{};
     for (int s = 0; s < ns; ++s) {
       a.masks[s] = masks[general[i0 + s]];
@@ -514,7 +604,7 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
     }
     sobol_error_matvec_kernel<<<dim3(lay.T * lay.RC, J), ETHREADS, smem, st>>>(a);
     RC_LAUNCH_OK();
-    int rc = finish_chunk(map, ns, ns, lay.RC, (long)lay.T * EC);
+    int rc = finish_chunk(map, ns, ns, lay.RC, (long)lay.T * EC, false);
     if (rc) return rc;
   }
   return 0;

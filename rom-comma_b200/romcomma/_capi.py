@@ -68,6 +68,11 @@ _SIGNATURES = {
     'rc_sobol_error': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                       ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, c_double_p, c_double_p, ctypes.c_void_p]),
+    'rc_sobol_error_mixed_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    'rc_sobol_error_mixed': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                            ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, c_double_p, c_double_p, c_double_p,
+                                            ctypes.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -375,18 +380,23 @@ def sobol_contract(X, Phi, c, L: int, is_F_diagonal: bool, masks: Sequence[int],
     return V
 
 
-def sobol_error(X, Lam, F, Phi, g0, g0KY, fac: Factorization, masks: Sequence[int]):
-    """ClosedSobolWithError for a list of subsets (diagonal F): -> (V, W), each (len(masks), L, L) on the device.
-    ``fac`` is the Cholesky factorisation of the GP's noisy gram: batch 1 (covariant, n = L*N) or L (variant, n = N)."""
+def sobol_error(X, Lam, F, Phi, g0, g0KY, fac: Factorization, masks: Sequence[int], mixed: bool = False):
+    """ClosedSobolWithError for a list of subsets (diagonal F): -> (V, W), each (len(masks), L, L) on the device; with ``mixed`` (is_T_partial=False)
+    -> (V, W, WMm).  ``fac`` is the Cholesky factorisation of the GP's noisy gram: batch 1 (covariant, n = L*N) or L (variant, n = N)."""
     N, M = X.shape
     L = Lam.shape[0]
     ns = len(masks)
-    nbytes = int(lib().rc_sobol_error_bufsize(N, M, L, ns, fac.n_pad, fac.batch))
+    bufsize = lib().rc_sobol_error_mixed_bufsize if mixed else lib().rc_sobol_error_bufsize
+    nbytes = int(bufsize(N, M, L, ns, fac.n_pad, fac.batch))
     work = workspace(nbytes, X.device)
     V = torch.empty((ns, L, L), dtype=torch.float64, device=X.device)
     W = torch.empty_like(V)
     arr = (ctypes.c_ulonglong * ns)(*[int(m) for m in masks])
-    check(lib().rc_sobol_error(ptr(X), N, M, ptr(Lam), ptr(F), ptr(Phi), ptr(g0), ptr(g0KY), L, ptr(fac.A), fac.n_pad, fac.n_pad,
-                               fac.n_pad * fac.n_pad, fac.batch, raw_ptr(fac.work), ctypes.cast(arr, ctypes.c_void_p), ns, raw_ptr(work), nbytes,
-                               ptr(V), ptr(W), stream_ptr()), 'rc_sobol_error')
+    common = (ptr(X), N, M, ptr(Lam), ptr(F), ptr(Phi), ptr(g0), ptr(g0KY), L, ptr(fac.A), fac.n_pad, fac.n_pad, fac.n_pad * fac.n_pad, fac.batch,
+              raw_ptr(fac.work), ctypes.cast(arr, ctypes.c_void_p), ns, raw_ptr(work), nbytes, ptr(V), ptr(W))
+    if mixed:
+        WMm = torch.empty_like(V)
+        check(lib().rc_sobol_error_mixed(*common, ptr(WMm), stream_ptr()), 'rc_sobol_error_mixed')
+        return V, W, WMm
+    check(lib().rc_sobol_error(*common, stream_ptr()), 'rc_sobol_error')
     return V, W

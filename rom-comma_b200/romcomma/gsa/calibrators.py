@@ -2,7 +2,7 @@
 
 The precomputation (Phi, g0, mean-centred g0KY) is rc_sobol_prepare; every marginal variance V(m) is the fused
 integrand + contraction kernel rc_sobol_contract, which takes a whole list of marginal subsets per launch (``marginalize_many``).
-``ClosedSobolWithError`` (the T/W error terms, reference :146-402) adds rc_sobol_error (diagonal F, is_T_partial)."""
+``ClosedSobolWithError`` (the T/W error terms, reference :146-402) adds rc_sobol_error / rc_sobol_error_mixed (diagonal F; is_T_partial or not)."""
 from __future__ import annotations
 
 from romcomma.base.definitions import *
@@ -109,11 +109,16 @@ class ClosedSobol(gf.Module, Calibrator):
 class ClosedSobolWithError(ClosedSobol):
     """ Closed Sobol indices with their standard errors T and the covariances W behind them (reference calibrators.py:146-402).
 
-    As in the reference the kernel variance F must be diagonal (``:380-381``).  ``is_T_partial=True`` (the default ``META`` and what all of
-    the reference's scripts run) asserts that the full model is variance free; the non-partial variant (MIXED rank equations, ``WMm``, ``Q``)
-    is not implemented on the device path.  One rc_sobol_error call evaluates, for every requested marginal subset, the _psi_factor /
-    Upsilon / Omega Gaussian chains as fused pairwise kernels and the triangular solve with K_cho as a single TRSM; V comes out as a by-product.
+    As in the reference the kernel variance F must be diagonal (``:380-381``).  ``is_T_partial=True`` (the class ``META``) asserts that the full
+    model is variance free: only W[mm] is formed (rc_sobol_error).  ``is_T_partial=False`` - what installation_test.py:51, csv_script.py:48 and
+    benchmark_script.py:144 pass - adds the MIXED rank equation (``:169-170``): W[Mm], Q and the non-partial T (``:342-346,358-372,388-402``), one
+    more family of pairwise kernels in rc_sobol_error_mixed.  Either way one C-ABI call evaluates, for every requested marginal subset, the
+    _psi_factor / Upsilon / Omega Gaussian chains as fused pairwise kernels and the triangular solve with K_cho as a single TRSM; V is a by-product.
     """
+
+    class RankEquations(NamedTuple):
+        DIAGONAL: Any
+        MIXED: Any
 
     @classproperty
     def META(cls) -> Dict[str, Any]:
@@ -124,8 +129,7 @@ class ClosedSobolWithError(ClosedSobol):
         super()._calibrate()
         if not self.is_F_diagonal:
             raise NotImplementedError('If the MOGP kernel covariance is not diagonal, the Sobol error calculation is unstable.')
-        if not self.meta.get('is_T_partial', True):
-            raise NotImplementedError('is_T_partial=False (the MIXED rank equations) is not implemented on the B200 path.')
+        self._mixed = not self.meta.get('is_T_partial', True)
         self.Upsilon = self.Lambda2[-1][2]
         self.V |= {4: HostTensor(self.V[2].numpy() * self.V[2].numpy())}
         pre = np.sqrt(np.prod(self.Lambda2[1][0].numpy() * self.Lambda2[-1][2].numpy(), axis=-1)) * self.F.numpy()
@@ -133,32 +137,61 @@ class ClosedSobolWithError(ClosedSobol):
         self._fac = self.gp._factorize()[0]                              # K_cho with its solve workspace, resident for the whole sweep
         self._Lam_d, self._F_d = _capi.dev(self.Lambda.numpy()), _capi.dev(self.F.numpy().reshape(-1))
         self._g0_d = self.g0.as_subclass(torch.Tensor).reshape(self.L, self.N).contiguous()
-        self._W_full = None
+        self._full = None                                                # (W[MM] DIAGONAL, W[MM] MIXED or None) of the full model
+
+    # -- the full model: evaluated on first use, and for free when a ``marginalize_*`` call comes first (the full-model subset rides along in
+    #    that call's single triangular solve instead of paying for a launch-latency-bound solve of its own) -------------------------------
+    def _full_model(self) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        if self._full is None:
+            self._VW_many([])
+        return self._full
 
     @property
-    def W(self) -> HostTensor:
-        """ The covariance W of the full model (reference calibrators.py: computed eagerly in ``_calibrate``).  Here it is evaluated on first
-        use, and for free when a ``marginalize_*`` call comes first: the full-model subset rides along in that call's single triangular
-        solve (16 more right-hand sides) instead of paying for a launch-latency-bound solve of its own."""
-        if self._W_full is None:
-            self._W_full = HostTensor(self._VW_many([_capi.slice_mask(0, self.M)])[1][0])
-        return self._W_full
+    def W(self):
+        """ The covariance W[MM] of the full model: an (L,L) tensor if is_T_partial, else RankEquations(DIAGONAL, MIXED) (reference :388-399)."""
+        diagonal, mixed = self._full_model()
+        return HostTensor(diagonal) if not self._mixed else self.RankEquations(DIAGONAL=HostTensor(diagonal), MIXED=HostTensor(mixed))
 
-    def _VW_many(self, masks: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+    @property
+    def Q(self) -> HostTensor:
+        """ q_l + q_i + 2 delta_li q_l with q = diag(W.MIXED) / (4 V[1]^2) (reference :400-401); only defined when not is_T_partial."""
+        if not self._mixed:
+            raise AttributeError('Q is only calculated when is_T_partial is False.')
+        q = np.diag(self._full_model()[1]) / (4.0 * self.V[1].numpy() * self.V[1].numpy())
+        return HostTensor(q[None, :] + q[:, None] + 2.0 * np.diag(q))
+
+    @property
+    def T(self) -> HostTensor:
+        """ The uncertainty of the full model's index (reference :402); only defined when not is_T_partial."""
+        if not self._mixed:
+            raise AttributeError('T of the full model is only calculated when is_T_partial is False.')
+        diagonal, mixed = self._full_model()
+        return HostTensor(self._T(diagonal, mixed, self.V[0].numpy()))
+
+    def _T(self, Wmm: np.ndarray, WMm: Optional[np.ndarray] = None, Vm: Optional[np.ndarray] = None) -> np.ndarray:
+        """ reference :335-346.  V[1] is an (L,) vector: it divides along the LAST axis, as in the reference (T is not symmetric)."""
+        Q = Wmm if not self._mixed else Wmm - 2.0 * Vm * WMm / self.V[1].numpy() + Vm * Vm * self.Q.numpy()
+        return np.sqrt(np.abs(Q) / self.V[4].numpy())
+
+    def _VW_many(self, masks: Sequence[int]):
+        """ -> (V, W[mm], W[Mm] or None), host arrays (len(masks), L, L)."""
         masks = [int(m) for m in masks]
-        ride_along = self._W_full is None             # rc_sobol_error chunks long lists itself
+        ride_along = self._full is None               # rc_sobol_error chunks long lists itself
         if ride_along:
             masks = masks + [_capi.slice_mask(0, self.M)]
-        V, W = _capi.sobol_error(self._Xd, self._Lam_d, self._F_d, self._Phi_d, self._g0_d, self._g0KY_d, self._fac, masks)
-        V, W = V.cpu().numpy(), W.cpu().numpy()
+        out = _capi.sobol_error(self._Xd, self._Lam_d, self._F_d, self._Phi_d, self._g0_d, self._g0KY_d, self._fac, masks, mixed=self._mixed)
+        V, W = out[0].cpu().numpy(), out[1].cpu().numpy()
+        WMm = out[2].cpu().numpy() if self._mixed else None
         if ride_along:
-            self._W_full = HostTensor(W[-1])
-            V, W = V[:-1], W[:-1]
-        return V, W
+            self._full = (W[-1], WMm[-1] if self._mixed else None)
+            V, W, WMm = V[:-1], W[:-1], (WMm[:-1] if self._mixed else None)
+        return V, W, WMm
 
-    def _results(self, V: np.ndarray, W: np.ndarray) -> List[Dict[str, HostTensor]]:
-        V2, V4 = self.V[2].numpy(), self.V[4].numpy()
-        return [{'V': HostTensor(v), 'S': HostTensor(v / V2), 'W': HostTensor(w), 'T': HostTensor(np.sqrt(np.abs(w) / V4))} for v, w in zip(V, W)]
+    def _results(self, V: np.ndarray, W: np.ndarray, WMm: Optional[np.ndarray]) -> List[Dict[str, HostTensor]]:
+        V2 = self.V[2].numpy()
+        if not self._mixed:
+            return [{'V': HostTensor(v), 'S': HostTensor(v / V2), 'W': HostTensor(w), 'T': HostTensor(self._T(w))} for v, w in zip(V, W)]
+        return [{'V': HostTensor(v), 'S': HostTensor(v / V2), 'W': HostTensor(w), 'T': HostTensor(self._T(w, wm, v))} for v, w, wm in zip(V, W, WMm)]
 
     def marginalize_many(self, slices: Sequence[Sequence[int]]) -> List[Dict[str, HostTensor]]:
         return self._results(*self._VW_many([_capi.slice_mask(int(m[0]), int(m[1])) for m in slices]))

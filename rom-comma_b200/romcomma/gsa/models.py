@@ -120,7 +120,7 @@ class Sobol(GSA):
         results['V'] = np.concatenate([results['V'], V0], axis=-1)
         S = S0 - results['S'] if self.kind == GSA.Kind.TOTAL else results['S']
         results['S'] = np.concatenate([S, S0], axis=-1)
-        if 'T' in results and not self.meta['is_T_partial']:     # reference models.py:211-213; unreachable here: the calibrator refuses is_T_partial=False
+        if 'T' in results and not self.meta['is_T_partial']:     # reference models.py:211-213 (TOTAL: the full model's T is ADDED, sic)
             T0 = np.asarray(calibrator.T)[..., None]
             T = T0 + results['T'] if self.kind == GSA.Kind.TOTAL else results['T']
             results['T'] = np.concatenate([T, T0], axis=-1)

@@ -96,3 +96,21 @@ def test_gemm_tile_order_visits_every_tile_once(tiles_m, tiles_n, lower, kmode, 
         lengths = nk * 16
         assert lengths[0] == lengths.max(), 'the list must start with the longest K range'
         assert lengths[-1] <= lengths[: max(1, count // 4)].min(), 'the shortest ranges belong at the end'
+
+
+@pytest.mark.parametrize('tiles,cols', [(20, 4), (7, 2), (5, 8), (9, 1), (128, 4)])
+def test_gemm_column_limited_lower_list(tiles, cols):
+    """The look-ahead panel update of the factorisation (chol.cu: potrf_lookahead, U_g) runs over the first `cols` tile columns of a lower
+    triangle (negative sel_block selects the list in the test hook): every such tile exactly once, full K, the triangle on the diagonal first."""
+    import numpy as np
+    from romcomma import _capi
+    lib = _capi.lib()
+    w = min(cols, tiles)
+    count = w * (w + 1) // 2 + (tiles - w) * w
+    out = np.full((count, 4), -7, dtype=np.int32)
+    assert lib.rc_debug_tile_order(128 * tiles, 128 * tiles, 512, 1, 0, -cols, out.ctypes.data_as(ctypes.c_void_p)) == count
+    m0, n0, kb, nk = out.T
+    want = {(tm * 128, tn * 128) for tm in range(tiles) for tn in range(min(tm + 1, w))}
+    assert {(a, b) for a, b in zip(m0.tolist(), n0.tolist())} == want and len(want) == count
+    assert np.all(kb == 0) and np.all(nk == 32)
+    assert np.all(np.diff(m0) >= 0), 'row-major: a strip of tiles shares its row panel'

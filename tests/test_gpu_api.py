@@ -216,3 +216,64 @@ def test_mogp_shares_one_factorisation_until_the_hyperparameters_change(small_re
     assert_close(m1, rm1, what='mean after the change')
     assert_close(s1, np.sqrt(rv1), what='std after the change')
     assert_close(model.K_inv_Y.numpy(), gp.k_inv_y_mo(X, Y, ls, F, E1), rtol=1e-7, atol=1e-8, what='K_inv_Y after the change')
+
+
+def test_installation_test_flow_not_partial(tmp_path):
+    """The flow of the reference's installation_test.py (:33-93): Oakley 2004 (L = 3) on M = 7 inputs, N = 300, K = 2 folds (+ improper), variant
+    GPs fitted isotropic then anisotropic, the three Sobol kinds WITH errors and is_T_partial=False (IS_GSA_ERROR_PARTIAL = False) - through
+    user.run.gpr / user.run.gsa / user.results.Collect; T and W of one fold against the oracle at the fitted hyper-parameters."""
+    from oracle import sobol_error
+    from romcomma.data.storage import Fold
+    from romcomma.gpr.models import MOGP
+    from romcomma.gsa.models import GSA
+    from romcomma.user import functions, results, run, sample
+    np.random.seed(3)
+    random.seed(3)
+    noise = sample.GaussianNoise.Variance(len(functions.OAKLEY2004), 0.04, False, True)
+    repo = sample.Function(tmp_path, lambda N, M: sample.DOE.latin_hypercube(N, M, seed=3), functions.OAKLEY2004, 300, 7, noise, None, True).repo
+    repo = repo.into_K_folds(2).rotate_folds(None)
+    models = run.gpr(name='gpr', repo=repo, is_read=False, is_covariant=False, is_isotropic=None, ignore_exceptions=False, maxiter=25)
+    assert models == ['gpr.v.i', 'gpr.v.a']
+    results.Collect({'test': {'header': [0, 1]}, 'test_summary': {'header': [0, 1], 'index_col': 0}},
+                    {repo.folder / model: {'model': model} for model in models}, False).from_folders(repo.folder / 'gpr', True)
+    run.gsa('gpr', repo, is_covariant=False, is_isotropic=False, kinds=GSA.ALL_KINDS, is_error_calculated=True, ignore_exceptions=False,
+            is_T_partial=False)
+    kind_names = [kind.name.lower() for kind in GSA.ALL_KINDS]
+    results.Collect({'S': {}, 'V': {}, 'T': {}, 'W': {}}, {f'{repo.folder / model}/gsa/{k}': {'model': model, 'kind': k} for k in kind_names for model in models},
+                    True).from_folders(repo.folder / 'gsa', True)
+    for f in ('gpr/test_summary.csv', 'gsa/T.csv', 'gsa/W.csv', 'gpr.v.a/gsa/total/T.csv'):
+        assert (repo.folder / f).exists(), f
+    fold = Fold(repo, 0)
+    gpv = MOGP('gpr.v.a', fold, is_read=True, is_covariant=False, is_isotropic=False)
+    X, Y = fold.X.values, fold.Y.values
+    ls, var, noise_v = gpv.kernel.data.frames.lengthscales.np, gpv.kernel.data.frames.variance.np[0], gpv.likelihood.data.frames.variance.np[0]
+    ref = sobol_error.ClosedSobolWithError(X, ls, var, gp.k_inv_y_rbf(X, Y, ls, var, noise_v), gp.k_cho_rbf(X, ls, var, noise_v), is_T_partial=False)
+    from romcomma.gsa.models import Sobol
+    for kind in GSA.ALL_KINDS:
+        want = sobol_error.sobol_kind_with_error(ref, int(kind))
+        folder = fold.folder / 'gpr.v.a' / 'gsa' / kind.name.lower()
+        for key in ('S', 'V', 'W'):
+            got = pd.read_csv(folder / f'{key}.csv', index_col=[0, 1]).values.reshape(3, 3, -1)
+            assert_close(got, want[key], rtol=0, atol=6e-7, what=f'{kind.name} {key}.csv (6 decimals)')
+        T_csv = pd.read_csv(folder / 'T.csv', index_col=[0, 1]).values.reshape(3, 3, -1)
+        assert T_csv.shape == want['T'].shape == want['S'].shape, 'T carries the full-model column when not partial'
+        # full precision, not through the csv.  T = sqrt(|Q_m|)/V2 with Q_m = W[mm] - 2 V W[Mm]/V1 + V^2 Q: three terms of either sign that largely
+        # cancel (the full model's diagonal cancels to rounding noise), so |Q_m| = T^2 V4 is compared with an atol of 1e-7 of the terms' magnitude.
+        gsa = Sobol(gpv, kind, m=-1, is_error_calculated=True, is_T_partial=False)
+        gsa.calibrate()
+        got = {k: np.asarray(v, dtype=float) for k, v in gsa.results.items()}
+        for key in ('S', 'V'):
+            assert_close(got[key], want[key], rtol=1e-7, atol=1e-9, what=f'{kind.name} {key}')
+        # W = mu_phi_mu - mu_psi_mu and Q_m = W[mm] - 2 V W[Mm]/V1 + V^2 Q are differences of nearly equal terms (here |W| ~ 1e-4 of them), each
+        # quadratic in K^-1 y, whose relative rounding error is eps * cond(K) ~ 1e-16 * 1e6 for this fitted model (noise 3e-3, variance 3): any
+        # two float64 evaluations - the oracle and the reference's own code included - differ by ~1e-10 of the TERMS.  Tolerance: 1e-8 of them.
+        per_slice = [ref.marginalize(s) for s in sobol.m_slices(int(kind), 7)]
+        W_scale, Q_scale = (np.stack([r[key] for r in per_slice], axis=-1) for key in ('W_scale', 'Q_scale'))
+        err = np.abs(got['W'] - want['W'])
+        assert np.all(err <= 1e-8 * W_scale), f'{kind.name} W: worst err/terms {np.max(err / W_scale):.2e}'
+        V4 = ref.V[4][..., None]
+        T_slices = (got['T'][..., :-1] - got['T'][..., -1:]) if kind == GSA.Kind.TOTAL else got['T'][..., :-1]      # models.py:212 adds the full-model T
+        T_want = (want['T'][..., :-1] - want['T'][..., -1:]) if kind == GSA.Kind.TOTAL else want['T'][..., :-1]
+        err = np.abs(T_slices ** 2 - T_want ** 2) * V4
+        assert np.all(err <= 1e-8 * Q_scale), f'{kind.name} |Q_m|: worst err/terms {np.max(err / Q_scale):.2e}'
+        assert_close(T_csv, got['T'], rtol=0, atol=6e-7, what=f'{kind.name} T.csv holds the computed T to 6 decimals')

@@ -390,6 +390,41 @@ def test_sobol_error_matches_oracle(C, N, M, L, covariant):
     assert_close(W[0], ref.W, rtol=1e-7, atol=1e-10, what='full-model W')
 
 
+@pytest.mark.parametrize('N,M,L,covariant', [(50, 3, 2, True), (130, 5, 3, True), (70, 2, 1, False), (150, 14, 2, False), (257, 12, 3, True)])
+def test_sobol_error_mixed_matches_oracle(C, N, M, L, covariant):
+    """rc_sobol_error_mixed (is_T_partial=False: W[mm] and the MIXED covariances W[Mm] with the full model) against oracle/sobol_error.py, for
+    structured slices (sweep form), general subsets and M > 12 (no sweep form: the full model's psi factor comes from the general kernel)."""
+    from oracle import sobol_error
+    X, Y, ls, F, E = random_problem(N, M, L, seed=N + 2 * M, full_E=False)
+    if covariant:
+        KiY, cho = gp.k_inv_y_mo(X, Y, ls, F, E), gp.k_cho_mo(X, ls, F, E)
+        K = C.gram(C.dev(X), None, C.dev(ls), C.dev(F[None]), C.dev(E[None]), lower_only=True, pad_to=L * N, pad_identity=True)
+    else:
+        var, noise = np.diag(F).copy(), np.diag(E).copy()
+        KiY, cho = gp.k_inv_y_rbf(X, Y, ls, var, noise), gp.k_cho_rbf(X, ls, var, noise)
+        K = C.gram(C.dev(X), None, C.dev(ls), C.dev(var.reshape(L, 1, 1)), C.dev(noise.reshape(L, 1, 1)), batch=L, lower_only=True, pad_to=N,
+                   pad_identity=True)
+    fac = C.Factorization(K)
+    fac.raise_if_failed()
+    dX, dLam, dF = C.dev(X), C.dev(ls), C.dev(np.diag(F).copy())
+    Phi, g0, g0KY = C.sobol_prepare(dX, dLam, dF, C.dev(KiY.reshape(L, N)), True)
+    subsets = [list(range(M)), [0], [M - 1], list(range(1, M)), [0, M - 1], list(range(0, M, 2))]
+    masks = [sum(1 << i for i in set(s)) for s in subsets]
+    V, W, WMm = (t.cpu().numpy() for t in C.sobol_error(dX, dLam, dF, Phi, g0, g0KY, fac, masks, mixed=True))
+    V1, W1 = (t.cpu().numpy() for t in C.sobol_error(dX, dLam, dF, Phi, g0, g0KY, fac, masks))
+    assert np.array_equal(V, V1) and np.array_equal(W, W1), 'the MIXED jobs must not change V and W[mm]'
+    ref = sobol_error.ClosedSobolWithError(X, ls, np.diag(F), KiY, cho, is_T_partial=False)
+    assert_close(W[0], ref.W_DIAGONAL, rtol=1e-7, atol=1e-10, what='full-model W.DIAGONAL')
+    assert_close(WMm[0], ref.W_MIXED, rtol=1e-7, atol=1e-10, what='full-model W.MIXED')
+    for k, sub in enumerate(subsets):
+        perm = sub + [i for i in range(M) if i not in sub]
+        rp = sobol_error.ClosedSobolWithError(X[:, perm], ls[:, perm], np.diag(F), KiY, cho, is_T_partial=False)       # subset as a prefix slice
+        out = rp.marginalize((0, len(sub)))
+        assert_close(V[k], out['V'], rtol=1e-7, atol=1e-10, what=f'V {sub}')
+        assert_close(W[k], out['W'], rtol=1e-7, atol=1e-10, what=f'W {sub}')
+        assert_close(WMm[k], out['WMm'], rtol=1e-7, atol=1e-10, what=f'WMm {sub}')
+
+
 def test_sobol_pair_space_parts_add_up(C):
     """rc_sobol_contract_part: the row-tile parts a multi-GPU sweep all-reduces sum to the single-GPU result, for structured slices
     (sweep form) and general subsets (one exp per subset) alike."""
@@ -439,3 +474,30 @@ def test_lml_grad_plan_cuda_graph_replay_is_bit_identical(C, N):
         assert np.array_equal(a, b), scale
     assert graph._graph is not None
     assert C.launch_count() - before >= 8 * 20, 'replayed launches are counted'
+
+
+def test_potrf_lookahead_same_bits_as_one_stream(C):
+    """The look-ahead factorisation (chol.cu: potrf_lookahead - serial chain on a high-priority stream, trailing updates as yielding launches on
+    a low-priority one; taken from 32 blocks up) computes the same tiles with the same K ranges in the same order as the one-stream sequence:
+    identical bits, run after run, also against a poisoned workspace; and the right numbers."""
+    N, M, L = 1500, 4, 3                                   # n_pad = 4608 = 36 blocks: groups of 2 block columns, 10 split steps + the tail
+    X, Y, ls, F, E = random_problem(N, M, L, seed=77, full_E=False)
+    dX, dY, args = C.dev(X), C.dev(Y), (C.dev(ls), C.dev(F[None]), C.dev(E[None]))
+    for flags in (C.RC_GRAD_NONE, C.RC_GRAD_VARIANCE | C.RC_GRAD_F_DIAGONAL, C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES):
+        la, one = C.LmlGradPlan(dX, dY, L, 1, flags), C.LmlGradPlan(dX, dY, L, 1, flags | C.RC_NO_OVERLAP)
+        a = la(*args).cpu().numpy().copy()
+        b = one(*args).cpu().numpy().copy()
+        la.work.fill_(0xFF)
+        a2 = la(*args).cpu().numpy().copy()
+        assert la.info.cpu().tolist() == [0]
+        assert np.array_equal(a, b), f'look-ahead differs from the one-stream sequence (flags {flags})'
+        assert np.array_equal(a, a2), 'look-ahead is not reproducible'
+    assert_close(a[0, 0], gp.lml_mo(X, Y, ls, F, E), what='LML')
+    # the factor itself through rc_potrf (look-ahead by default) against LAPACK
+    rng = np.random.default_rng(5)
+    n = 4200
+    B = rng.normal(size=(n, n))
+    K = B @ B.T / n + np.eye(n)
+    fac = C.Factorization(C.pad_identity(C.dev(K)))
+    fac.raise_if_failed()
+    assert_close(fac.lower(n)[0].cpu().numpy(), np.linalg.cholesky(K), rtol=1e-8, atol=1e-10, what='L (look-ahead)')

@@ -74,6 +74,20 @@ def test_scenario_reproduces_the_reference_run(api, name, tmp_path):
             assert_close(g, w, rtol=1e-7, atol=1e-9 * scale, what=f'{name} {key}')
         elif key == 'check_K_inv_Y':
             assert np.all(g < 1e-9), key
+        elif key.startswith('gsa_err_full.') and key.endswith('.T'):
+            # is_T_partial=False: T = sqrt(|Q_m|)/V2 with Q_m = W[mm] - 2 V W[Mm]/V1 + V^2 Q, which cancels to rounding noise on the full model's
+            # diagonal (T ~ 1e-7 = sqrt of noise, not reproducible) - and gsa/models.py:212 ADDS that full-model T to every TOTAL slice.  Compare T^2
+            # (= |Q_m|/V4) with the full-model column taken off the TOTAL slices again, and T itself where it is not the root of noise.
+            if key.startswith('gsa_err_full.total.'):
+                w = np.concatenate([w[..., :-1] - w[..., -1:], w[..., -1:]], axis=-1)
+                g = np.concatenate([g[..., :-1] - g[..., -1:], g[..., -1:]], axis=-1)
+            assert_close(g * g, w * w, rtol=1e-7, atol=1e-10, what=f'{name} {key} (squared)')
+            solid = w > 1e-4
+            assert_close(g[solid], w[solid], rtol=1e-7, what=f'{name} {key}')
+        elif key in ('sobol_err_full.T', 'sobol_err_full.marginalize.1.M.T'):
+            assert_close(g * g, w * w, rtol=1e-7, atol=1e-10, what=f'{name} {key} (squared)')
+        elif key.startswith('sobol_err_full.') or (key.startswith('gsa_err_full.') and key.endswith('.W')):
+            assert_close(g, w, rtol=1e-7, atol=1e-10, what=f'{name} {key} (difference of two O(1e-2) terms)')
         elif key.startswith('gsa_err.') and key.endswith('.T'):
             # T = sqrt(|W|)/V2: for the empty slice [M:M] W is pure cancellation noise (|W| ~ 1e-16), so compare T^2 (= |W|/V4) there
             assert_close(g * g, w * w, rtol=1e-7, atol=1e-10, what=f'{name} {key} (squared)')
