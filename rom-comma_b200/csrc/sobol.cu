@@ -14,6 +14,9 @@
 // Partial sums are written per CTA and reduced in a fixed order: bitwise reproducible, no atomics.
 #include "sobol.h"
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <map>
 #include <vector>
 
 namespace rc {
@@ -365,6 +368,201 @@ __global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs 
   }
 }
 
+
+// ---- all-subsets ("lattice") form -----------------------------------------------------------------------------------------
+// The product form holds for EVERY subset:  H_S = prod_{m in S} h_m.  A block of the subset lattice = the 2^KL subsets that share their
+// high mask bits hi (inputs KL..M-1) and run through all patterns lo of the KL low inputs:  H_(hi,lo) = H_hi * prod_{m in lo} h_m.  Per sample
+// pair a thread evaluates ONE exp for the summed exponents of the hi inputs (times the weight c_aN c_bn), KL exps for the low inputs, and walks
+// the binomial tree of the low patterns depth first - node = parent * h_b, accumulated as it is formed; the leaves (every pattern that contains
+// input KL-1) are a single FMA - 2^KL accumulators in registers: (KL + 1) exps + ~1.5 FP64 instructions per subset, against one exp + 2|S| FMAs
+// per (pair, subset) in sobol_pair_kernel (~33 instructions at M = 12).  CTA = (64-row tile ti, pair of output rows, lattice block); it walks
+// all column tiles, so one partial per (pair, ti, block, lo).  Fixed reduction order, no atomics.
+struct SobolLatticeArgs {
+  const double* X; int N, M;
+  const double* Phi;
+  const double* c;
+  int P, T;
+  int nhi;                // lattice blocks of this launch (gridDim.z)
+  double* parts;          // [npairs][T][nhi][2^KL]
+  int part, nparts;
+  unsigned hi[SOBOL_MAX_SLICES];   // high-bit pattern of each block (mask >> KL)
+};
+
+template <int KL, int S, int B>
+__device__ __forceinline__ void lattice_walk(double (&acc)[1 << KL], const double (&h)[KL], double P) {
+  if constexpr (B < KL) {
+    constexpr int child = S | (1 << B);
+    if constexpr (B == KL - 1) {
+      acc[child] = fma(P, h[B], acc[child]);
+    } else {
+      const double Pc = P * h[B];
+      acc[child] += Pc;
+      lattice_walk<KL, child, B + 1>(acc, h, Pc);
+      lattice_walk<KL, S, B + 1>(acc, h, P);
+    }
+  }
+}
+
+template <int KL>
+__global__ void __launch_bounds__(STHREADS, 1) sobol_lattice_kernel(SobolLatticeArgs p) {
+  constexpr int NLO = 1 << KL;
+  extern __shared__ __align__(16) double sm[];
+  const int M = p.M;
+  const unsigned hi = p.hi[blockIdx.z];
+  int hidx[64], nh = 0;                       // the inputs of the hi pattern (registers; M <= 64)
+  for (int m = KL; m < M; ++m)
+    if ((hi >> (m - KL)) & 1u) hidx[nh++] = m;
+  double* gam = sm;                 // [M]
+  double* cu = gam + M;
+  double* cv = cu + M;
+  double* lp = cv + M;
+  double* gxl = lp + M;             // [KL][64]   gamma_m x, low inputs (rows)
+  double* sul = gxl + KL * ST;      // [KL][64]   cu_m x^2 + lp_m
+  double* gxh = sul + KL * ST;      // [nh][64]   gamma_m x, hi inputs
+  double* suh = gxh + (M - KL) * ST;   // [64]    sum over the hi inputs of cu_m x^2 + lp_m
+  double* cr = suh + ST;            // [64]
+  double* yyl = cr + ST;            // [KL][64]   y, low inputs (columns)
+  double* svl = yyl + KL * ST;      // [KL][64]   cv_m y^2
+  double* yyh = svl + KL * ST;      // [nh][64]
+  double* svh = yyh + (M - KL) * ST;   // [64]
+  double* cc = svh + ST;            // [64]
+  double* wpart = cc + ST;          // [8][NLO]
+
+  const int pidx = blockIdx.y;
+  int a = (int)((sqrt(8.0 * (double)pidx + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
+  while (a * (a + 1) / 2 > pidx) --a;
+  const int b = pidx - a * (a + 1) / 2;
+  const int ti = blockIdx.x, tid = threadIdx.x;
+  double* out = p.parts + (((long)pidx * p.T + ti) * p.nhi + blockIdx.z) * NLO;
+  if ((ti % p.nparts) != p.part) {            // another rank's row tile
+    for (int s = tid; s < NLO; s += STHREADS) out[s] = 0.0;
+    return;
+  }
+  for (int m = tid; m < M; m += STHREADS) {
+    const double pp = p.Phi[a * M + m], qq = p.Phi[b * M + m];
+    const double psi = 1.0 - pp * qq, g = pp * qq / psi;
+    gam[m] = g;
+    cu[m] = -0.5 * g * pp;
+    cv[m] = -0.5 * g * qq;
+    lp[m] = -0.5 * log(psi);
+  }
+  __syncthreads();
+  for (int r = tid; r < ST; r += STHREADS) {
+    const int gi = ti * ST + r;
+    const bool live = gi < p.N;
+    cr[r] = live ? p.c[(long)a * p.N + gi] : 0.0;
+    double sh = 0.0;
+    for (int k = 0; k < nh; ++k) {
+      const int m = hidx[k];
+      const double x = live ? p.X[(long)gi * M + m] : 0.0;
+      gxh[k * ST + r] = gam[m] * x;
+      sh += fma(cu[m] * x, x, lp[m]);
+    }
+    suh[r] = sh;
+#pragma unroll
+    for (int m = 0; m < KL; ++m) {
+      const double x = (live && m < M) ? p.X[(long)gi * M + m] : 0.0;
+      gxl[m * ST + r] = m < M ? gam[m] * x : 0.0;
+      sul[m * ST + r] = m < M ? fma(cu[m] * x, x, lp[m]) : 0.0;
+    }
+  }
+  double acc[NLO];
+#pragma unroll
+  for (int s = 0; s < NLO; ++s) acc[s] = 0.0;
+  const int ty = tid >> 4, tx = tid & 15, lane = tid & 31, warp = tid >> 5;
+  const int tj_end = (a == b) ? ti + 1 : p.T;   // a == b: the mirrored tile carries weight 2 instead
+#pragma unroll 1
+  for (int tj = 0; tj < tj_end; ++tj) {
+    __syncthreads();                             // previous tile's column data is no longer read (and the row data is complete)
+    for (int r = tid; r < ST; r += STHREADS) {
+      const int gj = tj * ST + r;
+      const bool live = gj < p.N;
+      cc[r] = live ? p.c[(long)b * p.N + gj] * ((a == b && tj != ti) ? 2.0 : 1.0) : 0.0;
+      double sh = 0.0;
+      for (int k = 0; k < nh; ++k) {
+        const int m = hidx[k];
+        const double y = live ? p.X[(long)gj * M + m] : 0.0;
+        yyh[k * ST + r] = y;
+        sh = fma(cv[m] * y, y, sh);
+      }
+      svh[r] = sh;
+#pragma unroll
+      for (int m = 0; m < KL; ++m) {
+        const double y = (live && m < M) ? p.X[(long)gj * M + m] : 0.0;
+        yyl[m * ST + r] = y;
+        svl[m * ST + r] = m < M ? cv[m] * y * y : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int u = 0; u < 4; ++u) {
+      const int r = ty + 16 * u;
+      const double wr = cr[r], shr = suh[r];
+#pragma unroll 1
+      for (int v = 0; v < 4; ++v) {
+        const int cidx = tx + 16 * v;
+        double e = shr + svh[cidx];
+        for (int k = 0; k < nh; ++k) e = fma(gxh[k * ST + r], yyh[k * ST + cidx], e);
+        const double H = wr * cc[cidx] * exp_pairwise(fmin(e, 708.0));
+        double h[KL];
+#pragma unroll
+        for (int m = 0; m < KL; ++m) h[m] = exp_pairwise(fma(gxl[m * ST + r], yyl[m * ST + cidx], sul[m * ST + r] + svl[m * ST + cidx]));
+        acc[0] += H;
+        lattice_walk<KL, 0, 0>(acc, h, H);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < NLO; ++s) {
+    const double v = warp_sum(acc[s]);
+    if (lane == 0) wpart[warp * NLO + s] = v;
+  }
+  __syncthreads();
+  for (int s = tid; s < NLO; s += STHREADS) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += wpart[w * NLO + s];
+    out[s] = v;
+  }
+}
+
+struct LatticeDest {
+  int dest[8][64];        // output row of V for (block of this launch chunk, low pattern), -1 = not requested
+};
+
+// V[dest][l][j] = sum_{a in l, b in j} sum_ti parts[pair][ti][block][lo]      grid (2^KL, L*L, blocks of the chunk)
+__global__ void sobol_lattice_finish_kernel(const double* __restrict__ parts, int Lp, int L, int T, int nhi, int NLO, int hz0, LatticeDest map,
+                                            double* __restrict__ V) {
+  __shared__ double red[32];
+  const int lo = blockIdx.x, lj = blockIdx.y, l = lj / L, j = lj - l * L, hz = hz0 + blockIdx.z;
+  const int dest = map.dest[blockIdx.z][lo];
+  if (dest < 0) return;
+  double tot = 0.0;
+  for (int ka = 0; ka < Lp; ++ka)
+    for (int kb = 0; kb < Lp; ++kb) {
+      const int a = l * Lp + ka, b = j * Lp + kb;
+      const int hi_ = max(a, b), lo_ = min(a, b);
+      const long pidx = (long)hi_ * (hi_ + 1) / 2 + lo_;
+      const double* pp = parts + ((pidx * T) * nhi + hz) * NLO + lo;
+      double acc = 0.0;
+      for (int t = threadIdx.x; t < T; t += blockDim.x) acc += pp[(long)t * nhi * NLO];
+      acc = block_sum(acc, red);
+      tot += acc;   // meaningful in thread 0
+    }
+  if (threadIdx.x == 0) V[((long)dest * L + l) * L + j] = tot;
+}
+
+template <int KL>
+static int launch_lattice(const SobolLatticeArgs& a, int npairs, cudaStream_t st) {
+  const size_t smem = (size_t)(4 * a.M + 2 * (2 * KL + (a.M - KL > 0 ? a.M - KL : 0) + 2) * ST + 8 * (1 << KL)) * sizeof(double);
+  RC_REQUIRE(smem <= 200 * 1024, -2, "sobol_contract: shared memory %zu too large for the lattice form", smem);
+  if (smem > 48 * 1024) RC_ENSURE_SMEM(sobol_lattice_kernel<KL>, 200 * 1024);
+  sobol_lattice_kernel<KL><<<dim3(a.T, npairs, a.nhi), STHREADS, smem, st>>>(a);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
 template <int MAXM, int RU>
 static int launch_sweep(const SobolPairArgs& a, int npairs, cudaStream_t st) {
   const size_t smem = (size_t)(4 * a.M + 4 * a.M * ST + 2 * ST + 8 * 3 * MAXM + (size_t)a.M * 2 * RU * STHREADS) * sizeof(double);
@@ -445,8 +643,9 @@ __global__ void sobol_finish_kernel(const double* __restrict__ parts, int P, int
 
 size_t sobol_workspace_bytes(int N, int P, int ns) {
   const long T = (N + ST - 1) / ST;
-  (void)ns;   // 64 values per (pair, tile): a chunk of general subsets, or the 3M <= 36 outputs of the sweep form
-  return (size_t)((long)P * (P + 1) / 2) * T * T * SOBOL_MAX_SLICES * sizeof(double);
+  (void)ns;   // 64 values per (pair, tile): a chunk of general subsets, or the 3M <= 36 outputs of the sweep form ...
+  const long per_pair = T * T > T * SOBOL_MAX_SLICES ? T * T : T * SOBOL_MAX_SLICES;   // ... or 64 lattice blocks of 64 subsets per (pair, row tile)
+  return (size_t)((long)P * (P + 1) / 2) * per_pair * SOBOL_MAX_SLICES * sizeof(double);
 }
 
 int sobol_contract(const double* X, int N, int M, const double* Phi, const double* c, int L, int Lp,
@@ -457,12 +656,56 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
   RC_ENSURE_SMEM(sobol_pair_kernel, 200 * 1024);
   const int T = (N + ST - 1) / ST;
   const int npairs = P * (P + 1) / 2;
+  // Blocks of the subset lattice (the 2^KL subsets that share their inputs >= KL) of which at least half is asked for - the all-subsets sweep -
+  // take the lattice form: (KL + 1) exps and ~1.5 FP64 instructions per subset for the whole block.  RC_SOBOL_LATTICE=0 switches it off.
+  std::vector<char> taken(nslices, 0);
+  {
+    static const bool lattice_on = [] { const char* e = getenv("RC_SOBOL_LATTICE"); return !e || atoi(e) != 0; }();
+    const int KL = M < 6 ? M : 6, NLO = 1 << KL;
+    if (lattice_on && KL >= 3 && M - KL <= 32) {
+      std::map<unsigned long long, std::vector<int>> blocks;
+      for (int s = 0; s < nslices; ++s) blocks[masks[s] >> KL].push_back(s);
+      std::vector<unsigned> his;
+      std::vector<std::vector<int>> dests;
+      for (auto& kv : blocks) {
+        if ((int)kv.second.size() * 2 < NLO) continue;
+        std::vector<int> dest(64, -1);
+        for (int s : kv.second) {
+          const int lo = (int)(masks[s] & (unsigned long long)(NLO - 1));
+          if (dest[lo] < 0) {             // a subset listed twice: the second copy goes the general way
+            dest[lo] = s;
+            taken[s] = 1;
+          }
+        }
+        his.push_back((unsigned)kv.first);
+        dests.push_back(dest);
+      }
+      for (size_t h0 = 0; h0 < his.size(); h0 += SOBOL_MAX_SLICES) {
+        const int nhi = (int)std::min<size_t>(SOBOL_MAX_SLICES, his.size() - h0);
+        SobolLatticeArgs a{};
+        a.X = X; a.N = N; a.M = M; a.Phi = Phi; a.c = c; a.P = P; a.T = T; a.nhi = nhi; a.parts = parts; a.part = part; a.nparts = nparts;
+        for (int z = 0; z < nhi; ++z) a.hi[z] = his[h0 + z];
+        int rc = KL == 6 ? launch_lattice<6>(a, npairs, st) : KL == 5 ? launch_lattice<5>(a, npairs, st) : KL == 4 ? launch_lattice<4>(a, npairs, st)
+                                                                                                                  : launch_lattice<3>(a, npairs, st);
+        if (rc) return rc;
+        for (int z0 = 0; z0 < nhi; z0 += 8) {
+          const int nz = std::min(8, nhi - z0);
+          LatticeDest map;
+          for (int z = 0; z < 8; ++z)
+            for (int lo = 0; lo < 64; ++lo) map.dest[z][lo] = z < nz ? dests[h0 + z0 + z][lo] : -1;
+          sobol_lattice_finish_kernel<<<dim3(NLO, L * L, nz), 256, 0, st>>>(parts, Lp, L, T, nhi, NLO, z0, map, V);
+          RC_LAUNCH_OK();
+        }
+      }
+    }
+  }
   // Structured subsets (single inputs, prefixes, suffixes, full, empty: everything gsa.models.GSA asks for) go through the sweep form:
-  // ONE launch whatever their number; only general subsets (the all-subsets sweep) pay one exp per (pair, subset) below.
+  // ONE launch whatever their number; only general subsets that are not part of a lattice block pay one exp per (pair, subset) below.
   std::vector<int> general;
   if (M <= 20) {
     std::vector<int> structured, sidx;
     for (int s = 0; s < nslices; ++s) {
+      if (taken[s]) continue;
       const int k = sobol_sweep_index(masks[s], M);
       if (k >= 0) {
         structured.push_back(s);
@@ -494,7 +737,8 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
     }
     if (general.empty()) return 0;
   } else {
-    for (int s = 0; s < nslices; ++s) general.push_back(s);
+    for (int s = 0; s < nslices; ++s)
+      if (!taken[s]) general.push_back(s);
   }
   // general subsets: gather them into chunks (the output rows of a chunk need not be contiguous, so each chunk is finished per run)
   for (size_t g0 = 0; g0 < general.size();) {

@@ -96,10 +96,19 @@ class ClosedSobol(gf.Module, Calibrator):
         V = self._V_many([_capi.slice_mask(int(m[0]), int(m[1])) for m in slices])
         return [{'V': HostTensor(v), 'S': HostTensor(v / self.V[2].numpy())} for v in V]
 
-    def marginalize_subsets(self, subsets: Sequence[Sequence[int]]) -> List[Dict[str, HostTensor]]:
-        """ Closed indices of arbitrary (not necessarily contiguous) input subsets - the all-subsets sweep of cfg5."""
-        V = self._V_many([sum(1 << int(i) for i in set(s)) for s in subsets])
-        return [{'V': HostTensor(v), 'S': HostTensor(v / self.V[2].numpy())} for v in V]
+    def _subset_masks(self, subsets: Sequence[Sequence[int]], total: bool) -> List[int]:
+        """ Bit masks of the subsets - of their COMPLEMENTS for total indices: the total index of S is S_full - S_closed(complement of S), the rule
+        gsa.models.Sobol applies to its slices (reference gsa/models.py:86-89,207-210: total of [0:m+1] from the closed index of [m+1:M])."""
+        full = (1 << self.M) - 1
+        masks = [sum(1 << int(i) for i in set(s)) for s in subsets]
+        return [full & ~m for m in masks] if total else masks
+
+    def marginalize_subsets(self, subsets: Sequence[Sequence[int]], total: bool = False) -> List[Dict[str, HostTensor]]:
+        """ Closed (or, with ``total``, total) indices of arbitrary - not necessarily contiguous - input subsets: the all-subsets sweep of cfg5.
+        As in ``Sobol._post_calibrate`` a total result carries the V of the complement it was derived from and S = S_full - S_closed(complement)."""
+        V = self._V_many(self._subset_masks(subsets, total))
+        V2, S0 = self.V[2].numpy(), self.S.numpy()
+        return [{'V': HostTensor(v), 'S': HostTensor(S0 - v / V2 if total else v / V2)} for v in V]
 
     def marginalize(self, m: TF.Slice) -> Dict[str, HostTensor]:
         """ The closed Sobol index of the input slice [m[0]:m[1]]: {'V': (L,L), 'S': V / V[2]}."""
@@ -196,5 +205,14 @@ class ClosedSobolWithError(ClosedSobol):
     def marginalize_many(self, slices: Sequence[Sequence[int]]) -> List[Dict[str, HostTensor]]:
         return self._results(*self._VW_many([_capi.slice_mask(int(m[0]), int(m[1])) for m in slices]))
 
-    def marginalize_subsets(self, subsets: Sequence[Sequence[int]]) -> List[Dict[str, HostTensor]]:
-        return self._results(*self._VW_many([sum(1 << int(i) for i in set(s)) for s in subsets]))
+    def marginalize_subsets(self, subsets: Sequence[Sequence[int]], total: bool = False) -> List[Dict[str, HostTensor]]:
+        """ With ``total`` the results follow ``Sobol._post_calibrate``: S = S_full - S_closed(complement) and, when not is_T_partial,
+        T = T_full + T(complement) (reference gsa/models.py:207-213); V and W are those of the complement."""
+        results = self._results(*self._VW_many(self._subset_masks(subsets, total)))
+        if total:
+            S0 = self.S.numpy()
+            for r in results:
+                r['S'] = HostTensor(S0 - r['S'].numpy())
+                if self._mixed:
+                    r['T'] = HostTensor(self.T.numpy() + r['T'].numpy())
+        return results

@@ -501,3 +501,37 @@ def test_potrf_lookahead_same_bits_as_one_stream(C):
     fac = C.Factorization(C.pad_identity(C.dev(K)))
     fac.raise_if_failed()
     assert_close(fac.lower(n)[0].cpu().numpy(), np.linalg.cholesky(K), rtol=1e-8, atol=1e-10, what='L (look-ahead)')
+
+
+@pytest.mark.parametrize('N,M,L,diag', [(70, 7, 2, True), (130, 8, 2, True), (65, 5, 3, True), (40, 3, 2, True), (50, 9, 1, True), (45, 7, 2, False)])
+def test_sobol_lattice_form_all_subsets(C, N, M, L, diag):
+    """The all-subsets sweep: lists that hold at least half of a block of the subset lattice (the 2^min(6,M) subsets sharing their high inputs)
+    take the lattice kernel (one exp for the high inputs, one per low input, the low patterns by a depth-first product walk).  Every subset
+    against the one-exp-per-subset kernel (reached through sparse lists), sampled ones against the oracle; duplicates, a missing empty set and
+    a half-requested block included; the row-tile parts of a multi-GPU sweep add up."""
+    X, Y, ls, F, E = random_problem(N, M, L, seed=3 * N + M, full_F=not diag, full_E=False)
+    KiY = gp.k_inv_y_mo(X, Y, ls, F, E)
+    dX = C.dev(X)
+    Fin = np.diag(F).copy() if diag else F
+    Phi, g0, g0KY = C.sobol_prepare(dX, C.dev(ls), C.dev(Fin), C.dev(KiY.reshape(L, N)), diag)
+    every = list(range(1, 2 ** M))                                      # all non-empty subsets: block 0 lacks the empty one
+    V = C.sobol_contract(dX, Phi, g0KY, L, diag, every).cpu().numpy()
+    stride = 2 ** M // 4 if M > 3 else 2
+    sparse = np.empty_like(V)
+    for k in range(stride):                                             # lists with < half of every block: sweep form / general kernel
+        idx = [i for i, m in enumerate(every) if m % stride == k]
+        sparse[idx] = C.sobol_contract(dX, Phi, g0KY, L, diag, [every[i] for i in idx]).cpu().numpy()
+    scale = np.abs(sparse).max()
+    assert_close(V, sparse, rtol=1e-9, atol=1e-12 * scale, what='lattice form vs one exp per subset')
+    rng = np.random.default_rng(M)
+    for mask in [int(m) for m in rng.choice(every, 4, replace=False)] + [2 ** M - 1]:
+        subset = [m for m in range(M) if (mask >> m) & 1]
+        assert_close(V[mask - 1], sobol.subset_V(X, ls, F, KiY, subset, diag)['V'], what=f'subset {subset}')
+    # a duplicate, the empty set, and a block of which exactly half is requested
+    odd = [0, 5, 5, 2 ** M - 1] + [m for m in every if m % 2 == 0][: 2 ** (min(6, M) - 1)]
+    Vo = C.sobol_contract(dX, Phi, g0KY, L, diag, odd).cpu().numpy()
+    for k, mask in enumerate(odd):
+        want = sparse[mask - 1] if mask else C.sobol_contract(dX, Phi, g0KY, L, diag, [0]).cpu().numpy()[0]
+        assert_close(Vo[k], want, rtol=1e-9, atol=1e-12 * scale, what=f'list entry {k} (mask {mask})')
+    parts = sum(C.sobol_contract(dX, Phi, g0KY, L, diag, every, None, r, 3).cpu().numpy() for r in range(3))
+    assert_close(parts, V, rtol=1e-10, atol=1e-12 * scale, what='row-tile parts add up (lattice form)')
