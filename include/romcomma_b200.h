@@ -120,6 +120,14 @@ size_t rc_lml_grad_bufsize(int N, int M, int L, int batch, int flags);
 int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch, const double* ls, const double* F, const double* E,
                 const double* Kunit, int flags, void* work, size_t work_bytes, double* out, int* info, rc_stream_t stream);
 
+/* The same evaluation for `batch` problems that do NOT share their data - the folds of a repository (romcomma/user/run.py:60-61 fits them one
+ * after another), each with its own outputs fitted independently (romcomma/gpr/models.py:340-342,360-361): problem z reads inputs X + z*Nmax*M
+ * ((Nmax, M) row-major, its first Ns[z] rows), outputs Y + z*Nmax*L ((Nmax, L)), ls + z*L*M, F + z*L*L, E + z*L*L.  Ns: DEVICE array of `batch`
+ * sample counts, 1 <= Ns[z] <= Nmax; the rows beyond L*Ns[z] of a problem's padded matrix are identity padding.  Workspace and output layout as
+ * rc_lml_grad with N = Nmax (rc_lml_grad_bufsize(Nmax, M, L, batch, flags)); no cached unit gram. */
+int rc_lml_grad_multi(const double* X, const double* Y, const int* Ns, int Nmax, int M, int L, int batch, const double* ls, const double* F,
+                      const double* E, int flags, void* work, size_t work_bytes, double* out, int* info, rc_stream_t stream);
+
 /* ---- prediction reductions -----------------------------------------------------------------------------------------
  * With A = L^-1 Kmn (n_pad x c_pad, from rc_trsm_fwd; column c = l*nstar + i) and a = L^-1 y:
  *   mean[z][i][l] = sum_k A[k][c] a[k],   var[z][i][l] = kdiag[z][l] - sum_k A[k][c]^2 (+ noise[z][l] if noise != NULL)

@@ -59,14 +59,17 @@ static PotrfWork split_potrf_work(void* work, int n_pad, int batch) {
   return w;
 }
 
-// y_z[l*N + n] = Y[n][z*L + l], zero padded
-__global__ void pack_y_kernel(const double* __restrict__ Y, int N, int L, int batch, int n_pad, double* __restrict__ y) {
+// y_z[l*Nz + n] = Yz[n][l], zero padded;  Yz = Y + z*strideY with row stride ldY (one (N, batch*L) matrix: strideY = L, ldY = batch*L;
+// per-problem (Nmax, L) matrices: strideY = Nmax*L, ldY = L).  Nz: per-problem sample counts or nullptr.
+__global__ void pack_y_kernel(const double* __restrict__ Y, long strideY, int ldY, int N, const int* __restrict__ Nz, int L, int n_pad,
+                              double* __restrict__ y) {
   const int z = blockIdx.y;
+  const int Nq = Nz ? Nz[z] : N;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (long)gridDim.x * blockDim.x) {
     double v = 0.0;
-    if (i < (long)L * N) {
-      const int l = (int)(i / N), n = (int)(i - (long)l * N);
-      v = Y[(long)n * (batch * L) + z * L + l];
+    if (i < (long)L * Nq) {
+      const int l = (int)(i / Nq), n = (int)(i - (long)l * Nq);
+      v = Y[(long)z * strideY + (long)n * ldY + l];
     }
     y[(long)z * n_pad + i] = v;
   }
@@ -74,8 +77,9 @@ __global__ void pack_y_kernel(const double* __restrict__ Y, int N, int L, int ba
 
 // out_z = { lml, dF, dE, dls } from the raw sums { SF, SE, dls_row, dls_col }
 __global__ void lml_finalize_kernel(const double* __restrict__ logdet, const double* __restrict__ quad, const double* __restrict__ raw, int L, int M,
-                                    int n_real, int flags, double* __restrict__ out) {
+                                    int n_all, const int* __restrict__ Nz, int flags, double* __restrict__ out) {
   const int z = blockIdx.x;
+  const int n_real = Nz ? L * Nz[z] : n_all;
   const int stride = 1 + 2 * L * L + L * M, nvals = 2 * L * L + 2 * L * M;
   double* o = out + (long)z * stride;
   const double* r = raw + (long)z * nvals;
@@ -252,11 +256,11 @@ LmlLayout lml_layout(int N, int M, int L, int batch, int flags) {
 
 size_t rc_lml_grad_bufsize(int N, int M, int L, int batch, int flags) { return lml_layout(N, M, L, batch, flags & ~RC_NO_OVERLAP).total; }
 
-int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch, const double* ls, const double* F, const double* E,
-                const double* Kunit, int flags, void* work, size_t work_bytes, double* out, int* info, rc_stream_t stream) {
-  RC_REQUIRE(X && Y && ls && F && E && work && out && info, -2, "rc_lml_grad: null pointer");
-  RC_REQUIRE(N > 0 && M > 0 && L > 0 && batch > 0, -2, "rc_lml_grad: non-positive size");
-  RC_REQUIRE(!Kunit || batch == 1, -2, "rc_lml_grad: a cached unit gram is only supported for batch == 1");
+// One implementation behind rc_lml_grad (one design shared by the problems of the batch, Y an (N, batch*L) matrix) and rc_lml_grad_multi (every
+// problem its own (Nmax, M) inputs, (Nmax, L) outputs and sample count Nz[z] <= N: the folds of a repository).
+static int lml_grad_impl(const double* X, long strideX, const double* Y, long strideY, int ldY, int N, const int* Nz, int M, int L, int batch,
+                         const double* ls, const double* F, const double* E, const double* Kunit, int flags, void* work, size_t work_bytes, double* out,
+                         int* info, rc_stream_t stream) {
   const bool one_stream = (flags & RC_NO_OVERLAP) != 0;       // keep every kernel on `stream`: no look-ahead, no overlapped inverse
   const bool overlap = !one_stream && batch == 1 && (flags & ~RC_NO_OVERLAP) != RC_GRAD_NONE;
   flags &= ~RC_NO_OVERLAP;
@@ -286,6 +290,7 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
     g.X = X; g.N = N; g.X2 = X; g.N2 = N; g.M = M; g.L = L;
     g.ls = ls; g.stride_ls = (long)L * M; g.F = F; g.E = E; g.stride_FE = (long)L * L;
     g.out = A; g.ld_out = n_pad; g.stride_out = mat; g.rows_pad = n_pad; g.cols_pad = n_pad; g.lower_only = 1; g.pad_identity = 1;
+    g.stride_X = strideX; g.Nz = Nz;
     if ((rc = gram(g, batch, st))) return rc;
   }
   // 2. factor, log-determinant (gradient of one matrix: Z = L^-1 is produced as well, its independent part inside the factorisation)
@@ -296,7 +301,7 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
   }
   if ((rc = sum_parts(pw.logdet_parts, n_pad / TILE, batch, logdet, 1.0, st))) return rc;
   // 3. alpha = L^-1 y, quad = alpha^T alpha
-  pack_y_kernel<<<dim3((n_pad + 255) / 256, batch), 256, 0, st>>>(Y, N, L, batch, n_pad, yv);
+  pack_y_kernel<<<dim3((n_pad + 255) / 256, batch), 256, 0, st>>>(Y, strideY, ldY, N, Nz, L, n_pad, yv);
   RC_LAUNCH_OK();
   RC_CUDA_OK(cudaMemsetAsync(graw, 0, (size_t)batch * grad_nvals(L, M) * sizeof(double), st));
   if (flags == RC_GRAD_NONE) {
@@ -318,6 +323,7 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
     ga.Kinv = Kinv; ga.ldk = n_pad; ga.stride_K = mat; ga.alpha = kinvy; ga.stride_alpha = n_pad; ga.parts = gparts;
     ga.with_ls = (flags & RC_GRAD_LENGTHSCALES) ? 1 : 0;
     ga.diag_blocks_only = selected ? 1 : 0;
+    ga.stride_X = strideX; ga.Nz = Nz;
     if ((rc = grad_reduce(ga, n_pad, batch, graw, st))) return rc;
     if (selected) {   // dE off-diagonal entries from the diagonals of the off-diagonal blocks of K^-1 = Z^T Z (A holds Z = L^-1 now)
       double* dparts = reinterpret_cast<double*>(base + lay.dots);
@@ -327,9 +333,24 @@ int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch
       RC_LAUNCH_OK();
     }
   }
-  lml_finalize_kernel<<<batch, 128, 0, st>>>(logdet, quad, graw, L, M, n, flags, out);
+  lml_finalize_kernel<<<batch, 128, 0, st>>>(logdet, quad, graw, L, M, n, Nz, flags, out);
   RC_LAUNCH_OK();
   return 0;
+}
+
+int rc_lml_grad(const double* X, const double* Y, int N, int M, int L, int batch, const double* ls, const double* F, const double* E,
+                const double* Kunit, int flags, void* work, size_t work_bytes, double* out, int* info, rc_stream_t stream) {
+  RC_REQUIRE(X && Y && ls && F && E && work && out && info, -2, "rc_lml_grad: null pointer");
+  RC_REQUIRE(N > 0 && M > 0 && L > 0 && batch > 0, -2, "rc_lml_grad: non-positive size");
+  RC_REQUIRE(!Kunit || batch == 1, -2, "rc_lml_grad: a cached unit gram is only supported for batch == 1");
+  return lml_grad_impl(X, 0, Y, L, batch * L, N, nullptr, M, L, batch, ls, F, E, Kunit, flags, work, work_bytes, out, info, stream);
+}
+
+int rc_lml_grad_multi(const double* X, const double* Y, const int* Ns, int Nmax, int M, int L, int batch, const double* ls, const double* F,
+                      const double* E, int flags, void* work, size_t work_bytes, double* out, int* info, rc_stream_t stream) {
+  RC_REQUIRE(X && Y && Ns && ls && F && E && work && out && info, -2, "rc_lml_grad_multi: null pointer");
+  RC_REQUIRE(Nmax > 0 && M > 0 && L > 0 && batch > 0, -2, "rc_lml_grad_multi: non-positive size");
+  return lml_grad_impl(X, (long)Nmax * M, Y, (long)Nmax * L, L, Nmax, Ns, M, L, batch, ls, F, E, nullptr, flags, work, work_bytes, out, info, stream);
 }
 
 size_t rc_predict_bufsize(int c_pad, int batch) { return align256(predict_workspace_bytes(c_pad, batch)); }

@@ -33,6 +33,11 @@ struct GemmArgs {
   int kmode;
   int sel_block;    // > 0 (with lower_only): compute only tiles that intersect the diagonal blocks of size sel_block ("selected" LAUUM)
   int col_tiles;    // > 0 (with lower_only, K_FULL): only the first col_tiles tile columns of the lower triangle (look-ahead panel update)
+  // Second (outer) batch level, for launches that are already batched over sub-problems of ONE matrix (the pairs of a trtri level) and have to
+  // cover several matrices as well: problem z = z2 * batch + z1 reads A + z1*strideA + z2*strideA2 (B, C likewise).  0 / 1 = a single level.
+  int batch2;
+  long strideA2, strideB2, strideC2;
+  int batch1;       // set by the launcher: the inner batch count (what `batch` of launch_gemm_ws is)
 };
 
 // number of 128 x 128 tiles of one matrix in the list the arguments describe
@@ -168,9 +173,16 @@ __host__ __device__ __forceinline__ GemmTile gemm_decode_tile(const GemmArgs& p,
   t.kb = kb;
   t.nk = (ke - kb) / G_BK;
   if (p.sel_block > 0 && t.m0 / p.sel_block > (t.n0 + G_BN - 1) / p.sel_block) t.nk = -1;   // row blocks all above the column blocks
-  t.A = p.A + (long)z * p.strideA;
-  t.B = p.B + (long)z * p.strideB;
-  t.C = p.C + (long)z * p.strideC;
+  if (p.batch2 > 1) {
+    const int z2 = z / p.batch1, z1 = z - z2 * p.batch1;
+    t.A = p.A + (long)z1 * p.strideA + (long)z2 * p.strideA2;
+    t.B = p.B + (long)z1 * p.strideB + (long)z2 * p.strideB2;
+    t.C = p.C + (long)z1 * p.strideC + (long)z2 * p.strideC2;
+  } else {
+    t.A = p.A + (long)z * p.strideA;
+    t.B = p.B + (long)z * p.strideB;
+    t.C = p.C + (long)z * p.strideC;
+  }
   return t;
 }
 
@@ -303,7 +315,7 @@ inline double gemm_tile_flops(const GemmArgs& p, int batch) {
       if (p.sel_block > 0 && m0 / p.sel_block > (n0 + G_BN - 1) / p.sel_block) continue;
       if (ke > kb) ksum += (double)(ke - kb);
     }
-  return 2.0 * G_BM * G_BN * ksum * batch;
+  return 2.0 * G_BM * G_BN * ksum * batch * (p.batch2 > 1 ? p.batch2 : 1);
 }
 
 template <bool TA, bool TB>

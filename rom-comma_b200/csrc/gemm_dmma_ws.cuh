@@ -76,19 +76,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                : "memory");
 }
 
-__device__ __forceinline__ void tma_g2s_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(smem_u32(dst)),
-               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+__device__ __forceinline__ void tma_g2s_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                : "memory");
 }
 
 // One operand stage by the producer warp.  Transposed storage: 16 rows of 1 KB, one bulk copy per lane.  k-contiguous storage: one
-// tiled TMA load of the 16 x 128 box at (k, row, z) relative to the operand pointer the tensor map was built on.
+// tiled TMA load of the 16 x 128 box at (k, row, z1, z2) relative to the operand pointer the tensor map was built on.
 template <bool T>
-__device__ __forceinline__ void ws_load_operand(double* dst, const double* src, long ld, const CUtensorMap* map, int z, int mn0, int k0, int lane,
+__device__ __forceinline__ void ws_load_operand(double* dst, const double* src, long ld, const CUtensorMap* map, int z1, int z2, int mn0, int k0, int lane,
                                                 unsigned long long* bar) {
   if (!T) {
-    if (lane == 0) tma_g2s_3d(dst, map, k0, mn0, z, bar);
+    if (lane == 0) tma_g2s_4d(dst, map, k0, mn0, z1, z2, bar);
   } else {
     if (lane < G_BK) bulk_g2s(dst + lane * (G_BM + G_PAD), src + (long)(k0 + lane) * ld + mn0, G_BM * sizeof(double), bar);
   }
@@ -166,14 +166,17 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_dmma_ws_kernel(GemmArgs p, 
       }
       if (tile < 0) break;
       const int z = (int)(tile / tiles_per_matrix);
+      const int z2 = p.batch2 > 1 ? z / p.batch1 : 0, z1 = z - z2 * p.batch1;
+      // an operand shared by the problems of a level (stride 0) has a single slice in its tensor map
+      const int zA1 = p.strideA ? z1 : 0, zA2 = p.strideA2 ? z2 : 0, zB1 = p.strideB ? z1 : 0, zB2 = p.strideB2 ? z2 : 0;
       for (int kt = 0; kt < T.nk; kt += W_SUB) {   // K ranges are multiples of 128: nk is a multiple of W_SUB
         mbar_wait(empty + stage, phase ^ 1u);
         if (lane == 0) mbar_arrive_expect_tx(full + stage, S::STAGE_TX);
         __syncwarp();
 #pragma unroll
         for (int sub = 0; sub < W_SUB; ++sub) {
-          ws_load_operand<TA>(As + (stage * W_SUB + sub) * S::A_STAGE, T.A, p.lda, &mapA, z, T.m0, T.kb + (kt + sub) * G_BK, lane, full + stage);
-          ws_load_operand<TB>(Bs + (stage * W_SUB + sub) * S::B_STAGE, T.B, p.ldb, &mapB, z, T.n0, T.kb + (kt + sub) * G_BK, lane, full + stage);
+          ws_load_operand<TA>(As + (stage * W_SUB + sub) * S::A_STAGE, T.A, p.lda, &mapA, zA1, zA2, T.m0, T.kb + (kt + sub) * G_BK, lane, full + stage);
+          ws_load_operand<TB>(Bs + (stage * W_SUB + sub) * S::B_STAGE, T.B, p.ldb, &mapB, zB1, zB2, T.n0, T.kb + (kt + sub) * G_BK, lane, full + stage);
         }
         if (++stage == W_STAGES) {
           stage = 0;
@@ -312,19 +315,22 @@ inline TensorMapEncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
-// Tensor map over a k-contiguous operand: dims (k, rows, batch), box 16 x 128 x 1 doubles, 128-byte swizzle.
-inline int make_operand_map(CUtensorMap* map, const double* ptr, long ld, long stride, int rows, int K, int batch) {
+// Tensor map over a k-contiguous operand: dims (k, rows, inner batch, outer batch), box 16 x 128 x 1 x 1 doubles, 128-byte swizzle.  A batch
+// level whose stride is 0 (an operand shared by the problems) or whose count is 1 gets a single slice; the kernel then addresses slice 0.
+inline int make_operand_map(CUtensorMap* map, const double* ptr, long ld, long stride, int rows, int K, int batch, long stride2, int batch2) {
   TensorMapEncodeTiledFn enc = tensor_map_encoder();
   RC_REQUIRE(enc != nullptr, -3, "gemm_dmma_ws: cuTensorMapEncodeTiled is not available from this driver");
-  const bool batched = batch > 1 && stride != 0;
-  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batched ? batch : 1)};
-  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(double), (cuuint64_t)(batched ? stride : (long)rows * ld) * sizeof(double)};
-  const cuuint32_t box[3] = {(cuuint32_t)G_BK, (cuuint32_t)G_BM, 1u};
-  const cuuint32_t estr[3] = {1u, 1u, 1u};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const bool level1 = batch > 1 && stride != 0, level2 = batch2 > 1 && stride2 != 0;
+  const long dummy = (long)rows * ld;
+  const cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(level1 ? batch : 1), (cuuint64_t)(level2 ? batch2 : 1)};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * sizeof(double), (cuuint64_t)(level1 ? stride : dummy) * sizeof(double),
+                                 (cuuint64_t)(level2 ? stride2 : (level1 ? stride * batch : dummy)) * sizeof(double)};
+  const cuuint32_t box[4] = {(cuuint32_t)G_BK, (cuuint32_t)G_BM, 1u, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RC_REQUIRE(r == CUDA_SUCCESS, -3, "gemm_dmma_ws: cuTensorMapEncodeTiled failed (%d) for ptr=%p ld=%ld stride=%ld rows=%d K=%d batch=%d", (int)r,
-             (const void*)ptr, ld, stride, rows, K, batch);
+  RC_REQUIRE(r == CUDA_SUCCESS, -3, "gemm_dmma_ws: cuTensorMapEncodeTiled failed (%d) for ptr=%p ld=%ld stride=%ld/%ld rows=%d K=%d batch=%d/%d", (int)r,
+             (const void*)ptr, ld, stride, stride2, rows, K, batch, batch2);
   return 0;
 }
 
@@ -337,8 +343,11 @@ int* gemm_sched_slot(int device);   // defined in chol.cu
 // ceil(tiles / k) CTAs that retire after k tiles each - for background work on a low-priority stream: the SMs return to the block
 // scheduler every few tiles, so pending CTAs of a higher-priority stream never wait longer than that.
 template <bool TA, bool TB, bool LOWER>
-inline int launch_gemm_ws_impl(const GemmArgs& a, int batch, cudaStream_t stream, int tiles_per_cta) {
+inline int launch_gemm_ws_impl(const GemmArgs& a_in, int batch, cudaStream_t stream, int tiles_per_cta) {
   using S = GemmWsSmem<TA, TB>;
+  GemmArgs a = a_in;
+  a.batch1 = batch;
+  const int batch2 = a.batch2 > 1 ? a.batch2 : 1;
   int dev = 0;
   RC_CUDA_OK(cudaGetDevice(&dev));
   RC_ENSURE_SMEM((gemm_dmma_ws_kernel<TA, TB, LOWER>), S::BYTES);
@@ -349,14 +358,14 @@ inline int launch_gemm_ws_impl(const GemmArgs& a, int batch, cudaStream_t stream
   RC_REQUIRE(a.lda % 2 == 0 && a.ldb % 2 == 0 && a.ldc % 2 == 0, -2, "gemm_dmma_ws: leading dimensions must be even (16-byte rows)");
   RC_REQUIRE(a.col_tiles == 0 || (a.lower_only && a.kmode == K_FULL && a.sel_block == 0), -2, "gemm_dmma_ws: col_tiles needs a plain lower-triangular list");
   const long tiles = gemm_tile_count(a);
-  const long total = tiles * batch;
+  const long total = tiles * batch * batch2;
   const unsigned grid = tiles_per_cta > 0 ? (unsigned)((total + tiles_per_cta - 1) / tiles_per_cta) : (unsigned)(total < num_sms ? total : num_sms);
   alignas(64) CUtensorMap mapA, mapB;
   memset(&mapA, 0, sizeof(mapA));
   memset(&mapB, 0, sizeof(mapB));
   int rc;
-  if (!TA && (rc = make_operand_map(&mapA, a.A, a.lda, a.strideA, a.M, a.K, batch))) return rc;
-  if (!TB && (rc = make_operand_map(&mapB, a.B, a.ldb, a.strideB, a.N, a.K, batch))) return rc;
+  if (!TA && (rc = make_operand_map(&mapA, a.A, a.lda, a.strideA, a.M, a.K, batch, a.strideA2, batch2))) return rc;
+  if (!TB && (rc = make_operand_map(&mapB, a.B, a.ldb, a.strideB, a.N, a.K, batch, a.strideB2, batch2))) return rc;
   const bool prof = profile_enabled();
   if (prof) profile_gemm_begin(stream);
   int* sched = gemm_sched_slot(dev);

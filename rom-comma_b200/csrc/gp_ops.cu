@@ -63,8 +63,10 @@ __global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
   const double* E = p.E ? p.E + (long)z * p.stride_FE : nullptr;
   double* out = p.out + (long)z * p.stride_out;
 
-  stage_scaled(sr, li, ni, p.X, p.N, p.M, ls, p.L, (long)ti * GT);
-  for (int s = 0; s < ntj; ++s) stage_scaled(sc + s * GT * p.M, lj + s * GT, nj + s * GT, p.X2, p.N2, p.M, ls, p.L, (long)(tj0 + s) * GT);
+  const int Nr = p.Nz ? p.Nz[z] : p.N, Nc = p.Nz ? p.Nz[z] : p.N2;       // per-problem sample counts (folds) only exist for the square training gram
+  stage_scaled(sr, li, ni, p.X + (long)z * p.stride_X, Nr, p.M, ls, p.L, (long)ti * GT);
+  for (int s = 0; s < ntj; ++s)
+    stage_scaled(sc + s * GT * p.M, lj + s * GT, nj + s * GT, p.X2 + (long)z * p.stride_X, Nc, p.M, ls, p.L, (long)(tj0 + s) * GT);
   __syncthreads();
 
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
@@ -214,9 +216,12 @@ __global__ void __launch_bounds__(GTHREADS) grad_reduce_kernel(GradArgs p) {
   const int L = p.L, M = p.M;
 
   for (int e = threadIdx.x; e < p.nvals; e += GTHREADS) parts[e] = 0.0;
-  if (p.diag_blocks_only && ((long)ti * GT) / p.N > ((long)tj * GT + GT - 1) / p.N) return;   // tile lies wholly in off-diagonal blocks
-  stage_scaled(sr, li, ni, p.X, p.N, M, ls, L, (long)ti * GT);
-  stage_scaled(sc, lj, nj, p.X, p.N, M, ls, L, (long)tj * GT);
+  const int Nz = p.Nz ? p.Nz[z] : p.N;
+  const double* X = p.X + (long)z * p.stride_X;
+  if (p.diag_blocks_only && ((long)ti * GT) / Nz > ((long)tj * GT + GT - 1) / Nz) return;   // tile lies wholly in off-diagonal blocks
+  if ((long)tj * GT >= (long)L * Nz) return;                                                 // columns are all padding (smaller fold of a batch)
+  stage_scaled(sr, li, ni, X, Nz, M, ls, L, (long)ti * GT);
+  stage_scaled(sc, lj, nj, X, Nz, M, ls, L, (long)tj * GT);
   for (int r = threadIdx.x; r < GT; r += GTHREADS) {
     ar[r] = alpha[(long)ti * GT + r];
     ac[r] = alpha[(long)tj * GT + r];

@@ -17,6 +17,8 @@ struct GramArgs {
   int lower_only;                      // only 64-tiles on or below the diagonal
   int pad_identity;                    // padding gets the identity (square factorisation input) instead of zeros
   int strip;                           // set by gram(): 64-column tiles per CTA (1 for small problems, 4 once the grid exceeds a few waves)
+  long stride_X;                       // problems with their OWN inputs (folds): problem z reads X + z*stride_X (X2 likewise); 0 = shared
+  const int* Nz;                       // device array of per-problem sample counts (<= N) or nullptr = N for all; rows >= L*Nz[z] are padding
 };
 int gram(const GramArgs& a, int batch, cudaStream_t st);
 
@@ -33,6 +35,8 @@ struct GradArgs {
   int with_ls;
   int diag_blocks_only;                          // Kinv holds only the tiles that intersect the diagonal (l,l) blocks: restrict the sums to l_i == l_j
   int nvals, slots;                              // filled in by grad_reduce
+  long stride_X;                                 // per-problem inputs (folds): X + z*stride_X; 0 = shared
+  const int* Nz;                                 // device array of per-problem sample counts or nullptr
 };
 int grad_nvals(int L, int M);   // layout: SF (L*L), SE (L*L), dls row part (L*M), dls column part (L*M)
 size_t grad_workspace_bytes(int n_pad, int L, int M, int batch);

@@ -53,6 +53,9 @@ _SIGNATURES = {
     'rc_lml_grad': (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
                                    c_double_p, c_double_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, c_double_p, ctypes.c_void_p,
                                    ctypes.c_void_p]),
+    'rc_lml_grad_multi': (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
+                                         c_double_p, c_double_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, c_double_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]),
     'rc_predict_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     'rc_predict_reduce': (ctypes.c_int, [c_double_p, ctypes.c_long, ctypes.c_long, c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_void_p, c_double_p, c_double_p,
@@ -336,6 +339,40 @@ class LmlGradPlan:
             res.append({'lml': float(row[0]), 'dF': row[1:1 + L * L].reshape(L, L), 'dE': row[1 + L * L:1 + 2 * L * L].reshape(L, L),
                         'dls': row[1 + 2 * L * L:].reshape(L, M)})
         return res
+
+
+class LmlGradMultiPlan:
+    """LML(+gradient) of `batch` problems that do not share their data (folds, or any set of independent small GPs) in ONE call:
+    rc_lml_grad_multi.  Xs[z] (N_z, M), Ys[z] (N_z, L) are packed once into (batch, Nmax, .) device buffers; every call takes the
+    hyper-parameters of all problems: ls (batch*L, M), F, E (batch, L, L).  Result layout as LmlGradPlan."""
+
+    def __init__(self, Xs: Sequence[torch.Tensor], Ys: Sequence[torch.Tensor], L: int, flags: int):
+        self.batch, self.L, self.flags = len(Xs), L, flags
+        self.M = Xs[0].shape[1]
+        self.Ns = [int(x.shape[0]) for x in Xs]
+        self.Nmax = max(self.Ns)
+        device = Xs[0].device
+        self.X = torch.zeros((self.batch, self.Nmax, self.M), dtype=torch.float64, device=device)
+        self.Y = torch.zeros((self.batch, self.Nmax, L), dtype=torch.float64, device=device)
+        for z, (x, y) in enumerate(zip(Xs, Ys)):
+            assert x.shape[1] == self.M and tuple(y.shape) == (x.shape[0], L)
+            self.X[z, :x.shape[0]].copy_(x)
+            self.Y[z, :x.shape[0]].copy_(y)
+        self.Ns_dev = torch.tensor(self.Ns, dtype=torch.int32, device=device)
+        self.stride = int(lib().rc_lml_grad_stride(L, self.M))
+        self.nbytes = int(lib().rc_lml_grad_bufsize(self.Nmax, self.M, L, self.batch, flags))
+        self.work = workspace(self.nbytes, device)
+        self.out = torch.empty((self.batch, self.stride), dtype=torch.float64, device=device)
+        self.info = torch.zeros(self.batch, dtype=torch.int32, device=device)
+
+    def __call__(self, ls: torch.Tensor, F: torch.Tensor, E: torch.Tensor) -> torch.Tensor:
+        ls, F, E = ls.reshape(self.batch * self.L, self.M).contiguous(), F.reshape(self.batch, self.L, self.L).contiguous(), \
+            E.reshape(self.batch, self.L, self.L).contiguous()
+        check(lib().rc_lml_grad_multi(ptr(self.X), ptr(self.Y), raw_ptr(self.Ns_dev), self.Nmax, self.M, self.L, self.batch, ptr(ls), ptr(F), ptr(E),
+                                      self.flags, raw_ptr(self.work), self.nbytes, ptr(self.out), raw_ptr(self.info), stream_ptr()), 'rc_lml_grad_multi')
+        return self.out
+
+    unpack = LmlGradPlan.unpack
 
 
 def predict_reduce(A: torch.Tensor, a: torch.Tensor, L: int, nstar: int, kdiag: torch.Tensor, noise: Optional[torch.Tensor]):

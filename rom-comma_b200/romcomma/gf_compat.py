@@ -18,7 +18,7 @@ import numpy as np
 import scipy.optimize
 import torch
 
-from romcomma import _capi
+from romcomma import _capi, lockstep
 from romcomma._tensors import DeviceTensor, HostTensor, as_device
 
 
@@ -231,8 +231,12 @@ class _GPR(Module):
         return self._plans[flags]
 
     def _evaluate(self, flags: int) -> dict:
-        plan = self._plan(flags)
         M = self._Xd.shape[1]
+        broker = lockstep.current()
+        if broker is not None:     # a lock-step session: this evaluation joins the batch of the optimisers running beside this one
+            return broker.evaluate(self, self._Xd, self._Yd, 1, flags, self.kernel._ls_row(M), np.reshape(self.kernel.variance.numpy(), (1, 1)),
+                                   np.reshape(self.likelihood.variance.numpy(), (1, 1)))
+        plan = self._plan(flags)
         out = plan(_capi.dev(self.kernel._ls_row(M)), _capi.dev(np.reshape(self.kernel.variance.numpy(), (1, 1, 1))),
                    _capi.dev(np.reshape(self.likelihood.variance.numpy(), (1, 1, 1))))
         host = out.cpu().numpy()
@@ -351,7 +355,8 @@ class _Scipy:
             def callback(x):
                 step_callback(counter[0], variables, [x])
                 counter[0] += 1
-        result = scipy.optimize.minimize(fun, x0, jac=True, method=method, callback=callback, **scipy_kwargs)
+        with lockstep.participating():      # inside lockstep.run_together: the evaluations of concurrently running fits are batched
+            result = scipy.optimize.minimize(fun, x0, jac=True, method=method, callback=callback, **scipy_kwargs)
         unpack(result.x)
         return result
 

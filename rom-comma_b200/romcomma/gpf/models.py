@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 import romcomma.gpf as mf
-from romcomma import _capi
+from romcomma import _capi, lockstep
 from romcomma import gf_compat as gf
 from romcomma._tensors import DeviceTensor, HostTensor, as_device
 
@@ -89,6 +89,10 @@ class MOGPR(gf.Module):
         return plan(ls, F, E)
 
     def _evaluate(self, flags: int) -> dict:
+        broker = lockstep.current()
+        if broker is not None:     # a lock-step session (folds fitted side by side): join the batch; the selected inverse is a batch-of-one path
+            return broker.evaluate(self, self._X, self._Yd, self._L, flags & ~_capi.RC_GRAD_F_DIAGONAL, np.broadcast_to(self.kernel.lengthscales_neat.numpy(), (self._L, self._M)),
+                                   self.kernel.variance.value.numpy(), self.likelihood.variance.value.numpy())
         out = self._evaluate_device(flags).cpu().numpy()
         plan = self._plan(flags)
         if int(plan.info.cpu()[0]) != 0:

@@ -10,7 +10,7 @@ from romcomma.base.definitions import *
 from romcomma.data.storage import Fold, Frame
 from romcomma.base.classes import Data, Model
 from romcomma.gpr.kernels import Kernel
-from romcomma import _capi
+from romcomma import _capi, lockstep
 from romcomma._tensors import DeviceTensor, as_device
 
 
@@ -238,8 +238,11 @@ class MOGP(GPR):
         meta.update(kwargs)
         meta.pop('result', None)
         opt = gf.optimizers.Scipy()
-        results = tuple(opt.minimize(closure=gp.training_loss, variables=gp.trainable_variables, method=method, options=meta)
-                        for gp in self._implementation)
+        # The reference fits the L single-output GPs of a variant model one after another (gpr/models.py:359-361); they are independent, so here
+        # they run side by side and every L-BFGS-B iteration evaluates all of them in one batched launch (romcomma.lockstep).  Same optimiser,
+        # same trajectories, same result tuple.
+        results = tuple(lockstep.run_together([(lambda gp=gp: opt.minimize(closure=gp.training_loss, variables=gp.trainable_variables, method=method,
+                                                                            options=dict(meta))) for gp in self._implementation]))
         meta.update({'result': str(results), 'kernel': kernel_options, 'likelihood': likelihood_options})
         self.write_meta(meta)
         gps = self._implementation
@@ -251,6 +254,8 @@ class MOGP(GPR):
                                           log_marginal=tuple(float(gp.log_marginal_likelihood()) for gp in gps))
             self._kernel.data.replace(variance=tuple(float(gp.kernel.variance.numpy()) for gp in gps),
                                       lengthscales=tuple(np.atleast_1d(gp.kernel.lengthscales.numpy()) for gp in gps))
+        for gp in gps:            # the optimiser's workspaces (one or two n_pad^2 matrices per model) are not needed once the fit is recorded
+            gp._plans.clear()
         return meta
 
     # -- device-side views of the hyper-parameters -----------------------------------------------------------------
@@ -259,8 +264,9 @@ class MOGP(GPR):
         gps = self._implementation
         if self._likelihood.is_covariant:
             gp = gps[0]
-            return gp.kernel._ls_device(self._M), gp.kernel.variance.value.numpy()[None], gp.likelihood.variance.value.numpy()[None], self._L, 1
-        ls = np.concatenate([gp.kernel._ls_row(self._M) for gp in gps], axis=0)
+            self._ls_host = np.ascontiguousarray(np.broadcast_to(gp.kernel.lengthscales_neat.numpy(), (self._L, self._M)))
+            return _capi.dev(self._ls_host), gp.kernel.variance.value.numpy()[None], gp.likelihood.variance.value.numpy()[None], self._L, 1
+        ls = self._ls_host = np.concatenate([gp.kernel._ls_row(self._M) for gp in gps], axis=0)
         F = np.array([float(gp.kernel.variance.numpy()) for gp in gps]).reshape(-1, 1, 1)
         E = np.array([float(gp.likelihood.variance.numpy()) for gp in gps]).reshape(-1, 1, 1)
         return _capi.dev(ls), F, E, 1, self._L
@@ -273,7 +279,7 @@ class MOGP(GPR):
         fitted GP share one factor (same numbers: it is the same deterministic computation, done once).  The factor is read-only for
         its users; ``calibrate`` drops it before the optimiser allocates its own workspace."""
         ls, F, E, L, batch = self._hyper()
-        key = (ls.cpu().numpy().tobytes(), np.ascontiguousarray(F).tobytes(), np.ascontiguousarray(E).tobytes())
+        key = (self._ls_host.tobytes(), np.ascontiguousarray(F).tobytes(), np.ascontiguousarray(E).tobytes())   # host copies: no device sync for a cache key
         cached = getattr(self, '_fac_cache', None)
         if cached is not None and cached[0] == key:
             return cached[1], L, batch

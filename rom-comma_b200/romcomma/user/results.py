@@ -48,7 +48,7 @@ class Collect:
     def from_folds(self, dst: Repository, is_existing_deleted=False, **kwargs: Any) -> 'Collect':
         if isinstance(dst, Fold):
             raise NotADirectoryError('dst is a Fold, which cannot contain other Folds, so cannot be Collected from.')
-        folds = tuple(Fold(dst, k) for k in dst.folds)
+        folds = tuple(Fold(dst, k, init_mode=Repository._InitMode.READ_META_ONLY) for k in dst.folds)    # fold number and N: meta.json, not the data
         for sub_folder, extra_columns in self.folders.items():
             folders = {fold.folder / sub_folder: {'fold': fold.meta['k'], 'N': fold.N} | extra_columns for fold in folds}
             Collect(self.csvs, folders, self.ignore_missing).from_folders(dst.folder / sub_folder, is_existing_deleted, **kwargs)

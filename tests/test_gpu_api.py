@@ -277,10 +277,39 @@ def test_installation_test_flow_not_partial(tmp_path):
         per_slice = [ref.marginalize(s) for s in sobol.m_slices(int(kind), 7)]
         W_scale, Q_scale = (np.stack([r[key] for r in per_slice], axis=-1) for key in ('W_scale', 'Q_scale'))
         err = np.abs(got['W'] - want['W'])
-        assert np.all(err <= 1e-7 * W_scale), f'{kind.name} W: worst err/terms {np.max(err / W_scale):.2e}'
+        assert np.all(err <= 1e-7 * W_scale + 1e-10), f'{kind.name} W: worst err/terms {np.max(err / W_scale):.2e}'      # + 1e-10: the empty slice [M:M] of TOTAL is (sum c)^2 - ... = cancellation noise of mean-centred coefficients
         V4 = ref.V[4][..., None]
         T_slices = (got['T'][..., :-1] - got['T'][..., -1:]) if kind == GSA.Kind.TOTAL else got['T'][..., :-1]      # models.py:212 adds the full-model T
         T_want = (want['T'][..., :-1] - want['T'][..., -1:]) if kind == GSA.Kind.TOTAL else want['T'][..., :-1]
         err = np.abs(T_slices ** 2 - T_want ** 2) * V4
-        assert np.all(err <= 1e-7 * Q_scale), f'{kind.name} |Q_m|: worst err/terms {np.max(err / Q_scale):.2e}'
+        assert np.all(err <= 1e-7 * Q_scale + 1e-10), f'{kind.name} |Q_m|: worst err/terms {np.max(err / Q_scale):.2e}'
         assert_close(T_csv, got['T'], rtol=0, atol=6e-7, what=f'{kind.name} T.csv holds the computed T to 6 decimals')
+
+
+def test_lockstep_fits_equal_sequential_fits(small_repo, monkeypatch):
+    """Folds (and the outputs of a variant GP) fitted side by side with batched evaluations (romcomma.lockstep) follow the same L-BFGS-B
+    trajectories as the reference's one-after-another loop: identical csv files for the variant model, and the batching really happens."""
+    from romcomma import lockstep
+    from romcomma.user import run
+    repo = small_repo
+    sizes = []
+    original = lockstep.EvaluationBroker._run
+
+    def spy(self, key, group):
+        sizes.append(len(group))
+        return original(self, key, group)
+    monkeypatch.setattr(lockstep.EvaluationBroker, '_run', spy)
+    names = run.gpr('together', repo, is_read=False, is_covariant=None, is_isotropic=False, maxiter=30)
+    assert names == ['together.v.a', 'together.c.a']
+    assert max(sizes) >= 4, f'3 folds x 2 outputs should share launches, batch sizes seen: {sorted(set(sizes))}'
+    monkeypatch.setenv('ROMCOMMA_B200_LOCKSTEP', '0')
+    run.gpr('sequential', repo, is_read=False, is_covariant=None, is_isotropic=False, maxiter=30)
+    for k in repo.folds:
+        for model in ('v.a', 'c.a'):
+            for csv in ('kernel/lengthscales.csv', 'kernel/variance.csv', 'likelihood/variance.csv', 'likelihood/log_marginal.csv', 'test.csv'):
+                a = pd.read_csv(repo.fold_folder(k) / f'together.{model}' / csv, index_col=0, header=[0, 1] if csv == 'test.csv' else 0).values
+                b = pd.read_csv(repo.fold_folder(k) / f'sequential.{model}' / csv, index_col=0, header=[0, 1] if csv == 'test.csv' else 0).values
+                if model == 'v.a':
+                    assert np.array_equal(a, b), f'fold {k} {model} {csv}: lock-step and sequential fits differ'
+                else:   # the covariant fit on its own uses the selected inverse (default trainables); in a batch the full inverse: same to rounding
+                    assert_close(a, b, rtol=1e-6, atol=1e-8, what=f'fold {k} {model} {csv}')

@@ -535,3 +535,35 @@ def test_sobol_lattice_form_all_subsets(C, N, M, L, diag):
         assert_close(Vo[k], want, rtol=1e-9, atol=1e-12 * scale, what=f'list entry {k} (mask {mask})')
     parts = sum(C.sobol_contract(dX, Phi, g0KY, L, diag, every, None, r, 3).cpu().numpy() for r in range(3))
     assert_close(parts, V, rtol=1e-10, atol=1e-12 * scale, what='row-tile parts add up (lattice form)')
+
+
+@pytest.mark.parametrize('L', [1, 2])
+def test_lml_grad_multi_independent_problems(C, L):
+    """rc_lml_grad_multi: problems with their OWN inputs, outputs and sample counts (folds) in one batched call.  Problems of equal padded size
+    are computed exactly as on their own (identical bits to rc_lml_grad on that problem); a smaller problem padded up to the largest one agrees
+    to rounding; all against the oracle."""
+    M = 4
+    Ns = [250, 256, 231, 120]                         # padded sizes (L = 1): 256, 256, 256, 128 -> the last one is padded up to 256 in the batch
+    probs = [random_problem(N, M, L, seed=40 + N, full_E=False) for N in Ns]
+    flags = C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES
+    plan = C.LmlGradMultiPlan([C.dev(p[0]) for p in probs], [C.dev(p[1]) for p in probs], L, flags)
+    ls = np.concatenate([p[2] for p in probs], axis=0)
+    F, E = np.stack([p[3] for p in probs]), np.stack([p[4] for p in probs])
+    out = plan(C.dev(ls), C.dev(F), C.dev(E)).cpu().numpy().copy()
+    assert plan.info.cpu().tolist() == [0] * len(Ns)
+    res = plan.unpack(out)
+    for z, (X, Y, lsz, Fz, Ez) in enumerate(probs):
+        ref = gp.lml_grad_mo(X, Y, lsz, Fz, Ez)
+        assert_close(res[z]['lml'], ref['lml'], what=f'lml[{z}]')
+        for k in ('dF', 'dE', 'dls'):
+            assert_close(res[z][k], ref[k], atol=1e-10 * L * Ns[z], what=f'{k}[{z}]')
+        single = C.LmlGradPlan(C.dev(X), C.dev(Y), L, 1, flags)
+        alone = single(C.dev(lsz), C.dev(Fz[None]), C.dev(Ez[None])).cpu().numpy()[0]
+        if C.padded(L * Ns[z]) == C.padded(L * max(Ns)):
+            assert np.array_equal(out[z], alone), f'problem {z}: batched and single evaluation differ in bits'
+        else:
+            assert_close(out[z], alone, rtol=1e-9, atol=1e-9, what=f'problem {z} padded up')
+    # value only
+    plan0 = C.LmlGradMultiPlan([C.dev(p[0]) for p in probs], [C.dev(p[1]) for p in probs], L, C.RC_GRAD_NONE)
+    v = plan0(C.dev(ls), C.dev(F), C.dev(E)).cpu().numpy()[:, 0]
+    assert_close(v, [r['lml'] for r in res], rtol=1e-12, what='value-only call')

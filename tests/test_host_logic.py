@@ -268,3 +268,90 @@ def test_exp_pairwise_polynomial_constants():
     lo = -float(re.search(r'fma\(k, (-[0-9.e+-]+), r\)', body).group(1))
     assert (int(np.float64(hi).view(np.uint64)) & ((1 << 21) - 1)) == 0
     assert abs((np.longdouble(hi) + np.longdouble(lo)) - np.log(np.longdouble(2))) < 1e-18
+
+
+def test_run_stages_follow_the_reference_hierarchy():
+    """user.run flattens the (variant|covariant) x (isotropic|anisotropic) recursion of the reference (user/run.py:66-75) into an ordered list."""
+    from romcomma.user.run import Stage, stages
+    name = lambda plan: [s.model_name('gpr') for s in plan]
+    assert name(stages(False, None, None)) == ['gpr.v.i', 'gpr.v.a', 'gpr.c.a']
+    assert [s.is_read for s in stages(False, None, None)] == [False, None, None]
+    assert name(stages(True, None, False)) == ['gpr.v.a', 'gpr.c.a'] and [s.is_read for s in stages(True, None, False)] == [True, None]
+    assert name(stages(None, None, True)) == ['gpr.v.i', 'gpr.c.i']
+    assert name(stages(False, True, None)) == ['gpr.c.i', 'gpr.c.a'] and name(stages(False, False, False)) == ['gpr.v.a']
+    assert stages(None, True, False) == [Stage(True, False, None)]
+
+
+def test_run_seeds_a_model_from_its_nearest_ancestor(tmp_path):
+    """is_read=None (user/run.py:76-86): an existing folder is kept; a covariant model copies the variant one of the same isotropy, else the
+    isotropic one of the same covariance; without an ancestor the model starts from the defaults."""
+    from types import SimpleNamespace
+    from romcomma.user.run import Stage, _seed_from_ancestor
+    fold = SimpleNamespace(folder=tmp_path)
+    assert _seed_from_ancestor(fold, 'gpr', Stage(False, True, None)) is False            # nothing there: defaults
+    (tmp_path / 'gpr.v.i').mkdir()
+    (tmp_path / 'gpr.v.i' / 'kernel').mkdir()
+    (tmp_path / 'gpr.v.i' / 'kernel' / 'variance.csv').write_text('v.i')
+    assert _seed_from_ancestor(fold, 'gpr', Stage(False, False, None)) is True            # v.a <- v.i
+    assert (tmp_path / 'gpr.v.a' / 'kernel' / 'variance.csv').read_text() == 'v.i'
+    (tmp_path / 'gpr.v.a' / 'kernel' / 'variance.csv').write_text('v.a')
+    assert _seed_from_ancestor(fold, 'gpr', Stage(True, False, None)) is True             # c.a <- v.a (same isotropy) before c.i
+    assert (tmp_path / 'gpr.c.a' / 'kernel' / 'variance.csv').read_text() == 'v.a'
+    (tmp_path / 'gpr.c.a' / 'kernel' / 'variance.csv').write_text('kept')
+    assert _seed_from_ancestor(fold, 'gpr', Stage(True, False, None)) is True and (tmp_path / 'gpr.c.a' / 'kernel' / 'variance.csv').read_text() == 'kept'
+
+
+def test_lockstep_broker_batches_concurrent_optimisers(monkeypatch):
+    """romcomma.lockstep: optimiser threads that run side by side get their evaluations in ONE batched call per lock step, each follows the
+    trajectory it has alone, a thread that finishes early does not stall the others, and an error reaches the thread it belongs to."""
+    import scipy.optimize
+    import torch
+    from romcomma import _capi, lockstep
+    calls = []
+
+    class FakePlan:                                   # stands in for rc_lml_grad_multi: "lml" = -|ls - Y[0]|^2, "dls" its gradient
+        def __init__(self, Xs, Ys, L, flags):
+            self.targets = [x[0].numpy().copy() for x in Xs]
+            self.info = torch.zeros(len(Xs), dtype=torch.int32)
+
+        def __call__(self, ls, F, E):
+            calls.append(ls.shape[0])
+            self.ls = ls.numpy().copy()
+            self.info.zero_()
+            for z in range(len(self.targets)):
+                if self.ls[z, 0] > 1e6:
+                    self.info[z] = 3
+            return torch.zeros(len(self.targets), 1)
+
+        def unpack(self, out):
+            return [{'lml': -float(np.sum((x - t) ** 2)), 'dls': -2.0 * (x - t)[None]} for x, t in zip(self.ls, self.targets)]
+
+    monkeypatch.setattr(_capi, 'LmlGradMultiPlan', FakePlan)
+
+    def fit(target, x0, poison=False):
+        X, Y = torch.as_tensor(target)[None].repeat(10, 1), torch.zeros(10, 1)
+        model = object()
+
+        def fun(x):
+            broker = lockstep.current()
+            if broker is None:                        # no session (a single job): the model's own, unbatched evaluation
+                calls.append(1)
+                return float(np.sum((x - target) ** 2)), 2.0 * (x - target)
+            res = broker.evaluate(model, X, Y, 1, 0, (x * (1e9 if poison else 1.0))[None], np.eye(1), np.eye(1))
+            return -res['lml'], -res['dls'].reshape(-1)
+        with lockstep.participating():
+            return scipy.optimize.minimize(fun, x0, jac=True, method='L-BFGS-B', options={'maxiter': 50})
+
+    rng = np.random.default_rng(0)
+    targets = [rng.normal(size=3) * (k + 1) for k in range(5)]
+    starts = [rng.normal(size=3) * 10 ** k for k in range(5)]              # different scales: different iteration counts
+    alone = [lockstep.run_together([lambda t=t, s=s: fit(t, s)])[0] for t, s in zip(targets, starts)]       # one job each: no session, no threads
+    assert all(c == 1 for c in calls)
+    n_alone = len(calls)
+    together = lockstep.run_together([(lambda t=t, s=s: fit(t, s)) for t, s in zip(targets, starts)])
+    for a, b, t in zip(alone, together, targets):
+        assert np.array_equal(a.x, b.x) and a.nfev == b.nfev and np.allclose(b.x, t, atol=1e-6)
+    batched = calls[n_alone:]
+    assert max(batched) >= 2 and len(batched) < n_alone, 'optimisers that run side by side must share launches (how many at a time depends on thread timing)'
+    with pytest.raises(_capi.RomcommaB200Error):                         # a failed Cholesky in one problem raises in that thread, the others finish
+        lockstep.run_together([lambda: fit(targets[0], starts[0]), lambda: fit(targets[1], starts[1], poison=True)])
