@@ -138,6 +138,23 @@ size_t rc_predict_bufsize(int c_pad, int batch);
 int rc_predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n_pad, int c_pad, int batch, int L, int nstar,
                       const double* kdiag, const double* noise, void* parts, double* mean, double* var, rc_stream_t stream);
 
+/* C = alpha * A^T A + beta * C for an n_pad x c_pad block A (row-major; both multiples of 128), all of the c_pad x c_pad result, on the FP64
+ * tensor-core tile kernel: the A^T A of the FULL predictive covariance Knn - A^T A of gpflow base_conditional (MOGPR.predict_f with full_cov /
+ * full_output_cov, romcomma/gpf/models.py:94-109) and the -W^T W of MOGP.predict_gradient (romcomma/gpr/models.py:408-411). */
+int rc_syrk_tn(const double* A, int n_pad, int c_pad, long lda, long strideA, int batch, double alpha, double beta, double* C, long ldc, long strideC,
+               rc_stream_t stream);
+
+/* ---- the gradient GP dy/dx (MOGP.predict_gradient, romcomma/gpr/models.py:386-415; variant GPs: batch = L problems) ----------------------
+ * rc_predict_gradient_jacobian: B[z][n][j*M+m] = d k_z(X_n, x_j)/d x_jm (:395-398) - B is (batch, n_pad, ldb) and must be zeroed by the caller where
+ * it is padding - and mean[j][z][m] = sum_n B[z][n][j*M+m] KinvY[z][n] (:399).  ls (batch, M), variance (batch), KinvY (batch, N), xs (o, M).
+ * Then W = K_cho^-1 B (rc_trsm_fwd), C = -W^T W (rc_syrk_tn, alpha = -1, beta = 0) and
+ * rc_predict_gradient_finish: var[O][j][z][Mi][m] = C[z][O*M+Mi][j*M+m] + [Mi == m] k_z(x_O, x_j)/ls[z][Mi]^2 (:400-414; the reference's own
+ * expression, which fills only the Mi == m diagonal of the prior term). */
+int rc_predict_gradient_jacobian(const double* X, int N, int M, const double* xs, int o, const double* ls, const double* variance, const double* KinvY,
+                                 int batch, double* B, long ldb, long strideB, double* mean, rc_stream_t stream);
+int rc_predict_gradient_finish(const double* C, long ldc, long strideC, const double* xs, int o, int M, const double* ls, const double* variance,
+                               int batch, double* var, rc_stream_t stream);
+
 /* ---- Sobol ---------------------------------------------------------------------------------------------------------
  * rc_sobol_prepare: Phi, g0, g0KY (mean-centred) of ClosedSobol._calibrate / _Lambda2 (romcomma/gsa/calibrators.py:82-92,99-109,
  * 134-138).  P = L (is_F_diagonal) or L*L.  Lam (L,M); F (L) if diagonal else (L,L); KinvY (L,N).  Outputs Phi (P,M), g0 (P,N),

@@ -362,6 +362,26 @@ int rc_predict_reduce(const double* A, long lda, long strideA, const double* a, 
                         (cudaStream_t)stream);
 }
 
+int rc_syrk_tn(const double* A, int n_pad, int c_pad, long lda, long strideA, int batch, double alpha, double beta, double* C, long ldc, long strideC,
+               rc_stream_t stream) {
+  RC_REQUIRE(A && C && batch > 0, -2, "rc_syrk_tn: null pointer or empty batch");
+  RC_REQUIRE(lda >= c_pad && ldc >= c_pad && lda % 2 == 0 && ldc % 2 == 0, -2, "rc_syrk_tn: leading dimensions must be even and >= c_pad");
+  return syrk_tn(A, n_pad, c_pad, lda, strideA, batch, alpha, beta, C, ldc, strideC, (cudaStream_t)stream);
+}
+
+int rc_predict_gradient_jacobian(const double* X, int N, int M, const double* xs, int o, const double* ls, const double* variance, const double* KinvY,
+                                 int batch, double* B, long ldb, long strideB, double* mean, rc_stream_t stream) {
+  RC_REQUIRE(X && xs && ls && variance && KinvY && B && mean && N > 0, -2, "rc_predict_gradient_jacobian: null pointer or non-positive size");
+  RC_REQUIRE(ldb >= (long)o * M, -2, "rc_predict_gradient_jacobian: ldb too small");
+  return predict_gradient_jacobian(X, N, M, xs, o, ls, variance, KinvY, batch, B, ldb, strideB, mean, (cudaStream_t)stream);
+}
+
+int rc_predict_gradient_finish(const double* C, long ldc, long strideC, const double* xs, int o, int M, const double* ls, const double* variance,
+                               int batch, double* var, rc_stream_t stream) {
+  RC_REQUIRE(C && xs && ls && variance && var && M > 0, -2, "rc_predict_gradient_finish: null pointer or non-positive size");
+  return predict_gradient_finish(C, ldc, strideC, xs, o, M, ls, variance, batch, var, (cudaStream_t)stream);
+}
+
 size_t rc_sobol_bufsize(int N, int P, int nslices) { return align256(sobol_workspace_bytes(N, P, nslices)); }
 
 int rc_sobol_prepare(const double* X, int N, int M, const double* Lam, const double* F, const double* KinvY, int L, int is_F_diagonal, double* Phi,

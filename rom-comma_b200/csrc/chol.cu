@@ -926,6 +926,17 @@ int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_pa
   return 0;
 }
 
+// C = alpha * A^T A + beta * C for an n x c block A (row-major, both multiples of 128): every 128-tile of the c x c result.
+int syrk_tn(const double* A, int n, int c, long lda, long strideA, int batch, double alpha, double beta, double* C, long ldc, long strideC, cudaStream_t st) {
+  RC_REQUIRE(n > 0 && c > 0 && n % DB == 0 && c % DB == 0, -2, "syrk_tn: n=%d and c=%d must be positive multiples of 128", n, c);
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.strideA = strideA;
+  g.B = A; g.ldb = lda; g.strideB = strideA;
+  g.C = C; g.ldc = ldc; g.strideC = strideC;
+  g.M = g.N = c; g.K = n; g.alpha = alpha; g.beta = beta; g.kmode = K_FULL;
+  return launch_gemm_ws<true, true>(g, batch, st);
+}
+
 // dots[pair(l > l')][i] = sum_{k >= l*N+i} Z[k][l*N+i] * Z[k][l'*N+i] = K^-1[(l,i),(l',i)]: the diagonals of the off-diagonal
 // (l,l') blocks of K^-1 = Z^T Z, which is all of those blocks that dLML/dE needs.  Row-split partial sums, fixed-order finish.
 constexpr int BD_SPLIT = 16;

@@ -36,6 +36,9 @@ int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_pa
 // Kinv(lower 128-tiles) = Z^T Z; sel_block > 0 restricts it to the tiles that intersect the diagonal blocks of that size.
 int lauum_lower(const double* Z, int n, long ld, long strideZ, int batch, double* Kinv, long ldk, long strideK, int sel_block, cudaStream_t st);
 
+// C = alpha * A^T A + beta * C (A: n x c row-major, n and c multiples of 128; all tiles of the c x c result).
+int syrk_tn(const double* A, int n, int c, long lda, long strideA, int batch, double alpha, double beta, double* C, long ldc, long strideC, cudaStream_t st);
+
 // dots[pair(l > l')][i] = K^-1[(l,i),(l',i)] from Z = L^-1 (pair index l*(l-1)/2 + l').
 size_t block_diag_dots_workspace_bytes(int N, int L);
 int block_diag_dots(const double* Z, long ld, int n, int N, int L, double* parts, double* dots, cudaStream_t st);

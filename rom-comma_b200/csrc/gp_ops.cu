@@ -429,4 +429,100 @@ int predict_reduce(const double* A, long lda, long strideA, const double* a, lon
   return 0;
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// The gradient GP dy/dx of a variant model (romcomma/gpr/models.py:386-415).
+//   J_z[n][j*M+m] = d k_z(X_n, x_j) / d x_jm = v_z exp(-1/2 sum_m' ((X_nm' - x_jm')/ls_zm')^2) (X_nm - x_jm) / ls_zm^2      (:395-398)
+//   mean[j][z][m]  = sum_n J_z[n][j*M+m] KiY[z][n]                                                                           (:399)
+// then W = K_cho^-1 J (rc_trsm_fwd), C = -W^T W (rc_syrk_tn) and
+//   var[O][j][z][Mi][m] = C_z[O*M+Mi][j*M+m] + [Mi == m] k_z(x_O, x_j) / ls_zMi^2                                            (:400-414)
+// One CTA per (test point j, output z): the threads walk the N training points, write the M Jacobian entries of each and reduce the mean.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int PG_MAXM = 64;
+
+__global__ void __launch_bounds__(256) predict_gradient_jacobian_kernel(const double* __restrict__ X, int N, int M, const double* __restrict__ xs, int o,
+                                                                         const double* __restrict__ ls, const double* __restrict__ variance,
+                                                                         const double* __restrict__ KiY, double* __restrict__ B, long ldb, long strideB,
+                                                                         double* __restrict__ mean, int batch) {
+  __shared__ double xj[PG_MAXM], il2[PG_MAXM], red[32];
+  const int j = blockIdx.x, z = blockIdx.y;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const double l = ls[(long)z * M + m];
+    xj[m] = xs[(long)j * M + m];
+    il2[m] = 1.0 / (l * l);
+  }
+  __syncthreads();
+  const double v = variance[z];
+  double* Bz = B + (long)z * strideB + (long)j * M;
+  double acc[PG_MAXM / 8];                      // the mean is reduced 8 inputs at a time (registers)
+  for (int m0 = 0; m0 < M; m0 += 8) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const double* xn = X + (long)n * M;
+      double r2 = 0.0;
+      for (int m = 0; m < M; ++m) {
+        const double d = xn[m] - xj[m];
+        r2 = fma(d * d, il2[m], r2);
+      }
+      const double k = v * exp_pairwise(-0.5 * r2), a = KiY[(long)z * N + n];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (m0 + q < M) {
+          const double jac = k * (xn[m0 + q] - xj[m0 + q]) * il2[m0 + q];
+          Bz[(long)n * ldb + m0 + q] = jac;
+          acc[q] = fma(jac, a, acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double t = block_sum(acc[q], red);
+      if (threadIdx.x == 0 && m0 + q < M) mean[((long)j * batch + z) * M + m0 + q] = t;
+    }
+  }
+}
+
+__global__ void predict_gradient_finish_kernel(const double* __restrict__ C, long ldc, long strideC, const double* __restrict__ xs, int o, int M,
+                                               const double* __restrict__ ls, const double* __restrict__ variance, int batch,
+                                               double* __restrict__ var) {
+  const int O = blockIdx.x, j = blockIdx.y, z = blockIdx.z;
+  __shared__ double kxx;
+  if (threadIdx.x == 0) {
+    double r2 = 0.0;
+    for (int m = 0; m < M; ++m) {
+      const double d = (xs[(long)O * M + m] - xs[(long)j * M + m]) / ls[(long)z * M + m];
+      r2 = fma(d, d, r2);
+    }
+    kxx = variance[z] * exp_pairwise(-0.5 * r2);
+  }
+  __syncthreads();
+  const double* Cz = C + (long)z * strideC;
+  double* out = var + ((((long)O * o + j) * batch + z) * M) * M;
+  for (int e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const int Mi = e / M, m = e - Mi * M;
+    double val = Cz[((long)O * M + Mi) * ldc + (long)j * M + m];
+    if (Mi == m) {
+      const double l = ls[(long)z * M + Mi];
+      val += kxx / (l * l);
+    }
+    out[e] = val;
+  }
+}
+
+int predict_gradient_jacobian(const double* X, int N, int M, const double* xs, int o, const double* ls, const double* variance, const double* KiY,
+                              int batch, double* B, long ldb, long strideB, double* mean, cudaStream_t st) {
+  RC_REQUIRE(M >= 1 && M <= PG_MAXM, -2, "predict_gradient: M=%d out of range [1,%d]", M, PG_MAXM);
+  RC_REQUIRE(o >= 1 && o <= 65535 && batch >= 1 && batch <= 65535, -2, "predict_gradient: %d test points / %d outputs exceed the grid limits", o, batch);
+  predict_gradient_jacobian_kernel<<<dim3(o, batch), 256, 0, st>>>(X, N, M, xs, o, ls, variance, KiY, B, ldb, strideB, mean, batch);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
+int predict_gradient_finish(const double* C, long ldc, long strideC, const double* xs, int o, int M, const double* ls, const double* variance, int batch,
+                            double* var, cudaStream_t st) {
+  RC_REQUIRE(o >= 1 && o <= 65535 && batch >= 1 && batch <= 65535, -2, "predict_gradient: %d test points / %d outputs exceed the grid limits", o, batch);
+  predict_gradient_finish_kernel<<<dim3(o, o, batch), 64, 0, st>>>(C, ldc, strideC, xs, o, M, ls, variance, batch, var);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace rc

@@ -46,4 +46,11 @@ size_t predict_workspace_bytes(int c_pad, int batch);
 int predict_reduce(const double* A, long lda, long strideA, const double* a, long stride_a, int n, int c_pad, int batch, int L, int nstar,
                    const double* kdiag, const double* noise, double* parts, double* mean, double* var, cudaStream_t st);
 
+// The gradient GP of a variant model (gpr/models.py:386-415): Jacobian of k(X, x) into the zero-padded right-hand sides B (batch, n_pad, c_pad),
+// c = j*M + m, plus the mean; and the final assembly of the (o, o, batch, M, M) covariance from C = -W^T W.
+int predict_gradient_jacobian(const double* X, int N, int M, const double* xs, int o, const double* ls, const double* variance, const double* KiY,
+                              int batch, double* B, long ldb, long strideB, double* mean, cudaStream_t st);
+int predict_gradient_finish(const double* C, long ldc, long strideC, const double* xs, int o, int M, const double* ls, const double* variance, int batch,
+                            double* var, cudaStream_t st);
+
 }  // namespace rc

@@ -60,6 +60,12 @@ _SIGNATURES = {
     'rc_predict_reduce': (ctypes.c_int, [c_double_p, ctypes.c_long, ctypes.c_long, c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_void_p, c_double_p, c_double_p,
                                          ctypes.c_void_p]),
+    'rc_syrk_tn': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                  c_double_p, ctypes.c_long, ctypes.c_long, ctypes.c_void_p]),
+    'rc_predict_gradient_jacobian': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p, c_double_p, c_double_p,
+                                                    ctypes.c_int, c_double_p, ctypes.c_long, ctypes.c_long, c_double_p, ctypes.c_void_p]),
+    'rc_predict_gradient_finish': (ctypes.c_int, [c_double_p, ctypes.c_long, ctypes.c_long, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
+                                                  ctypes.c_int, c_double_p, ctypes.c_void_p]),
     'rc_sobol_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'rc_sobol_prepare': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int,
                                         c_double_p, c_double_p, c_double_p, ctypes.c_void_p]),
@@ -368,6 +374,7 @@ class LmlGradMultiPlan:
     def __call__(self, ls: torch.Tensor, F: torch.Tensor, E: torch.Tensor) -> torch.Tensor:
         ls, F, E = ls.reshape(self.batch * self.L, self.M).contiguous(), F.reshape(self.batch, self.L, self.L).contiguous(), \
             E.reshape(self.batch, self.L, self.L).contiguous()
+        self._hold = (ls, F, E)       # read by the kernels until the evaluation ends - possibly on another stream than the one they were made on
         check(lib().rc_lml_grad_multi(ptr(self.X), ptr(self.Y), raw_ptr(self.Ns_dev), self.Nmax, self.M, self.L, self.batch, ptr(ls), ptr(F), ptr(E),
                                       self.flags, raw_ptr(self.work), self.nbytes, ptr(self.out), raw_ptr(self.info), stream_ptr()), 'rc_lml_grad_multi')
         return self.out
@@ -383,6 +390,34 @@ def predict_reduce(A: torch.Tensor, a: torch.Tensor, L: int, nstar: int, kdiag: 
     var = torch.empty_like(mean)
     check(lib().rc_predict_reduce(ptr(A), c_pad, n_pad * c_pad, ptr(a), n_pad, n_pad, c_pad, b, L, nstar, ptr(kdiag), ptr(noise), raw_ptr(parts),
                                   ptr(mean), ptr(var), stream_ptr()), 'rc_predict_reduce')
+    return mean, var
+
+
+def syrk_tn(A: torch.Tensor, alpha: float = 1.0, beta: float = 0.0, C: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = alpha * A^T A + beta * C for A (batch, n_pad, c_pad), both multiples of 128 -> (batch, c_pad, c_pad)."""
+    b, n_pad, c_pad = A.shape
+    if C is None:
+        assert beta == 0.0
+        C = torch.empty((b, c_pad, c_pad), dtype=torch.float64, device=A.device)
+    check(lib().rc_syrk_tn(ptr(A), n_pad, c_pad, c_pad, n_pad * c_pad, b, float(alpha), float(beta), ptr(C), c_pad, c_pad * c_pad, stream_ptr()),
+          'rc_syrk_tn')
+    return C
+
+
+def predict_gradient(X, xs, ls, variance, KinvY, fac: Factorization):
+    """MOGP.predict_gradient of a variant GP (batch = L problems): X (N,M), xs (o,M), ls (L,M), variance (L,), KinvY (L,N) device tensors and the
+    factorisation of the L noisy grams -> mean (o,L,M), var (o,o,L,M,M) on the device."""
+    (N, M), o, L = X.shape, xs.shape[0], ls.shape[0]
+    c_pad = padded(o * M)
+    B = torch.zeros((L, fac.n_pad, c_pad), dtype=torch.float64, device=X.device)
+    mean = torch.empty((o, L, M), dtype=torch.float64, device=X.device)
+    check(lib().rc_predict_gradient_jacobian(ptr(X), N, M, ptr(xs), o, ptr(ls), ptr(variance), ptr(KinvY), L, ptr(B), c_pad, fac.n_pad * c_pad, ptr(mean),
+                                             stream_ptr()), 'rc_predict_gradient_jacobian')
+    fac.trsm_fwd_(B)
+    C = syrk_tn(B, alpha=-1.0)
+    var = torch.empty((o, o, L, M, M), dtype=torch.float64, device=X.device)
+    check(lib().rc_predict_gradient_finish(ptr(C), c_pad, c_pad * c_pad, ptr(xs), o, M, ptr(ls), ptr(variance), L, ptr(var), stream_ptr()),
+          'rc_predict_gradient_finish')
     return mean, var
 
 

@@ -209,29 +209,11 @@ class Repository:
         return self
 
     def rotate_folds(self, rotation: NP.Matrix | None) -> 'Repository':
-        M = self.M
-        if rotation is None:
-            rotation = np.eye(M)
-        elif rotation.shape != (M, M) or not np.allclose(np.dot(rotation, rotation.T), np.eye(M)):
-            rotation = scipy.stats.special_ortho_group.rvs(M)
-        for k in self.folds:
-            Fold(self, k).X_rotation = rotation
+        """ The reference can rotate the input basis of every fold (an OUT-OF-SCOPE data-preparation feature).  Its scripts
+        call this with ``None`` - the identity - which is all that is supported here."""
+        if rotation is not None:
+            raise NotImplementedError('input rotations are not part of the B200 hot path; rotate the data before building the Repository.')
         return self
-
-    def Y_split(self):
-        """ One single-output Repository ``Y.<l>`` per output column."""
-        if isinstance(self, Fold):
-            raise TypeError('Cannot Y_split a Fold, only a Repository.')
-        for l in range(self.L):
-            destination = self.folder / f'Y.{l:d}'
-            columns = list(range(self.M)) + [self.M + l]
-            meta = deepcopy(self._meta)
-            meta['data']['L'] = 1
-            Repository.from_df(destination, self.data.df.iloc[:, columns].copy(), meta)
-
-    @property
-    def Y_splits(self) -> List[Tuple[int, Path]]:
-        return [(int(Y_dir.suffix[1:]), Y_dir) for Y_dir in self.folder.glob('Y.[0-9]*')]
 
     def __repr__(self) -> str:
         return str(self._folder)
@@ -246,7 +228,6 @@ class Fold(Repository):
     def __init__(self, parent: Repository, k: int, **kwargs):
         init_mode = kwargs.get('init_mode', Repository._InitMode.READ)
         super().__init__(parent.fold_folder(k), init_mode=init_mode)
-        self._X_rotation = self.folder / 'X_rotation.csv'
         self._test_csv = self.folder / 'test.csv'
         if init_mode == Repository._InitMode.READ:
             self._test_data = Frame(self._test_csv)
@@ -287,22 +268,6 @@ class Fold(Repository):
     @property
     def test_y(self) -> pd.DataFrame:
         return self._test_data.df[self._meta['data']['Y_heading']]
-
-    def _X_rotate(self, frame: Frame, rotation: NP.Matrix):
-        frame.df.iloc[:, :self.M] = np.einsum('Nm,Mm->NM', frame.df.iloc[:, :self.M], rotation)
-        frame.write()
-
-    @property
-    def X_rotation(self) -> NP.Matrix:
-        """ The cumulative rotation applied to the inputs, stored in X_rotation.csv."""
-        return pd.read_csv(self._X_rotation, index_col=0).values if self._X_rotation.exists() else np.eye(self.M)
-
-    @X_rotation.setter
-    def X_rotation(self, value: NP.Matrix):
-        old_value = self.X_rotation
-        self._X_rotate(self._data, value)
-        self._X_rotate(self._test_data, value)
-        pd.DataFrame(np.matmul(old_value, value)).to_csv(self._X_rotation)
 
 
 class Normalization:
@@ -356,25 +321,21 @@ class Normalization:
         return pd.concat((X, Y), axis=1)
 
     def undo_from(self, df: pd.DataFrame) -> pd.DataFrame:
+        """ The inverse of ``apply_to``: N(0,1) inputs back through the normal cdf onto [min, min + rng], outputs back to mean + std * y."""
         if not self._is_applicable:
             return df
-        X_min, X_rng, Y_mean, Y_std = self._relevant_stats
+        lo, span, centre, spread = (stat.to_numpy(dtype=float) for stat in self._relevant_stats)
         M = self._fold.M
-        X, Y = df.iloc[:, :M].copy(deep=True), df.iloc[:, M:].copy(deep=True)
-        X.iloc[:, :] = scipy.stats.norm.cdf(X.values, loc=0, scale=1) * X_rng.values + X_min.values
-        Y.iloc[:, :] = Y.values * Y_std.values + Y_mean.values
-        return pd.concat((X, Y), axis=1)
+        values = df.to_numpy(dtype=float, copy=True)
+        values[:, :M] = lo + span * scipy.stats.norm.cdf(values[:, :M])
+        values[:, M:] = centre + spread * values[:, M:]
+        return pd.DataFrame(values, index=df.index, columns=df.columns)
 
     def unscale_Y(self, dfY: pd.DataFrame) -> pd.DataFrame:
+        """ Standard deviations of normalised outputs in the units of the raw outputs (a scale, so no shift)."""
         if not self._is_applicable:
             return dfY
-        out = dfY.copy(deep=True)
-        out.iloc[:, :] = dfY.values * self._relevant_stats[3].values
-        return out
-
-    def X_gradient(self, X: NP.Matrix, m: int | List[int]):
-        X_rng = self._relevant_stats[1].values[m]
-        return X_rng * scipy.stats.norm.pdf(X[..., m], loc=0, scale=1) if self._is_applicable else np.ones_like(X[..., m])
+        return dfY * self._relevant_stats[3].to_numpy(dtype=float)
 
     def __repr__(self) -> str:
         return str(self.csv)

@@ -273,9 +273,16 @@ class _GPR(Module):
 
     # -- prediction ------------------------------------------------------------------------------------------------
     def _predict(self, Xnew, full_cov, full_output_cov, y_instead_of_f):
-        if full_cov or full_output_cov:
-            raise NotImplementedError('only marginal predictive variances are computed on this path (as romcomma uses them).')
         M = self._Xd.shape[1]
+        if full_cov or full_output_cov:
+            if y_instead_of_f:       # gpflow GPModel.predict_y (2.5.2) refuses these arguments, see GPflow issue 1461
+                raise NotImplementedError('The predict_y method currently supports only the argument values full_cov=False and full_output_cov=False')
+            Xn = as_device(Xnew)
+            mean, cov = predict_full_core(self._Xd, self._Yd, _capi.dev(self.kernel._ls_row(M)), np.reshape(self.kernel.variance.numpy(), (1, 1, 1)),
+                                          np.reshape(self.likelihood.variance.numpy(), (1, 1, 1)), Xn, 1, 1)
+            # gpflow GPR.predict_f: full_cov -> [1, n, n]; full_output_cov alone -> [n, 1, 1]
+            var = cov if full_cov else torch.diagonal(cov[0]).reshape(-1, 1, 1)
+            return DeviceTensor.wrap(mean[0]), DeviceTensor.wrap(var)
         mean, var = predict_core(self._Xd, self._Yd, _capi.dev(self.kernel._ls_row(M)), np.reshape(self.kernel.variance.numpy(), (1, 1, 1)),
                                  np.reshape(self.likelihood.variance.numpy(), (1, 1, 1)), as_device(Xnew), 1, 1, y_instead_of_f)
         return DeviceTensor.wrap(mean[0]), DeviceTensor.wrap(var[0])
@@ -315,6 +322,41 @@ def predict_core(X, Y, ls, F, E, Xn, L: int, batch: int, y_instead_of_f: bool = 
     kdiag = _capi.dev(np.ascontiguousarray(np.diagonal(F, axis1=1, axis2=2)))
     noise = _capi.dev(np.ascontiguousarray(np.diagonal(E, axis1=1, axis2=2))) if y_instead_of_f else None
     return _capi.predict_reduce(Kmn, alpha, L, nstar, kdiag, noise)
+
+
+def predict_full_core(X, Y, ls, F, E, Xn, L: int, batch: int, fac=None):
+    """Mean (batch, n*, L) and the FULL covariance Knn - A^T A of f at Xn, (batch, L n*, L n*) with index (l, i) -> l n* + i: gpflow
+    ``base_conditional(full_cov=True)`` as MOGPR.predict_f calls it (romcomma/gpf/models.py:97).  A = L^-1 Kmn by rc_trsm_fwd, A^T A on the
+    tensor-core tile kernel (rc_syrk_tn, accumulated straight onto the gram of the new points)."""
+    N, nstar = X.shape[0], Xn.shape[0]
+    n, c = L * N, L * nstar
+    n_pad, c_pad = _capi.padded(n), _capi.padded(c)
+    F, E = np.asarray(F, dtype=np.float64).reshape(batch, L, L), np.asarray(E, dtype=np.float64).reshape(batch, L, L)
+    dF, dE = _capi.dev(F), _capi.dev(E)
+    if fac is None:
+        fac = _capi.Factorization(_capi.gram(X, None, ls, dF, dE, batch=batch, lower_only=True, pad_to=n, pad_identity=True))
+        fac.raise_if_failed()
+    y = torch.zeros((batch, n_pad), dtype=torch.float64, device=X.device)
+    y[:, :n] = Y.reshape(N, batch, L).permute(1, 2, 0).reshape(batch, n)
+    alpha = fac.trsv(y)
+    Kmn = torch.empty((batch, n_pad, c_pad), dtype=torch.float64, device=X.device)
+    _capi.check(_capi.lib().rc_gram(_capi.ptr(X), N, _capi.ptr(Xn), nstar, X.shape[1], _capi.ptr(ls), L, _capi.ptr(dF), None, _capi.ptr(Kmn), c_pad,
+                                    n_pad * c_pad, n_pad, c_pad, 0, 0, batch, _capi.stream_ptr()), 'rc_gram')
+    fac.trsm_fwd_(Kmn)
+    kdiag = _capi.dev(np.ascontiguousarray(np.diagonal(F, axis1=1, axis2=2)))
+    mean, _ = _capi.predict_reduce(Kmn, alpha, L, nstar, kdiag, None)
+    cov = _capi.gram(Xn, None, ls, dF, None, batch=batch, pad_to=c)                  # Knn, zero padding
+    _capi.syrk_tn(Kmn, alpha=-1.0, beta=1.0, C=cov)
+    return mean, cov[:, :c, :c]
+
+
+def shape_full_covariance(cov: torch.Tensor, L: int, nstar: int, full_cov: bool) -> torch.Tensor:
+    """(L n*, L n*) -> what MOGPR.predict_f returns (romcomma/gpf/models.py:99-109): 'LNln -> LlNn', the diagonal over (N, n) unless full_cov,
+    axes reversed: (n*, n*, L, L) for full_cov, (n*, L, L) for full_output_cov alone."""
+    four = cov.reshape(L, nstar, L, nstar).permute(0, 2, 1, 3)            # [L, l, N, n]
+    if not full_cov:
+        return torch.diagonal(four, dim1=2, dim2=3).permute(2, 1, 0).contiguous()
+    return four.permute(3, 2, 1, 0).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -139,15 +139,20 @@ class MOGPR(gf.Module):
 
     # -- prediction ------------------------------------------------------------------------------------------------
     def _predict(self, Xnew, full_cov, full_output_cov, y_instead_of_f):
-        if full_cov or full_output_cov:
-            raise NotImplementedError('only marginal predictive variances are computed on the device path (all that romcomma.gpr uses).')
         Xn = as_device(Xnew).reshape(-1, self._M)
+        if full_cov or full_output_cov:
+            if y_instead_of_f:       # inherited gpflow GPModel.predict_y (2.5.2) refuses these arguments, see GPflow issue 1461
+                raise NotImplementedError('The predict_y method currently supports only the argument values full_cov=False and full_output_cov=False')
+            mean, cov = gf.predict_full_core(self._X, self._Yd, self.kernel._ls_device(self._M), self.kernel.variance.value.numpy()[None],
+                                             self.likelihood.variance.value.numpy()[None], Xn, self._L, 1)
+            return DeviceTensor.wrap(mean[0]), DeviceTensor.wrap(gf.shape_full_covariance(cov[0], self._L, Xn.shape[0], bool(full_cov)))
         mean, var = gf.predict_core(self._X, self._Yd, self.kernel._ls_device(self._M), self.kernel.variance.value.numpy()[None],
                                     self.likelihood.variance.value.numpy()[None], Xn, self._L, 1, y_instead_of_f)
         return DeviceTensor.wrap(mean[0]), DeviceTensor.wrap(var[0])
 
     def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):
-        """ Mean and marginal variance of f at Xnew, each of shape (n, L)."""
+        """ Mean (n, L) of f at Xnew and its variance: marginal (n, L) by default; (n, L, L) with full_output_cov; (n, n, L, L) with full_cov, which
+        implies full_output_cov - the shapes of the reference (gpf/models.py:94-109)."""
         return self._predict(Xnew, full_cov, full_output_cov, False)
 
     def predict_y(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):

@@ -305,31 +305,15 @@ class MOGP(GPR):
 
         Variant GPs only: the reference's covariant branch calls ``kernel(x)`` on an ``MOStationary`` whose ``__call__`` requires ``X2`` and
         raises a TypeError (:405); the same exception is raised here.  ``y_instead_of_f`` is accepted and ignored, as in the reference.
-        The O(N^2 o M) part - the triangular solve of the kernel Jacobian with K_cho - is rc_trsm_fwd; the Jacobian itself and the
-        small (oM)^2 contractions are device tensor algebra.
+        All of it runs in the library: the Jacobian of k(X, x) and the mean (rc_predict_gradient_jacobian), the triangular solve with K_cho
+        (rc_trsm_fwd), the (oM)^2 N contraction -W^T W on FP64 tensor-core tiles (rc_syrk_tn) and the assembly (rc_predict_gradient_finish).
         """
         if self._likelihood.is_covariant:
             raise TypeError("MOStationary.__call__() missing 1 required positional argument: 'X2'")
         xd = as_device(np.asarray(x, dtype=FLOAT()))
-        Xd = as_device(self._X)
-        o, N, M, L = xd.shape[0], self._N, self._M, self._L
         ls, F, E, _, batch = self._hyper()                                                # ls (L,M) device; F, E (L,1,1) host
-        Kx = _capi.gram(Xd, xd, ls, _capi.dev(F), None, batch=batch)[:, :N, :o]           # (L,N,o)  k_l(X, x)
-        J = Kx[..., None] * (Xd[None, :, None, :] - xd[None, None, :, :]) / (ls * ls)[:, None, None, :]    # (L,N,o,M) dk_l(X,x)/dx
-        KiY = self.K_inv_Y.as_subclass(torch.Tensor).reshape(L, N)
-        mean = torch.einsum('lNoM,lN->olM', J, KiY)
-        fac = self._factorize()[0]
-        c_pad = _capi.padded(o * M)
-        B = torch.zeros((L, fac.n_pad, c_pad), dtype=torch.float64, device=Xd.device)
-        B[:, :N, :o * M] = J.reshape(L, N, o * M)
-        fac.trsm_fwd_(B)
-        W = B[:, :N, :o * M].reshape(L, N, o, M)
-        var = -torch.einsum('LNOM,LNom->OoLMm', W, W)
-        kxx = _capi.gram(xd, None, ls, _capi.dev(F), None, batch=batch)[:, :o, :o]        # (L,o,o)  k_l(x, x)
-        lam = 1.0 / ls
-        dd = torch.einsum('LM,LM,LOo->OoLM', lam, lam, kxx)
-        idx = torch.arange(M, device=Xd.device)
-        var[:, :, :, idx, idx] += dd
+        KiY = self.K_inv_Y.as_subclass(torch.Tensor).reshape(self._L, self._N).contiguous()
+        mean, var = _capi.predict_gradient(as_device(self._X), xd, ls, _capi.dev(F.reshape(-1)), KiY, self._factorize()[0])
         return DeviceTensor.wrap(mean), DeviceTensor.wrap(var)
 
     @property

@@ -51,6 +51,7 @@ class EvaluationBroker:
         self._participants: set = set()
         self._pending: Dict[int, _Request] = {}
         self._plans: Dict[Tuple, Tuple[Any, List[Any]]] = {}
+        self._streams: List[Any] = []
         self.batches: List[int] = []            # size of every batch that has been launched (diagnostics / tests)
 
     # -- who takes part ---------------------------------------------------------------------------------------------------------------
@@ -112,32 +113,56 @@ class EvaluationBroker:
         for r in requests:
             n_pad = _capi.padded(r.L * r.X.shape[0])
             groups.setdefault((n_pad, r.X.shape[1], r.L, r.flags, r.X.device), []).append(r)
-        for key, group in groups.items():
+        # Launch every group first - each on a stream of its own, so that a lone odd-sized problem (the improper fold) overlaps the big batch -
+        # then wait for them in turn: one device-to-host copy per group.
+        launched = []
+        for i, (key, group) in enumerate(groups.items()):
             group.sort(key=lambda r: id(r.model))
             try:
-                self._run(key, group)
+                launched.append((group, self._launch(key, group, i if len(groups) > 1 else None)))
             except BaseException as exc:           # hand the failure to every waiting optimiser of the group
+                for r in group:
+                    r.error = exc
+        for group, (plan, stream) in launched:
+            try:
+                self._collect(group, plan, stream)
+            except BaseException as exc:
                 for r in group:
                     r.error = exc
         self._cond.notify_all()
 
-    def _run(self, key: Tuple, group: List[_Request]):
+    def _launch(self, key: Tuple, group: List[_Request], stream_index: Optional[int]):
         n_pad, M, L, flags, device = key
         # A cached plan holds the packed data of a COMPOSITION of problems, identified by the models' ids - which stay unique only while the models
         # are alive, so the cache entry keeps them alive (a freed model's id may be handed to the next one created).
         plan_key = key + tuple(id(r.model) for r in group)
         plan = self._plans.get(plan_key, (None, None))[0]
         if plan is None:
-            if len(self._plans) >= 4:                # compositions change as optimisers finish: keep the workspaces of the latest few only
+            if len(self._plans) >= 6:                # compositions change as optimisers finish: keep the workspaces of the latest few only
                 self._plans.pop(next(iter(self._plans)))
             plan = _capi.LmlGradMultiPlan([r.X for r in group], [r.Y for r in group], L, flags)
             self._plans[plan_key] = (plan, [r.model for r in group])
-        ls = np.concatenate([r.ls.reshape(L, M) for r in group], axis=0)
-        F = np.stack([r.F for r in group])
-        E = np.stack([r.E for r in group])
-        out = plan(_capi.dev(ls, device), _capi.dev(F, device), _capi.dev(E, device)).cpu().numpy()     # the one synchronisation of the batch
-        info = plan.info.cpu().numpy()
+        ls = _capi.dev(np.concatenate([r.ls.reshape(L, M) for r in group], axis=0), device)
+        F, E = _capi.dev(np.stack([r.F for r in group]), device), _capi.dev(np.stack([r.E for r in group]), device)
+        stream = None
+        if stream_index is not None and device.type == 'cuda':
+            while len(self._streams) <= stream_index:
+                self._streams.append(torch.cuda.Stream(device))
+            stream = self._streams[stream_index]
+            stream.wait_stream(torch.cuda.current_stream(device))      # the hyper-parameter uploads above
+            with torch.cuda.stream(stream):
+                plan(ls, F, E)
+        else:
+            plan(ls, F, E)
         self.batches.append(len(group))
+        return plan, stream
+
+    @staticmethod
+    def _collect(group: List[_Request], plan, stream):
+        if stream is not None:
+            torch.cuda.current_stream(stream.device).wait_stream(stream)
+        out = plan.out.cpu().numpy()               # the one synchronisation of this group
+        info = plan.info.cpu().numpy()
         for z, (r, res) in enumerate(zip(group, plan.unpack(out))):
             if int(info[z]) != 0:
                 r.error = _capi.RomcommaB200Error('Cholesky decomposition was not successful. The input might not be valid.')

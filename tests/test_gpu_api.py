@@ -293,12 +293,12 @@ def test_lockstep_fits_equal_sequential_fits(small_repo, monkeypatch):
     from romcomma.user import run
     repo = small_repo
     sizes = []
-    original = lockstep.EvaluationBroker._run
+    original = lockstep.EvaluationBroker._launch
 
-    def spy(self, key, group):
+    def spy(self, key, group, stream_index):
         sizes.append(len(group))
-        return original(self, key, group)
-    monkeypatch.setattr(lockstep.EvaluationBroker, '_run', spy)
+        return original(self, key, group, stream_index)
+    monkeypatch.setattr(lockstep.EvaluationBroker, '_launch', spy)
     names = run.gpr('together', repo, is_read=False, is_covariant=None, is_isotropic=False, maxiter=30)
     assert names == ['together.v.a', 'together.c.a']
     assert max(sizes) >= 4, f'3 folds x 2 outputs should share launches, batch sizes seen: {sorted(set(sizes))}'
@@ -313,3 +313,92 @@ def test_lockstep_fits_equal_sequential_fits(small_repo, monkeypatch):
                     assert np.array_equal(a, b), f'fold {k} {model} {csv}: lock-step and sequential fits differ'
                 else:   # the covariant fit on its own uses the selected inverse (default trainables); in a batch the full inverse: same to rounding
                     assert_close(a, b, rtol=1e-6, atol=1e-8, what=f'fold {k} {model} {csv}')
+
+
+def test_gsa_base_gaussian_reproduces_the_closed_sobol_chain():
+    """romcomma.gsa.base.Gaussian / diag_det keep the reference's broadcasting contract (gsa/base.py:52-126): the Gaussian-ratio chain of
+    ClosedSobol._calibrate / _V (gsa/calibrators.py:60-92) written with them, as a user of the reference would, gives the oracle's g0 and V - and
+    the numbers the fused kernel (rc_sobol_contract) produces."""
+    from romcomma.gsa.base import Gaussian, diag_det, sym_check
+    X, Y, ls, F, E = random_problem(24, 3, 2, seed=9, full_E=False)
+    KiY = gp.k_inv_y_mo(X, Y, ls, F, E)
+    ref = sobol.ClosedSobol(X, ls, F, KiY, True)
+    Xd, Lam = torch.as_tensor(X, device='cuda'), torch.as_tensor(ls, device='cuda')
+    L2p1 = (Lam * Lam)[:, None, :] + 1.0                                    # Lambda2[1][1], (L,1,M)
+    Phi = 1.0 / L2p1
+    pre = torch.sqrt(torch.prod((Lam * Lam)[:, None, :] * Phi, dim=-1)) * torch.as_tensor(np.diag(F).reshape(2, 1).copy(), device='cuda')
+    g0 = torch.exp(Gaussian(mean=Xd[None, None, ...], variance=L2p1, is_variance_diagonal=True, LBunch=2).exponent) * pre[..., None]
+    assert_close(g0.cpu().numpy(), ref.g0, what='g0 through gsa.base.Gaussian')
+    g0KY = torch.as_tensor(ref.g0KY, device='cuda')
+    G = torch.einsum('lLM,NM->lLNM', Phi, Xd)
+
+    def V(m0, m1):
+        g, phi = G[..., m0:m1], Phi[..., m0:m1]
+        Gamma = 1 - phi
+        Psi = Gamma[:, :, None, None, :] + Gamma[None, None, ...] - torch.einsum('lLM,jJM->lLjJM', Gamma, Gamma)
+        PsiPhi = torch.einsum('lLjJM,lLM->lLjJM', Psi, phi)
+        PhiG = torch.einsum('lLM,jJnM->lLjJnM', phi, g).unsqueeze(2)
+        PhiGauss = Gaussian(mean=g, variance=phi, is_variance_diagonal=True, LBunch=2)
+        H = Gaussian(mean=PhiG, variance=PsiPhi, ordinate=g[..., None, None, None, :], is_variance_diagonal=True, LBunch=2)
+        H = H / PhiGauss.expand_dims([-1, -2, -3])
+        assert np.array_equal(H.det.cpu().numpy(), diag_det(H.cho_diag).cpu().numpy()), 'det == diag_det(cho_diag)'
+        return torch.einsum('lLN,lLNjJn,jJn->lj', g0KY, H.pdf, g0KY)
+    for s in ((0, 3), (1, 2), (0, 2)):
+        Vs = V(*s)
+        assert_close(Vs.cpu().numpy(), ref._V(*s), what=f'V{s} through gsa.base.Gaussian')
+        assert float(sym_check(Vs, [1, 0]).cpu()) < 1e-24
+    # the full (non-diagonal) variance branch: a 2 x 2 covariance against the explicit quadratic form
+    S = torch.tensor([[2.0, 0.3], [0.3, 1.0]], dtype=torch.float64, device='cuda')
+    z = torch.tensor([[0.5, -1.0]], dtype=torch.float64, device='cuda')
+    gfull = Gaussian(mean=z, variance=S, is_variance_diagonal=False)
+    want = -0.5 * (z @ torch.linalg.inv(S) @ z.T).item()
+    assert_close(gfull.exponent.cpu().numpy().reshape(-1)[0], want, what='full-covariance exponent')
+    assert_close(gfull.det.cpu().numpy().reshape(-1)[0], np.sqrt(np.linalg.det(S.cpu().numpy())), what='sqrt det')
+
+
+def test_predict_gradient_and_full_covariance_against_oracle(small_repo):
+    """MOGP.predict_gradient (variant GP: Jacobian kernel, TRSM, -W^T W on tensor-core tiles, assembly - all in the library) and predict_f with
+    full_cov / full_output_cov (Knn - A^T A through rc_syrk_tn) against the oracle; shapes as the reference returns them."""
+    from romcomma.data.storage import Fold
+    from romcomma.gpf import kernels, models
+    from romcomma.gpr.models import MOGP
+    fold = Fold(small_repo, 0)
+    gpv = MOGP('pg.v.a', fold, is_read=False, is_covariant=False, is_isotropic=False)
+    gpv.kernel.data.replace(variance=np.array([[1.3, 0.7]]), lengthscales=np.array([[0.8, 1.7, 1.1], [2.0, 0.6, 1.4]]))
+    gpv.likelihood.data.replace(variance=np.array([[0.02, 0.05]]))
+    gpv = MOGP('pg.v.a', fold, is_read=True, is_covariant=False, is_isotropic=False)
+    X, Y = fold.X.values, fold.Y.values
+    ls, var, noise = gpv.kernel.data.frames.lengthscales.np, gpv.kernel.data.frames.variance.np[0], gpv.likelihood.data.frames.variance.np[0]
+    for o in (1, 5, 50):                                            # 50 x 3 = 150 columns: more than one 128-tile of right-hand sides
+        xs = fold.test_x.values[:o] * 0.9 + 0.02
+        mean, cov = gpv.predict_gradient(xs)
+        rm, rv = gp.predict_gradient_rbf(X, Y, ls, var, noise, xs)
+        assert tuple(mean.shape) == (o, 2, 3) and tuple(cov.shape) == (o, o, 2, 3, 3)
+        assert_close(mean.numpy(), rm, rtol=1e-7, atol=1e-9, what=f'predict_gradient mean (o={o})')
+        assert_close(cov.numpy(), rv, rtol=1e-7, atol=1e-9, what=f'predict_gradient covariance (o={o})')
+    # full predictive covariance of the covariant model
+    Xr, Yr, lsr, F, E = random_problem(70, 3, 2, seed=12, full_F=True, full_E=False)
+    model = models.MOGPR((Xr, Yr), kernels.RBF(F, lsr), noise_variance=E)
+    xs = Xr[:9] + 0.1
+    Kmm = gp.add_noise_mo(gp.gram_mo(Xr, None, lsr, F), E)
+    Kmn, Knn = gp.gram_mo(Xr, xs, lsr, F), gp.gram_mo(xs, xs, lsr, F)
+    A = np.linalg.solve(np.linalg.cholesky(Kmm), Kmn)
+    full = (Knn - A.T @ A).reshape(2, 9, 2, 9)                       # [L, N, l, n]
+    mean, v4 = model.predict_f(xs, full_cov=True)
+    rm, rv = gp.predict_mo(Xr, Yr, lsr, F, E, xs, y_instead_of_f=False)
+    assert tuple(v4.shape) == (9, 9, 2, 2)
+    assert_close(mean.numpy(), rm, what='mean (full_cov)')
+    assert_close(v4.numpy(), full.transpose(3, 1, 2, 0), what='full_cov: (n, N, l, L) = reversed "LNln -> LlNn"')
+    _, v3 = model.predict_f(xs, full_output_cov=True)
+    assert tuple(v3.shape) == (9, 2, 2)
+    assert_close(v3.numpy(), np.stack([full[:, i, :, i].T for i in range(9)]), what='full_output_cov: (n, l, L)')
+    assert_close(np.stack([np.diag(v3.numpy()[i]) for i in range(9)]), rv, what='its diagonal is the marginal variance')
+    with pytest.raises(NotImplementedError):
+        model.predict_y(xs, full_cov=True)
+    # the variant GP (gpflow GPR shapes): [1, n, n] and [n, 1, 1]
+    gpr0 = gpv.implementation[0]
+    _, vc = gpr0.predict_f(xs0 := fold.test_x.values[:6], full_cov=True)
+    Kv = gp.gram_rbf(X, None, ls[0], var[0]) + noise[0] * np.eye(X.shape[0])
+    Av = np.linalg.solve(np.linalg.cholesky(Kv), gp.gram_rbf(X, xs0, ls[0], var[0]))
+    assert tuple(vc.shape) == (1, 6, 6)
+    assert_close(vc.numpy()[0], gp.gram_rbf(xs0, xs0, ls[0], var[0]) - Av.T @ Av, what='variant full covariance')
