@@ -10,8 +10,12 @@
  *  - return value: 0 ok; < 0 bad argument (-2) or CUDA error (-1000 - cudaError); text via rc_last_error();
  *    a failed Cholesky (the reference's tf InvalidArgumentError) is reported through the device-side `info` word:
  *    0, or the 1-based index of the first non-positive pivot (LAPACK convention);
- *  - no global state, thread-safe per (device, stream); nothing here allocates device memory: workspaces are sized by
- *    the *_bufsize twins and provided by the caller;
+ *  - workspaces are sized by the *_bufsize twins and provided by the caller.  What the library keeps itself, per DEVICE and created on
+ *    first use: 32 KB of tile-scheduler counters for the GEMM kernel (its only device allocation), and - for factorisations of 32 blocks
+ *    or more and the optional overlapped inverse - two internal streams (high / low priority) with their events per (device, caller stream),
+ *    forked from and joined to `stream` by events, so the call is still ordered on `stream` and capturable.  Per-process: the launch counter
+ *    and the diagnostic GEMM profile (rc_profile_begin/end, not thread-safe).  Calls are thread-safe per (device, stream); kernel attributes
+ *    (dynamic shared memory opt-in) and SM counts are tracked per device, so one process may drive several devices;
  *  - factorisation matrices are stored padded: n_pad = rc_padded(n) (multiple of 128), identity in the padding,
  *    row stride `ld` (even, >= n_pad).  Only the lower triangle is meaningful.
  *  - multi-output index convention: row (l, n) -> l*N + n  (romcomma/gpf/kernels.py:103-104, gpf/models.py:130).

@@ -167,6 +167,7 @@ int rc_gram(const double* X, int N, const double* X2, int N2, int M, const doubl
 int rc_apply_variance_noise(const double* Kunit, long ldu, const double* F, const double* E, int L, int N, int n_pad, double* out, long ld_out,
                             int lower_only, rc_stream_t stream) {
   RC_REQUIRE(Kunit && F && out, -2, "rc_apply_variance_noise: null pointer");
+  RC_REQUIRE(L > 0 && N > 0 && n_pad >= L * N && ld_out >= n_pad && ldu >= (long)L * N, -2, "rc_apply_variance_noise: inconsistent sizes");
   return apply_variance_noise(Kunit, ldu, F, E, L, N, n_pad, out, ld_out, lower_only, (cudaStream_t)stream);
 }
 
@@ -176,30 +177,45 @@ int rc_debug_tile_order(int M, int N, int K, int lower_only, int kmode, int sel_
 
 size_t rc_potrf_bufsize(int n_pad, int batch) { return align256(potrf_workspace_bytes(n_pad, batch)); }
 
+#define RC_CHECK_FACTOR_ARGS(who)                                                                                              \
+  RC_REQUIRE(n_pad > 0 && n_pad % TILE == 0, -2, who ": n_pad=%d must be a positive multiple of 128 (rc_padded)", n_pad); \
+  RC_REQUIRE(batch > 0, -2, who ": batch=%d must be positive", batch)
+
 int rc_potrf(double* A, int n_pad, long ld, long strideA, int batch, void* work, int* info, rc_stream_t stream) {
   RC_REQUIRE(A && work && info, -2, "rc_potrf: null pointer");
+  RC_CHECK_FACTOR_ARGS("rc_potrf");
   PotrfWork w = split_potrf_work(work, n_pad, batch);
   return potrf_lower(A, n_pad, ld, strideA, batch, w.dinv, w.logdet_parts, info, (cudaStream_t)stream);
 }
 
 int rc_logdet(const void* work, int n_pad, int batch, double* out, rc_stream_t stream) {
+  RC_REQUIRE(work && out, -2, "rc_logdet: null pointer");
+  RC_CHECK_FACTOR_ARGS("rc_logdet");
   PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, batch);
   return sum_parts(w.logdet_parts, n_pad / TILE, batch, out, 1.0, (cudaStream_t)stream);
 }
 
 int rc_trsv(const double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* wv, double* x, long strideV, int transpose,
             rc_stream_t stream) {
+  RC_REQUIRE(A && work && wv && x, -2, "rc_trsv: null pointer");
+  RC_CHECK_FACTOR_ARGS("rc_trsv");
   PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, batch);
   return trsv_lower(A, n_pad, ld, strideA, batch, w.dinv, wv, x, strideV, transpose, (cudaStream_t)stream);
 }
 
 int rc_trsm_fwd(const double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* B, int nrhs_pad, long ldb, long strideB,
                 rc_stream_t stream) {
+  RC_REQUIRE(A && work && B, -2, "rc_trsm_fwd: null pointer");
+  RC_CHECK_FACTOR_ARGS("rc_trsm_fwd");
+  RC_REQUIRE(nrhs_pad > 0 && nrhs_pad % TILE == 0 && ldb >= nrhs_pad && ldb % 2 == 0, -2, "rc_trsm_fwd: nrhs_pad=%d must be a positive multiple of 128 and ldb=%ld even and >= it", nrhs_pad, ldb);
   PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, batch);
   return trsm_lower_fwd(A, n_pad, ld, strideA, batch, w.dinv, B, nrhs_pad, ldb, strideB, (cudaStream_t)stream);
 }
 
 int rc_potri(double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* Kinv, long ldk, long strideK, rc_stream_t stream) {
+  RC_REQUIRE(A && work && Kinv, -2, "rc_potri: null pointer");
+  RC_CHECK_FACTOR_ARGS("rc_potri");
+  RC_REQUIRE(ld >= n_pad && ldk >= n_pad && ld % 2 == 0 && ldk % 2 == 0, -2, "rc_potri: leading dimensions must be even and >= n_pad");
   PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, batch);
   int rc = trtri_lower(A, n_pad, ld, strideA, batch, w.dinv, Kinv, strideK, (cudaStream_t)stream);
   if (rc) return rc;
@@ -207,11 +223,13 @@ int rc_potri(double* A, int n_pad, long ld, long strideA, int batch, const void*
 }
 
 int rc_pad_identity(const double* src, int n, long stride_src, double* dst, int n_pad, long ld, long stride_dst, int batch, rc_stream_t stream) {
+  RC_REQUIRE(src && dst && n > 0 && n_pad >= n && ld >= n_pad && batch > 0, -2, "rc_pad_identity: null pointer or inconsistent sizes");
   return pad_identity(src, n, stride_src, dst, n_pad, ld, stride_dst, batch, (cudaStream_t)stream);
 }
 
 int rc_extract_lower(const double* src, long ld, long stride_src, double* dst, int n, long stride_dst, int batch, int symmetrize,
                      rc_stream_t stream) {
+  RC_REQUIRE(src && dst && n > 0 && ld >= n && batch > 0, -2, "rc_extract_lower: null pointer or inconsistent sizes");
   return extract_lower(src, ld, stride_src, dst, n, stride_dst, batch, symmetrize, (cudaStream_t)stream);
 }
 

@@ -1085,19 +1085,19 @@ int dot_batched(const double* a, const double* b, long n, long stride, int batch
 __global__ void extract_lower_kernel(const double* __restrict__ src, long lds, long strideS, double* __restrict__ dst, int n, long strideDst,
                                      int symmetrize) {
   const int z = blockIdx.z;
-  const long i = blockIdx.y;
   const double* s = src + z * strideS;
   double* d = dst + z * strideDst;
-  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long)gridDim.x * blockDim.x) {
-    double v;
-    if (j <= i) v = s[i * lds + j];
-    else v = symmetrize ? s[j * lds + i] : 0.0;
-    d[i * n + j] = v;
-  }
+  for (long i = blockIdx.y; i < n; i += gridDim.y)              // rows in a grid-stride loop: gridDim.y is limited to 65535
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long)gridDim.x * blockDim.x) {
+      double v;
+      if (j <= i) v = s[i * lds + j];
+      else v = symmetrize ? s[j * lds + i] : 0.0;
+      d[i * n + j] = v;
+    }
 }
 
 int extract_lower(const double* src, long lds, long strideS, double* dst, int n, long strideDst, int batch, int symmetrize, cudaStream_t st) {
-  dim3 grid((n + 1023) / 1024 > 0 ? (n + 1023) / 1024 : 1, n, batch);
+  dim3 grid((n + 1023) / 1024 > 0 ? (n + 1023) / 1024 : 1, n < 65535 ? n : 65535, batch);
   extract_lower_kernel<<<grid, 256, 0, st>>>(src, lds, strideS, dst, n, strideDst, symmetrize);
   RC_LAUNCH_OK();
   return 0;
@@ -1106,15 +1106,15 @@ int extract_lower(const double* src, long lds, long strideS, double* dst, int n,
 // dst (n_pad storage) <- src (n x n dense) with identity padding
 __global__ void pad_identity_kernel(const double* __restrict__ src, int n, long strideS, double* __restrict__ dst, int n_pad, long ldd, long strideD) {
   const int z = blockIdx.z;
-  const long i = blockIdx.y;
-  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n_pad; j += (long)gridDim.x * blockDim.x) {
-    double v = (i < n && j < n) ? src[z * strideS + i * n + j] : (i == j ? 1.0 : 0.0);
-    dst[z * strideD + i * ldd + j] = v;
-  }
+  for (long i = blockIdx.y; i < n_pad; i += gridDim.y)
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n_pad; j += (long)gridDim.x * blockDim.x) {
+      double v = (i < n && j < n) ? src[z * strideS + i * n + j] : (i == j ? 1.0 : 0.0);
+      dst[z * strideD + i * ldd + j] = v;
+    }
 }
 
 int pad_identity(const double* src, int n, long strideS, double* dst, int n_pad, long ldd, long strideD, int batch, cudaStream_t st) {
-  dim3 grid((n_pad + 1023) / 1024, n_pad, batch);
+  dim3 grid((n_pad + 1023) / 1024, n_pad < 65535 ? n_pad : 65535, batch);
   pad_identity_kernel<<<grid, 256, 0, st>>>(src, n, strideS, dst, n_pad, ldd, strideD);
   RC_LAUNCH_OK();
   return 0;

@@ -156,26 +156,27 @@ int gram(const GramArgs& a_in, int batch, cudaStream_t st) {
 // K = F (x) Kunit + E (x) I  from a cached unit-variance gram (gpf/models.py:66-68 cached branch + likelihoods.add_to).
 __global__ void apply_variance_noise_kernel(const double* __restrict__ Ku, long ldu, const double* __restrict__ F, const double* __restrict__ E, int L,
                                             int N, int n_pad, double* __restrict__ out, long ldo, int lower_only) {
-  const long i = blockIdx.y;
-  const int l_i = i < (long)L * N ? (int)(i / N) : -1;
-  const int n_i = l_i >= 0 ? (int)(i - (long)l_i * N) : -1;
-  const long jend = lower_only ? ((i / TILE + 1) * TILE) : n_pad;
-  for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < jend; j += (long)gridDim.x * blockDim.x) {
-    double v;
-    if (l_i >= 0 && j < (long)L * N) {
-      const int l_j = (int)(j / N), n_j = (int)(j - (long)l_j * N);
-      v = F[l_i * L + l_j] * Ku[i * ldu + j];
-      if (E && n_i == n_j) v += E[l_i * L + l_j];
-    } else {
-      v = (i == j) ? 1.0 : 0.0;
+  for (long i = blockIdx.y; i < n_pad; i += gridDim.y) {        // rows in a grid-stride loop: gridDim.y is limited to 65535
+    const int l_i = i < (long)L * N ? (int)(i / N) : -1;
+    const int n_i = l_i >= 0 ? (int)(i - (long)l_i * N) : -1;
+    const long jend = lower_only ? ((i / TILE + 1) * TILE) : n_pad;
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < jend; j += (long)gridDim.x * blockDim.x) {
+      double v;
+      if (l_i >= 0 && j < (long)L * N) {
+        const int l_j = (int)(j / N), n_j = (int)(j - (long)l_j * N);
+        v = F[l_i * L + l_j] * Ku[i * ldu + j];
+        if (E && n_i == n_j) v += E[l_i * L + l_j];
+      } else {
+        v = (i == j) ? 1.0 : 0.0;
+      }
+      out[i * ldo + j] = v;
     }
-    out[i * ldo + j] = v;
   }
 }
 
 int apply_variance_noise(const double* Ku, long ldu, const double* F, const double* E, int L, int N, int n_pad, double* out, long ldo,
                          int lower_only, cudaStream_t st) {
-  dim3 grid((n_pad + 1023) / 1024, n_pad);
+  dim3 grid((n_pad + 1023) / 1024, n_pad < 65535 ? n_pad : 65535);
   apply_variance_noise_kernel<<<grid, 256, 0, st>>>(Ku, ldu, F, E, L, N, n_pad, out, ldo, lower_only);
   RC_LAUNCH_OK();
   return 0;
@@ -366,7 +367,8 @@ int grad_reduce(GradArgs a, int n_pad, int batch, double* out, cudaStream_t st) 
   a.slots = grad_slots(a.L, a.N);
   const long t = n_pad / GT, tiles = t * (t + 1) / 2;
   const size_t smem = (size_t)(2 * GT * a.M + 2 * GT + 32 + 16 * a.slots * a.M) * sizeof(double) + 4 * GT * sizeof(int);
-  RC_REQUIRE(smem <= 48 * 1024, -2, "grad_reduce: M=%d / slots=%d need %zu bytes of shared memory (>48 KB)", a.M, a.slots, smem);
+  RC_REQUIRE(smem <= 200 * 1024, -2, "grad_reduce: M=%d / slots=%d need %zu bytes of shared memory (> 200 KB)", a.M, a.slots, smem);
+  if (smem > 48 * 1024) RC_ENSURE_SMEM(grad_reduce_kernel, 200 * 1024);     // M > ~36: opt in, as gram() does (round-1 advice)
   grad_reduce_kernel<<<dim3((unsigned)tiles, 1, batch), GTHREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
   grad_finish_kernel<<<dim3(a.nvals, batch), 256, 0, st>>>(a.parts, tiles, a.nvals, out);

@@ -118,9 +118,10 @@ __global__ void __launch_bounds__(STHREADS) sobol_pair_kernel(SobolPairArgs p) {
   while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
   while (a * (a + 1) / 2 > pidx) --a;
   const int b = pidx - a * (a + 1) / 2;
-  const int ti = blockIdx.x / p.T, tj = blockIdx.x - ti * p.T;
-  double* out = p.parts + ((long)pidx * p.T * p.T + blockIdx.x) * ns;
-  if ((a == b && tj > ti) || (ti % p.nparts) != p.part) {   // covered by the mirrored tile (weight 2), or another rank's row tile
+  // only this rank's row tiles are launched: local row k of the grid is the global row tile part + k * nparts
+  const int ti = p.part + (int)(blockIdx.x / p.T) * p.nparts, tj = blockIdx.x % p.T;
+  double* out = p.parts + ((long)pidx * gridDim.x + blockIdx.x) * ns;
+  if (a == b && tj > ti) {   // covered by the mirrored tile (weight 2)
     for (int s = threadIdx.x; s < ns; s += STHREADS) out[s] = 0.0;
     return;
   }
@@ -244,9 +245,9 @@ __global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs 
   while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
   while (a * (a + 1) / 2 > pidx) --a;
   const int b = pidx - a * (a + 1) / 2;
-  const int ti = blockIdx.x / p.T, tj = blockIdx.x - ti * p.T;
-  double* out = p.parts + ((long)pidx * p.T * p.T + blockIdx.x) * nv;
-  if ((a == b && tj > ti) || (ti % p.nparts) != p.part) {   // covered by the mirrored tile (weight 2), or another rank's row tile
+  const int ti = p.part + (int)(blockIdx.x / p.T) * p.nparts, tj = blockIdx.x % p.T;   // only this rank's row tiles are launched
+  double* out = p.parts + ((long)pidx * gridDim.x + blockIdx.x) * nv;
+  if (a == b && tj > ti) {   // covered by the mirrored tile (weight 2)
     for (int s = threadIdx.x; s < nv; s += STHREADS) out[s] = 0.0;
     return;
   }
@@ -433,12 +434,8 @@ __global__ void __launch_bounds__(STHREADS, 1) sobol_lattice_kernel(SobolLattice
   while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
   while (a * (a + 1) / 2 > pidx) --a;
   const int b = pidx - a * (a + 1) / 2;
-  const int ti = blockIdx.x, tid = threadIdx.x;
-  double* out = p.parts + (((long)pidx * p.T + ti) * p.nhi + blockIdx.z) * NLO;
-  if ((ti % p.nparts) != p.part) {            // another rank's row tile
-    for (int s = tid; s < NLO; s += STHREADS) out[s] = 0.0;
-    return;
-  }
+  const int ti = p.part + (int)blockIdx.x * p.nparts, tid = threadIdx.x;       // only this rank's row tiles are launched
+  double* out = p.parts + (((long)pidx * gridDim.x + blockIdx.x) * p.nhi + blockIdx.z) * NLO;
   for (int m = tid; m < M; m += STHREADS) {
     const double pp = p.Phi[a * M + m], qq = p.Phi[b * M + m];
     const double psi = 1.0 - pp * qq, g = pp * qq / psi;
@@ -558,7 +555,7 @@ static int launch_lattice(const SobolLatticeArgs& a, int npairs, cudaStream_t st
   const size_t smem = (size_t)(4 * a.M + 2 * (2 * KL + (a.M - KL > 0 ? a.M - KL : 0) + 2) * ST + 8 * (1 << KL)) * sizeof(double);
   RC_REQUIRE(smem <= 200 * 1024, -2, "sobol_contract: shared memory %zu too large for the lattice form", smem);
   if (smem > 48 * 1024) RC_ENSURE_SMEM(sobol_lattice_kernel<KL>, 200 * 1024);
-  sobol_lattice_kernel<KL><<<dim3(a.T, npairs, a.nhi), STHREADS, smem, st>>>(a);
+  sobol_lattice_kernel<KL><<<dim3((a.T - a.part + a.nparts - 1) / a.nparts, npairs, a.nhi), STHREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
   return 0;
 }
@@ -568,7 +565,7 @@ static int launch_sweep(const SobolPairArgs& a, int npairs, cudaStream_t st) {
   const size_t smem = (size_t)(4 * a.M + 4 * a.M * ST + 2 * ST + 8 * 3 * MAXM + (size_t)a.M * 2 * RU * STHREADS) * sizeof(double);
   RC_ENSURE_SMEM((sobol_sweep_kernel<MAXM, RU>), 160 * 1024);
   RC_REQUIRE(smem <= 160 * 1024, -2, "sobol_contract: shared memory %zu too large", smem);
-  sobol_sweep_kernel<MAXM, RU><<<dim3(a.T * a.T, npairs), STHREADS, smem, st>>>(a);
+  sobol_sweep_kernel<MAXM, RU><<<dim3(a.T * ((a.T - a.part + a.nparts - 1) / a.nparts), npairs), STHREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
   return 0;
 }
@@ -656,6 +653,11 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
   RC_ENSURE_SMEM(sobol_pair_kernel, 200 * 1024);
   const int T = (N + ST - 1) / ST;
   const int npairs = P * (P + 1) / 2;
+  const int own_rows = (T - part + nparts - 1) / nparts;      // row tiles part, part + nparts, ... : the only ones this call launches
+  if (own_rows <= 0) {                                         // more ranks than row tiles: this one has nothing to add
+    RC_CUDA_OK(cudaMemsetAsync(V, 0, (size_t)nslices * L * L * sizeof(double), st));
+    return 0;
+  }
   // Blocks of the subset lattice (the 2^KL subsets that share their inputs >= KL) of which at least half is asked for - the all-subsets sweep -
   // take the lattice form: (KL + 1) exps and ~1.5 FP64 instructions per subset for the whole block.  RC_SOBOL_LATTICE=0 switches it off.
   std::vector<char> taken(nslices, 0);
@@ -693,7 +695,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
           LatticeDest map;
           for (int z = 0; z < 8; ++z)
             for (int lo = 0; lo < 64; ++lo) map.dest[z][lo] = z < nz ? dests[h0 + z0 + z][lo] : -1;
-          sobol_lattice_finish_kernel<<<dim3(NLO, L * L, nz), 256, 0, st>>>(parts, Lp, L, T, nhi, NLO, z0, map, V);
+          sobol_lattice_finish_kernel<<<dim3(NLO, L * L, nz), 256, 0, st>>>(parts, Lp, L, own_rows, nhi, NLO, z0, map, V);
           RC_LAUNCH_OK();
         }
       }
@@ -729,7 +731,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
           map.idx[j - i] = sidx[j];
           ++j;
         }
-        sobol_finish_map_kernel<<<dim3((unsigned)(j - i), L * L), 256, 0, st>>>(parts, P, Lp, L, (long)T * T, 3 * M, map,
+        sobol_finish_map_kernel<<<dim3((unsigned)(j - i), L * L), 256, 0, st>>>(parts, P, Lp, L, (long)T * own_rows, 3 * M, map,
                                                                                 V + (long)structured[i] * L * L, nullptr);
         RC_LAUNCH_OK();
         i = j;
@@ -750,9 +752,9 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
     for (int s = 0; s < ns; ++s) a.masks[s] = masks[s0 + s];
     const size_t smem = (size_t)(4 * M + 3 * M * ST + 2 * ns * ST + 2 * ST + 8 * ns) * sizeof(double);
     RC_REQUIRE(smem <= 200 * 1024, -2, "sobol_contract: shared memory %zu too large", smem);
-    sobol_pair_kernel<<<dim3(T * T, npairs), STHREADS, smem, st>>>(a);
+    sobol_pair_kernel<<<dim3(T * own_rows, npairs), STHREADS, smem, st>>>(a);
     RC_LAUNCH_OK();
-    sobol_finish_kernel<<<dim3(ns, L * L), 256, 0, st>>>(parts, P, Lp, L, (long)T * T, ns, V + (long)s0 * L * L);
+    sobol_finish_kernel<<<dim3(ns, L * L), 256, 0, st>>>(parts, P, Lp, L, (long)T * own_rows, ns, V + (long)s0 * L * L);
     RC_LAUNCH_OK();
     g0 = g1;
   }

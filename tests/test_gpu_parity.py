@@ -567,3 +567,32 @@ def test_lml_grad_multi_independent_problems(C, L):
     plan0 = C.LmlGradMultiPlan([C.dev(p[0]) for p in probs], [C.dev(p[1]) for p in probs], L, C.RC_GRAD_NONE)
     v = plan0(C.dev(ls), C.dev(F), C.dev(E)).cpu().numpy()[:, 0]
     assert_close(v, [r['lml'] for r in res], rtol=1e-12, what='value-only call')
+
+
+def test_lml_grad_many_inputs(C):
+    """M = 64 inputs (round-1 advice: the gradient reduction was capped at 48 KB of shared memory, i.e. M <= 36-40, while gram / predict take
+    M <= 80 and Sobol M <= 64): value and all gradients against the oracle."""
+    X, Y, ls, F, E = random_problem(150, 64, 2, seed=64, full_E=False)
+    ls = ls * 6.0                                         # 64 inputs: keep the kernel from vanishing
+    plan = C.LmlGradPlan(C.dev(X), C.dev(Y), 2, 1, C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES)
+    res = plan.unpack(plan(C.dev(ls), C.dev(F[None]), C.dev(E[None])).cpu().numpy())[0]
+    ref = gp.lml_grad_mo(X, Y, ls, F, E)
+    assert_close(res['lml'], ref['lml'], what='lml (M = 64)')
+    for k in ('dF', 'dE', 'dls'):
+        assert_close(res[k], ref[k], atol=1e-10 * 300, what=f'{k} (M = 64)')
+
+
+def test_capi_rejects_bad_arguments(C):
+    """Null pointers and unpadded sizes come back as status -2 with a message, not as a launch failure (round-1 advice)."""
+    import ctypes
+    lib = C.lib()
+    A = torch.zeros((1, 256, 256), dtype=torch.float64, device='cuda')
+    work = C.workspace(lib.rc_potrf_bufsize(256, 1))
+    out = torch.zeros(1, dtype=torch.float64, device='cuda')
+    assert lib.rc_logdet(None, 256, 1, C.ptr(out), C.stream_ptr()) == -2
+    assert lib.rc_logdet(C.raw_ptr(work), 200, 1, C.ptr(out), C.stream_ptr()) == -2 and b'multiple of 128' in lib.rc_last_error()
+    assert lib.rc_trsv(C.ptr(A), 256, 256, 256 * 256, 1, C.raw_ptr(work), None, C.ptr(out), 256, 0, C.stream_ptr()) == -2
+    assert lib.rc_trsm_fwd(C.ptr(A), 256, 256, 256 * 256, 0, C.raw_ptr(work), C.ptr(A), 256, 256, 256 * 256, C.stream_ptr()) == -2
+    assert lib.rc_potri(C.ptr(A), 250, 256, 256 * 256, 1, C.raw_ptr(work), C.ptr(A), 256, 256 * 256, C.stream_ptr()) == -2
+    assert lib.rc_pad_identity(None, 10, 100, C.ptr(A), 256, 256, 256 * 256, 1, C.stream_ptr()) == -2
+    assert lib.rc_extract_lower(C.ptr(A), 256, 256 * 256, None, 10, 100, 1, 0, C.stream_ptr()) == -2
