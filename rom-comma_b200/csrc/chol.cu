@@ -398,7 +398,7 @@ size_t potrf_workspace_bytes(int n, int batch) {
 static int potrf_group_env() {
   const char* e = getenv("RC_POTRF_GROUP");
   const int v = e ? atoi(e) : 0;
-  return v < 1 ? 0 : (v > 8 ? 8 : v);
+  return v < 1 ? 0 : (v > 16 ? 16 : v);
 }
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -407,8 +407,8 @@ static int env_int(const char* name, int dflt) {
 static int potrf_group(int blocks_left) {
   const int v = potrf_group_env();
   if (v) return v;
-  static const int t4 = env_int("RC_POTRF_T4", 40), t8 = env_int("RC_POTRF_T8", 160);
-  return blocks_left >= t8 ? 8 : (blocks_left >= t4 ? 4 : 2);
+  static const int t4 = env_int("RC_POTRF_T4", 40), t8 = env_int("RC_POTRF_T8", 48), t16 = env_int("RC_POTRF_T16", 1 << 30);
+  return blocks_left >= t16 ? 16 : (blocks_left >= t8 ? 8 : (blocks_left >= t4 ? 4 : 2));
 }
 
 template <typename Hook>

@@ -422,12 +422,11 @@ __global__ void __launch_bounds__(STHREADS, 1) sobol_lattice_kernel(SobolLattice
   double* gxh = sul + KL * ST;      // [nh][64]   gamma_m x, hi inputs
   double* suh = gxh + (M - KL) * ST;   // [64]    sum over the hi inputs of cu_m x^2 + lp_m
   double* cr = suh + ST;            // [64]
-  double* yyl = cr + ST;            // [KL][64]   y, low inputs (columns)
-  double* svl = yyl + KL * ST;      // [KL][64]   cv_m y^2
-  double* yyh = svl + KL * ST;      // [nh][64]
-  double* svh = yyh + (M - KL) * ST;   // [64]
-  double* cc = svh + ST;            // [64]
-  double* wpart = cc + ST;          // [8][NLO]
+  // column-side data of a tile, double buffered: the 64 loader threads fetch tile tj + 1 while everybody computes tile tj (one barrier per tile)
+  constexpr int COLS = 2 * KL + 2;  // per buffer: yyl [KL][64], svl [KL][64], svh [64], cc [64], then yyh [M - KL][64]
+  double* colbuf = cr + ST;
+  const int col_stride = (COLS + (M - KL)) * ST;
+  double* wpart = colbuf + 2 * col_stride;   // [8][NLO]
 
   const int pidx = blockIdx.y;
   int a = (int)((sqrt(8.0 * (double)pidx + 1.0) - 1.0) * 0.5);
@@ -469,9 +468,12 @@ __global__ void __launch_bounds__(STHREADS, 1) sobol_lattice_kernel(SobolLattice
   for (int s = 0; s < NLO; ++s) acc[s] = 0.0;
   const int ty = tid >> 4, tx = tid & 15, lane = tid & 31, warp = tid >> 5;
   const int tj_end = (a == b) ? ti + 1 : p.T;   // a == b: the mirrored tile carries weight 2 instead
-#pragma unroll 1
-  for (int tj = 0; tj < tj_end; ++tj) {
-    __syncthreads();                             // previous tile's column data is no longer read (and the row data is complete)
+  auto load_columns = [&](int tj, double* buf) {
+    double* yyl = buf;                 // [KL][64]   y, low inputs (columns)
+    double* svl = yyl + KL * ST;       // [KL][64]   cv_m y^2
+    double* svh = svl + KL * ST;       // [64]
+    double* cc = svh + ST;             // [64]
+    double* yyh = cc + ST;             // [nh][64]
     for (int r = tid; r < ST; r += STHREADS) {
       const int gj = tj * ST + r;
       const bool live = gj < p.N;
@@ -491,7 +493,18 @@ __global__ void __launch_bounds__(STHREADS, 1) sobol_lattice_kernel(SobolLattice
         svl[m * ST + r] = m < M ? cv[m] * y * y : 0.0;
       }
     }
-    __syncthreads();
+  };
+  load_columns(0, colbuf);
+#pragma unroll 1
+  for (int tj = 0; tj < tj_end; ++tj) {
+    __syncthreads();                             // buffer tj & 1 is complete (and the row data); buffer (tj + 1) & 1 is no longer read
+    if (tj + 1 < tj_end) load_columns(tj + 1, colbuf + ((tj + 1) & 1) * col_stride);
+    const double* buf = colbuf + (tj & 1) * col_stride;
+    const double* yyl = buf;
+    const double* svl = yyl + KL * ST;
+    const double* svh = svl + KL * ST;
+    const double* cc = svh + ST;
+    const double* yyh = cc + ST;
 #pragma unroll 1
     for (int u = 0; u < 4; ++u) {
       const int r = ty + 16 * u;
@@ -552,7 +565,8 @@ __global__ void sobol_lattice_finish_kernel(const double* __restrict__ parts, in
 
 template <int KL>
 static int launch_lattice(const SobolLatticeArgs& a, int npairs, cudaStream_t st) {
-  const size_t smem = (size_t)(4 * a.M + 2 * (2 * KL + (a.M - KL > 0 ? a.M - KL : 0) + 2) * ST + 8 * (1 << KL)) * sizeof(double);
+  const int hi_inputs = a.M - KL > 0 ? a.M - KL : 0;     // rows: gxl, sul [KL] + gxh [hi] + suh + cr; columns: two buffers of yyl, svl [KL] + yyh [hi] + svh + cc
+  const size_t smem = (size_t)(4 * a.M + 3 * (2 * KL + hi_inputs + 2) * ST + 8 * (1 << KL)) * sizeof(double);
   RC_REQUIRE(smem <= 200 * 1024, -2, "sobol_contract: shared memory %zu too large for the lattice form", smem);
   if (smem > 48 * 1024) RC_ENSURE_SMEM(sobol_lattice_kernel<KL>, 200 * 1024);
   sobol_lattice_kernel<KL><<<dim3((a.T - a.part + a.nparts - 1) / a.nparts, npairs, a.nhi), STHREADS, smem, st>>>(a);

@@ -63,15 +63,15 @@ def _seed_from_ancestor(fold: Fold, name: str, stage: Stage) -> bool:
     return False
 
 
-def _each_owned_fold(repo: Repository, job: Callable[[Fold], Any]) -> List[Any]:
-    """ ``job(Fold(repo, k))`` for every fold this process owns - side by side, evaluations batched - and agreement between the processes on
-    whether everybody succeeded, so that no rank is left waiting at a barrier for one that raised."""
+def _each_owned_fold(repo: Repository, job: Callable[[Fold], Any], side_by_side: bool) -> List[Any]:
+    """ ``job(Fold(repo, k))`` for every fold this process owns - side by side with batched evaluations where the job fits GPs - and agreement
+    between the processes on whether everybody succeeded, so that no rank is left waiting at a barrier for one that raised."""
     mine = distributed.shard(list(repo.folds))
     error, done = None, []
     jobs = [(lambda k=k: job(Fold(repo, k))) for k in mine]
     try:
         # Side by side only where one fit leaves the GPU idle: past n = L N ~ 4096 a single evaluation fills it (and K workspaces would not be free)
-        done = lockstep.run_together(jobs) if repo.L * repo.N <= LOCKSTEP_MAX_N else [j() for j in jobs]
+        done = lockstep.run_together(jobs) if side_by_side and repo.L * repo.N <= LOCKSTEP_MAX_N else [j() for j in jobs]
     except BaseException as exception:
         error = exception
     somebody_failed = distributed.all_reduce_max(0.0 if error is None else 1.0) > 0.0
@@ -122,7 +122,7 @@ def gpr(name: str, repo: Repository, is_read: bool | None, is_covariant: bool | 
     if isinstance(repo, Fold):
         fit(repo)
         return names
-    _each_owned_fold(repo, fit)
+    _each_owned_fold(repo, fit, side_by_side=is_calibrated)
     distributed.barrier()
     if distributed.rank() == 0:
         per_model = {'': ({'test': {'header': [0, 1]}, 'test_summary': {'header': [0, 1], 'index_col': 0}} if is_tested else {}),
@@ -169,7 +169,7 @@ def gsa(name: str, repo: Repository, is_covariant: Optional[bool], is_isotropic:
 
     if isinstance(repo, Fold):
         return analyse(repo)
-    per_fold = _each_owned_fold(repo, analyse)
+    per_fold = _each_owned_fold(repo, analyse, side_by_side=False)      # nothing to batch: threads would only contend for the interpreter
     distributed.barrier()
     written = per_fold[-1] if per_fold else []
     if distributed.rank() == 0 and len(repo.folds) > 0:
