@@ -172,29 +172,28 @@ class GPR(Model):
         """ The gradient GP dy/dx."""
 
     def test(self) -> Frame:
-        """ Predict the fold's test data; writes test.csv (Mean, SD, Abs Error, Z Score, Outlier per output) and test_summary.csv
-        (RMSE, mean SD, outlier fraction)."""
-        result = Frame(self.test_csv, self._fold.test_data.df)
+        """ Predict the fold's test data; writes test.csv (the test data followed by Mean, SD, Abs Error, Z Score and Outlier per output, plus
+        Outlier for any / all outputs) and test_summary.csv (RMSE, mean SD and outlier fraction per output) - the reference's files
+        (gpr/models.py:235-272), assembled in one pass."""
+        data = self._fold.test_data.df
         Y_heading = self._fold.meta['data']['Y_heading']
-        truth = result.df.loc[:, [Y_heading]]
+        outputs = list(data[Y_heading].columns)
+        truth = data[Y_heading].to_numpy(dtype=float)
         mean, std = self.predict(self._fold.test_x.values)
-
-        def block(values, label):
-            return pd.DataFrame(np.asarray(values), index=truth.index, columns=truth.rename(columns={Y_heading: label}, level=0).columns)
-
-        error = truth.to_numpy(dtype=float) - mean
+        error = truth - mean
         z_score = error / std
-        is_outlier = (z_score ** 2 > 4.0)
-        outliers = block(is_outlier, 'Outlier')
-        both = pd.DataFrame(np.column_stack((is_outlier.any(axis=1), is_outlier.all(axis=1))), index=outliers.index,
-                            columns=pd.MultiIndex.from_tuples([('Outlier', 'Any Output'), ('Outlier', 'All Outputs')]))
-        outliers = outliers.join(both)
-        abs_err = block(np.abs(error), 'Abs Error')
-        sd = block(std, 'SD')
-        result.df = result.df.join([block(mean, 'Mean'), sd, abs_err, block(z_score, 'Z Score'), outliers])
-        result.write()
-        rmse = pd.DataFrame(np.sqrt((abs_err.rename(columns={'Abs Error': 'RMSE'}, level=0) ** 2).mean(axis=0))).transpose()
-        summary = rmse.join([pd.DataFrame(sd.mean(axis=0)).transpose(), pd.DataFrame(outliers.mean(axis=0)).transpose()])
+        is_outlier = z_score ** 2 > 4.0
+
+        def columns(label, names=outputs):
+            return pd.MultiIndex.from_tuples([(label, name) for name in names])
+
+        reals = pd.DataFrame(np.concatenate([mean, std, np.abs(error), z_score], axis=1), index=data.index,
+                             columns=columns('Mean').append([columns('SD'), columns('Abs Error'), columns('Z Score')]))
+        flags = pd.DataFrame(np.concatenate([is_outlier, is_outlier.any(axis=1, keepdims=True), is_outlier.all(axis=1, keepdims=True)], axis=1),
+                             index=data.index, columns=columns('Outlier').append(columns('Outlier', ['Any Output', 'All Outputs'])))
+        result = Frame(self.test_csv, pd.concat([data, reals, flags], axis=1))
+        summary = pd.DataFrame([np.concatenate([np.sqrt(np.mean(error ** 2, axis=0)), std.mean(axis=0), flags.to_numpy(dtype=float).mean(axis=0)])],
+                               columns=columns('RMSE').append([columns('SD'), flags.columns]))
         Frame(self.test_summary_csv, summary)
         return result
 
