@@ -367,29 +367,46 @@ class _Scipy:
     scipy.optimize.minimize(jac=True).  The closure must be a bound ``training_loss`` of a model of this package (its
     analytic ``_loss_and_grad`` replaces the tf.GradientTape of the reference)."""
 
-    def minimize(self, closure: Callable, variables: Sequence[Parameter], method: Optional[str] = 'L-BFGS-B', step_callback=None, compile=True,
-                 allow_unused_variables=False, **scipy_kwargs) -> scipy.optimize.OptimizeResult:
+    @staticmethod
+    def _model_of(closure: Callable):
         model = getattr(closure, '__self__', None)
         if model is None or not hasattr(model, '_loss_and_grad'):
-            raise TypeError('Scipy.minimize needs closure=model.training_loss of a romcomma B200 model: gradients are analytic, not taped.')
+            raise TypeError('Scipy needs closure=model.training_loss of a romcomma B200 model: gradients are analytic, not taped.')
+        return model
+
+    @staticmethod
+    def initial_parameters(variables: Sequence[Parameter]) -> np.ndarray:
+        """ gpflow.optimizers.Scipy.initial_parameters: the unconstrained variables packed into one float64 vector."""
+        return np.concatenate([np.reshape(v.unconstrained_variable, -1) for v in variables]).astype(np.float64)
+
+    @staticmethod
+    def assign_tensors(variables: Sequence[Parameter], x: np.ndarray):
+        offset = 0
+        for v in variables:
+            size = int(np.prod(v.shape))
+            v.unconstrained_variable = np.array(x[offset:offset + size], dtype=np.float64).reshape(v.shape)
+            offset += size
+
+    @classmethod
+    def eval_func(cls, closure: Callable, variables: Sequence[Parameter], compile: bool = True, allow_unused_variables: bool = False):
+        """ gpflow.optimizers.Scipy.eval_func: the function x -> (loss, gradient) that ``minimize`` hands to scipy - ONE evaluation of the LML
+        and its analytic gradient per call."""
+        model, variables = cls._model_of(closure), tuple(variables)
+
+        def fun(x):
+            cls.assign_tensors(variables, x)
+            loss, grads = model._loss_and_grad(variables)
+            return float(loss), np.concatenate([np.reshape(g, -1) for g in grads]).astype(np.float64)
+        return fun
+
+    def minimize(self, closure: Callable, variables: Sequence[Parameter], method: Optional[str] = 'L-BFGS-B', step_callback=None, compile=True,
+                 allow_unused_variables=False, **scipy_kwargs) -> scipy.optimize.OptimizeResult:
         variables = tuple(variables)
         if not variables:
             raise ValueError('no trainable variables')
-        shapes = [v.shape for v in variables]
-        sizes = [int(np.prod(s)) for s in shapes]
-
-        def unpack(x):
-            offset = 0
-            for v, shape, size in zip(variables, shapes, sizes):
-                v.unconstrained_variable = np.array(x[offset:offset + size], dtype=np.float64).reshape(shape)
-                offset += size
-
-        def fun(x):
-            unpack(x)
-            loss, grads = model._loss_and_grad(variables)
-            return float(loss), np.concatenate([np.reshape(g, -1) for g in grads]).astype(np.float64)
-
-        x0 = np.concatenate([np.reshape(v.unconstrained_variable, -1) for v in variables]).astype(np.float64)
+        fun = self.eval_func(closure, variables)
+        unpack = lambda x: self.assign_tensors(variables, x)
+        x0 = self.initial_parameters(variables)
         callback = None
         if step_callback is not None:
             counter = [0]
