@@ -391,10 +391,10 @@ size_t potrf_workspace_bytes(int n, int batch) {
 // The factorisation proper.  `after_panel(done)` (optional) is called once the panel solve of block `done - 1` has been enqueued, i.e. when
 // block columns [0, done) of L are final for ALL rows in stream order - the hook the overlapped inverse below forks its side work from.
 // `invert_all`: finish with the batched launch of the 128 x 128 inverses (off the critical path).
-// Block columns factored between two trailing updates (rank 128 * group).  Four while the trailing matrix is large (its K = 512 tiles
-// amortise the read-modify-write epilogue; cfg3 117.6 -> 116.8 ms against two), two once the trailing update is down to a wave or two
-// of tiles and the longer column updates of a wide group are pure chain latency (n = 2048: 2.86 -> 2.72 ms).  RC_POTRF_GROUP (1..8)
-// fixes the width.  Eight while 160+ blocks remain (n >= 20480; cfg4 933 -> 927 ms); thresholds: RC_POTRF_T4 / RC_POTRF_T8.
+// Block columns factored between two trailing updates (rank 128 * group): 16 while 96+ blocks remain (RC_POTRF_T16), 8 while 48+ remain
+// (RC_POTRF_T8), 4 while 40+ remain (RC_POTRF_T4), else 2; RC_POTRF_GROUP (1..16) fixes the width.  Wide groups amortise the read-modify-write
+// of the trailing matrix (K = 1024 / 2048 tiles run at 97 % of the DMMA pipe); their longer in-group chain is hidden by the look-ahead below and
+// cut into wide launches by factor_columns.  Round 2 at n = 16384 / 24576 / 32768: 50.3 / 152.4 / 346.9 ms (round 1, widths 4/2: 52.9 / 158.2 / -).
 static int potrf_group_env() {
   const char* e = getenv("RC_POTRF_GROUP");
   const int v = e ? atoi(e) : 0;
@@ -407,7 +407,7 @@ static int env_int(const char* name, int dflt) {
 static int potrf_group(int blocks_left) {
   const int v = potrf_group_env();
   if (v) return v;
-  static const int t4 = env_int("RC_POTRF_T4", 40), t8 = env_int("RC_POTRF_T8", 48), t16 = env_int("RC_POTRF_T16", 1 << 30);
+  static const int t4 = env_int("RC_POTRF_T4", 40), t8 = env_int("RC_POTRF_T8", 48), t16 = env_int("RC_POTRF_T16", 96);
   return blocks_left >= t16 ? 16 : (blocks_left >= t8 ? 8 : (blocks_left >= t4 ? 4 : 2));
 }
 
@@ -418,6 +418,58 @@ static int potrf_group_at(int b0, int nblk) {
   int w = potrf_group(nblk - b0);
   if (b0 == 0 && nblk >= first_min && first >= 1 && w > first && potrf_group_env() == 0) w = first;
   return std::min(w, nblk - b0);
+}
+
+// Factor block columns [c0, c0 + w) of a group, all rows below included, RECURSIVELY: left half, then ONE update of the right half's columns
+// with the left half as K (a lower-trapezoidal tile list: the first w - h tile columns of the square that starts at block c0 + h), then the
+// right half.  The same flops as updating every column on its own with everything to its left in the group (K = 128 j, N = 128 - seven
+// tall-skinny launches per 8-wide group that ran at half the tile kernel's rate: 6.6 ms of a 16384 factorisation), in wider launches:
+// per 8-wide group one K = 512 x 4 columns, two K = 256 x 2 columns and four K = 128 x 1 column.  RC_POTRF_FLAT=1 restores the flat form.
+static int factor_columns(double* A, int n, long ld, long strideA, int batch, double* dinv, long strideD, double* logdet_parts, int nblk, int* info,
+                          int c0, int w, cudaStream_t st) {
+  int rc;
+  if (w == 1) {
+    if ((rc = launch_diag_factor(A, ld, strideA, dinv, strideD, c0, logdet_parts, nblk, info, batch, st))) return rc;
+    return launch_panel_trsm(A, n, ld, strideA, c0, batch, st);
+  }
+  int h = 1;
+  while (2 * h < w) h *= 2;
+  if ((rc = factor_columns(A, n, ld, strideA, batch, dinv, strideD, logdet_parts, nblk, info, c0, h, st))) return rc;
+  const long r0 = (long)(c0 + h) * DB;
+  GemmArgs u{};
+  u.A = A + r0 * ld + (long)c0 * DB; u.lda = ld; u.strideA = strideA;
+  u.B = u.A; u.ldb = ld; u.strideB = strideA;
+  u.C = A + r0 * ld + r0; u.ldc = ld; u.strideC = strideA;
+  u.M = u.N = n - (int)r0; u.K = h * DB; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1; u.kmode = K_FULL;
+  u.col_tiles = w - h;
+  if ((rc = launch_gemm_ws<false, false>(u, batch, st))) return rc;
+  return factor_columns(A, n, ld, strideA, batch, dinv, strideD, logdet_parts, nblk, info, c0 + h, w - h, st);
+}
+
+static int factor_group_flat(double* A, int n, long ld, long strideA, int batch, double* dinv, long strideD, double* logdet_parts, int nblk, int* info,
+                             int b0, int w, cudaStream_t st) {
+  int rc;
+  for (int j = 0; j < w; ++j) {
+    const long r0 = (long)(b0 + j) * DB;
+    if (j > 0) {   // block column b0+j, rows from block b0+j down:  A -= P[:, b0:b0+j] * P[b0+j, b0:b0+j]^T
+      GemmArgs g{};
+      g.A = A + r0 * ld + (long)b0 * DB; g.lda = ld; g.strideA = strideA;
+      g.B = g.A; g.ldb = ld; g.strideB = strideA;
+      g.C = A + r0 * ld + r0; g.ldc = ld; g.strideC = strideA;
+      g.M = n - (int)r0; g.N = DB; g.K = j * DB; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kmode = K_FULL;
+      if ((rc = launch_gemm_ws<false, false>(g, batch, st))) return rc;
+    }
+    if ((rc = launch_diag_factor(A, ld, strideA, dinv, strideD, b0 + j, logdet_parts, nblk, info, batch, st))) return rc;
+    if ((rc = launch_panel_trsm(A, n, ld, strideA, b0 + j, batch, st))) return rc;
+  }
+  return 0;
+}
+
+static int factor_group(double* A, int n, long ld, long strideA, int batch, double* dinv, long strideD, double* logdet_parts, int nblk, int* info,
+                        int b0, int w, cudaStream_t st) {
+  static const bool flat = env_int("RC_POTRF_FLAT", 0) != 0;
+  return flat ? factor_group_flat(A, n, ld, strideA, batch, dinv, strideD, logdet_parts, nblk, info, b0, w, st)
+              : factor_columns(A, n, ld, strideA, batch, dinv, strideD, logdet_parts, nblk, info, b0, w, st);
 }
 
 template <typename Hook>
@@ -431,19 +483,7 @@ static int potrf_core(double* A, int n, long ld, long strideA, int batch, double
   int rc;
   for (int b0 = 0, w = 0; b0 < nblk; b0 += w) {
     w = potrf_group_at(b0, nblk);
-    for (int j = 0; j < w; ++j) {
-      const long r0 = (long)(b0 + j) * DB;
-      if (j > 0) {   // block column b0+j, rows from block b0+j down:  A -= P[:, b0:b0+j] * P[b0+j, b0:b0+j]^T
-        GemmArgs g{};
-        g.A = A + r0 * ld + (long)b0 * DB; g.lda = ld; g.strideA = strideA;
-        g.B = g.A; g.ldb = ld; g.strideB = strideA;
-        g.C = A + r0 * ld + r0; g.ldc = ld; g.strideC = strideA;
-        g.M = n - (int)r0; g.N = DB; g.K = j * DB; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kmode = K_FULL;
-        if ((rc = launch_gemm_ws<false, false>(g, batch, st))) return rc;
-      }
-      if ((rc = launch_diag_factor(A, ld, strideA, dinv, strideD, b0 + j, logdet_parts, nblk, info, batch, st))) return rc;
-      if ((rc = launch_panel_trsm(A, n, ld, strideA, b0 + j, batch, st))) return rc;
-    }
+    if ((rc = factor_group(A, n, ld, strideA, batch, dinv, strideD, logdet_parts, nblk, info, b0, w, st))) return rc;
     if ((rc = after_panel(b0 + w))) return rc;
     const long r0 = (long)(b0 + w) * DB;
     if (r0 < n) {   // trailing update, lower tiles only, rank 128*w
@@ -750,22 +790,8 @@ static int potrf_lookahead(double* A, int n, long ld, double* dinv, double* logd
   RC_CUDA_OK(cudaEventRecord(cx->fork0, st));
   RC_CUDA_OK(cudaStreamWaitEvent(hi, cx->fork0, 0));
   int rc;
-  auto factor_group = [&](int g) -> int {
-    const int b0 = start[g], w = start[g + 1] - b0;
-    for (int j = 0; j < w; ++j) {
-      const long r0 = (long)(b0 + j) * DB;
-      if (j > 0) {
-        GemmArgs u{};
-        u.A = A + r0 * ld + (long)b0 * DB; u.lda = ld;
-        u.B = u.A; u.ldb = ld;
-        u.C = A + r0 * ld + r0; u.ldc = ld;
-        u.M = n - (int)r0; u.N = DB; u.K = j * DB; u.alpha = -1.0; u.beta = 1.0; u.kmode = K_FULL;
-        if ((rc = launch_gemm_ws<false, false>(u, 1, hi))) return rc;
-      }
-      if ((rc = launch_diag_factor(A, ld, 0, dinv, strideD, b0 + j, logdet_parts, nblk, info, 1, hi))) return rc;
-      if ((rc = launch_panel_trsm(A, n, ld, 0, b0 + j, 1, hi))) return rc;
-    }
-    return 0;
+  auto factor_group_on_chain = [&](int g) -> int {
+    return factor_group(A, n, ld, 0, 1, dinv, strideD, logdet_parts, nblk, info, start[g], start[g + 1] - start[g], hi);
   };
   // lower tiles of the square that starts at block `from`, rank = group g; col_tiles > 0: only its first col_tiles tile columns
   auto update = [&](int g, int from, int col_tiles, cudaStream_t stream, int yield) -> int {
@@ -796,7 +822,7 @@ static int potrf_lookahead(double* A, int n, long ld, double* dinv, double* logd
   };
   mark('0', 0, hi);
   for (int g = 0; g < G; ++g) {
-    if ((rc = factor_group(g))) return rc;
+    if ((rc = factor_group_on_chain(g))) return rc;
     mark('F', g, hi);
     if (g + 1 == G) break;
     const bool split = g + 2 < G && nblk - start[g + 2] >= LA_TAIL;
