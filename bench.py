@@ -42,17 +42,16 @@ for p in (ROOT, ROOT / 'rom-comma_b200'):
         sys.path.insert(0, str(p))
 
 METRIC, UNIT = 'mogpr_lml_grad_evals_per_s', 'evals/s'
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (gemm_dmma_ws_kernel) from the committed `ncu --set full` captures, per
-# launch (constants from profiles/, NOT measured in this run): the first rank-512 trailing update of potrf, the top level of trtri and the
-# selected LAUUM.  Algorithmic bytes of the same launches (operands once + C read/write): 2.08 GB, 1.34 GB, 1.34 GB - the re-reads of
-# the long-K launches are L2 capacity misses; at <= 0.3 TB/s (5 % of the HBM bandwidth) they are not the bound.
-NCU_TRAFFIC = {'syrk_rank512_first_launch_bytes': 2.401e9, 'syrk_rank512_first_launch_algorithmic_bytes': 2.08e9,
-               'trtri_top_level_launch_bytes': 4.83e9, 'trtri_top_level_launch_algorithmic_bytes': 1.34e9,
-               'trtri_top_level_note': 'L2-blocked 12 x 12 tile raster: 4.8 GB in 15.96 ms (18.0 GB in 16.29 ms with column-major tile order); DMMA pipe '
-                                       '94.6 % active, L2 hit rate 78 %',
-               'lauum_selected_launch_bytes': 3.42e9, 'lauum_selected_launch_algorithmic_bytes': 1.34e9,
-               'source': 'profiles/r01_ncu_syrk512_raster.csv (L2-blocked raster + streaming C accesses: 2.40 GB, DMMA pipe 90.6 % of active cycles; '
-                         '3.47 GB before, profiles/r01_ncu_ws_syrk512.md), profiles/r01_ncu_trtri_top_lauum_raster.csv'}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (gemm_dmma_ws_kernel) from the committed `ncu --set full` captures of round 2
+# (profiles/r02_ncu_gemm.md), per launch - constants from profiles/, NOT measured in this run: the first trailing update of potrf (rank 2048), the
+# two launches of the top level of trtri and the selected LAUUM.  Algorithmic bytes of the same launches (operands once + C read/write): 1.88 GB,
+# 1.34 GB, 1.34 GB.  The re-reads are L2 capacity misses of 12 x 12 super-tiles whose operand panels are up to 8192 long; at <= 0.44 TB/s (7 % of
+# the HBM bandwidth) with the DMMA pipe 97-98 % busy they are not the bound.
+NCU_TRAFFIC = {'syrk_rank2048_first_launch_bytes': 5.145e9, 'syrk_rank2048_first_launch_algorithmic_bytes': 1.88e9,
+               'trtri_top_level_launch_bytes': [4.804e9, 5.169e9], 'trtri_top_level_launch_algorithmic_bytes': 1.34e9,
+               'lauum_selected_launch_bytes': 3.420e9, 'lauum_selected_launch_algorithmic_bytes': 1.34e9,
+               'dmma_pipe_active_pct': {'syrk_rank2048': 97.6, 'trtri_top_level': 98.0, 'lauum_selected': 97.4},
+               'source': 'profiles/r02_ncu_gemm.md (ncu --set full --clock-control none on tools/eval_cfg3.py, B200)'}
 
 
 def parse():
@@ -492,7 +491,7 @@ def run_b200(args):
                            'l2': 'inputs larger than L2: each step rewrites and re-reads 2.1 GB matrices (126 MB L2), no explicit flush needed'},
                 'roofline': {'bound': 'tensor', 'kernel': 'gemm_dmma_ws_kernel (warp-specialised TMA-fed FP64 DMMA.8x8x4 tiles: Cholesky trailing update, triangular inverse, LAUUM)',
                              'achieved': achieved, 'peak': peaks['dmma_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['dmma_tflops'],
-                             'traffic': NCU_TRAFFIC['trtri_top_level_launch_bytes'], 'traffic_detail': NCU_TRAFFIC,
+                             'traffic': NCU_TRAFFIC['trtri_top_level_launch_bytes'][1], 'traffic_detail': NCU_TRAFFIC,
                              'launches_per_step': prof.launches, 'kernel_ms_per_step': prof.ms, 'kernel_share_of_step': prof.ms / (serial_ms or ms_per_step),
                              'one_stream_step_ms': serial_ms,
                              'flops_per_step': prof.flops, 'reference_flops_per_step': float(n) ** 3,
@@ -502,7 +501,7 @@ def run_b200(args):
                                      'n^3 (n^3/3 potrf + n^3/3 trtri + n^3/3 lauum) because, with the default trainables and a diagonal F, K^-1 is only '
                                      'formed on its diagonal (l,l) blocks (RC_GRAD_F_DIAGONAL); peak = FP64 tensor peak measured live by a '
                                      'register-resident DMMA loop (MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 is ~37-40 TFLOP/s); '
-                                     'traffic = ncu dram bytes (read+write) of the launch with the most traffic (top level of trtri, 16.4 ms); see traffic_detail for the other captured launches',
+                                     'traffic = ncu dram bytes (read+write) of the launch with the most traffic per flop (second launch of the top level of trtri, 15.4 ms); see traffic_detail for the other captured launches',
                              'stages': stages},
                 'cpu_baseline': cpu, 'parity_full_size': parity,
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
