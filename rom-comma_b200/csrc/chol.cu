@@ -640,8 +640,8 @@ int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, con
 // ----------------------------------------------------------------------------------------------------------------
 // Triangular inverse (in place) and K^-1 = L^-T L^-1 (out of place, lower triangle).
 // ----------------------------------------------------------------------------------------------------------------
-__global__ void copy_dinv_to_diag_kernel(double* __restrict__ A, long ld, long strideA, const double* __restrict__ dinv, long strideD) {
-  const int blk = blockIdx.x, z = blockIdx.y;
+__global__ void copy_dinv_to_diag_kernel(double* __restrict__ A, long ld, long strideA, const double* __restrict__ dinv, long strideD, int first_block) {
+  const int blk = first_block + blockIdx.x, z = blockIdx.y;
   double* Ab = A + (long)z * strideA + (long)blk * DB * (ld + 1);
   const double* Db = dinv + (long)z * strideD + (long)blk * DB * DB;
   for (int idx = threadIdx.x; idx < DB * DB; idx += blockDim.x) Ab[(long)(idx >> 7) * ld + (idx & 127)] = Db[idx];
@@ -649,22 +649,30 @@ __global__ void copy_dinv_to_diag_kernel(double* __restrict__ A, long ld, long s
 
 // Bottom-up recursive doubling: with Z11, Z22 the inverses of two adjacent diagonal blocks of size h,
 //   Z21 = -Z22 * (L21 * Z11),  all pairs of a level batched into two launches.  `tmp` needs >= n*n/4 doubles per matrix.
-int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double* dinv, double* tmp, long strideT, cudaStream_t st) {
+// rest_from > 0 (a power of two times 128, < n): the leading rest_from x rest_from block has been inverted already (by a call with n = rest_from,
+// possibly while the factorisation of the trailing columns was still running - potrf_trtri_lower); do everything else: the pairs of every level
+// that lie beyond it and the level(s) that couple it to the rest.  Every pair is computed exactly as in the one-call form.  strideD_blocks: blocks
+// per matrix in dinv (0 = n / 128).  tiles_per_cta > 0: yielding launches (background work on a low-priority stream).
+int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double* dinv, double* tmp, long strideT, cudaStream_t st, int rest_from,
+                int strideD_blocks, int tiles_per_cta) {
   RC_REQUIRE(n > 0 && n % DB == 0, -2, "trtri_lower: n=%d must be a positive multiple of 128", n);
+  RC_REQUIRE(rest_from >= 0 && rest_from < n && rest_from % DB == 0 && (rest_from & (rest_from - 1)) == 0, -2,
+             "trtri_lower: rest_from=%d must be 0 or a power of two times 128 below n=%d", rest_from, n);
   const int nblk = n / DB;
-  const long strideD = (long)nblk * DB * DB;
-  copy_dinv_to_diag_kernel<<<dim3(nblk, batch), 256, 0, st>>>(A, ld, strideA, dinv, strideD);
+  const long strideD = (long)(strideD_blocks > 0 ? strideD_blocks : nblk) * DB * DB;
+  copy_dinv_to_diag_kernel<<<dim3(nblk - rest_from / DB, batch), 256, 0, st>>>(A, ld, strideA, dinv, strideD, rest_from / DB);
   RC_LAUNCH_OK();
   int rc;
   for (long h = DB; h < n; h *= 2) {
     const int np = (int)(n / (2 * h));
     const long rem = n - (long)np * 2 * h;
+    const int first_pair = (rest_from > 0 && 2 * h <= rest_from) ? (int)(rest_from / (2 * h)) : 0;     // pairs inside the finished leading block
     // (count, h2): full problems then the ragged one (second block shorter)
     for (int pass = 0; pass < 2; ++pass) {
-      const int count = pass == 0 ? np : ((rem > h) ? 1 : 0);
-      if (count == 0) continue;
+      const int count = pass == 0 ? np - first_pair : ((rem > h) ? 1 : 0);
+      if (count <= 0) continue;
       const long h2 = pass == 0 ? h : rem - h;
-      const long base = pass == 0 ? 0 : (long)np * 2 * h;
+      const long base = pass == 0 ? (long)first_pair * 2 * h : (long)np * 2 * h;
       {   // the pairs of a level are the inner batch of one launch, the matrices its outer batch (looping over the matrices cost 120 latency-sized
           // launches = 7.5 of the 11 ms of a batched evaluation of ten n = 1920 folds)
         double* Az = A + base * (ld + 1);
@@ -675,14 +683,14 @@ int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double
         g.C = Tz; g.ldc = h; g.strideC = h * h;
         g.M = (int)h2; g.N = (int)h; g.K = (int)h; g.alpha = 1.0; g.beta = 0.0; g.kmode = K_GE_N0;
         g.batch2 = batch; g.strideA2 = strideA; g.strideB2 = strideA; g.strideC2 = strideT;
-        if ((rc = launch_gemm_ws<false, true>(g, count, st))) return rc;
+        if ((rc = launch_gemm_ws<false, true>(g, count, st, tiles_per_cta))) return rc;
         GemmArgs u{};   // Z21 = -Z22 * T    (Z22 lower, stored [m][k]  ->  k < m0 + 128)
         u.A = Az + h * ld + h; u.lda = ld; u.strideA = 2 * h * (ld + 1);
         u.B = Tz; u.ldb = h; u.strideB = h * h;
         u.C = Az + h * ld; u.ldc = ld; u.strideC = 2 * h * (ld + 1);
         u.M = (int)h2; u.N = (int)h; u.K = (int)h2; u.alpha = -1.0; u.beta = 0.0; u.kmode = K_LT_M1;
         u.batch2 = batch; u.strideA2 = strideA; u.strideB2 = strideT; u.strideC2 = strideA;
-        if ((rc = launch_gemm_ws<false, true>(u, count, st))) return rc;
+        if ((rc = launch_gemm_ws<false, true>(u, count, st, tiles_per_cta))) return rc;
       }
     }
   }
@@ -721,9 +729,9 @@ constexpr int OV_MAX_PANELS = 16;
 struct OverlapCtx {
   int device = -1;
   cudaStream_t user = nullptr;
-  cudaStream_t side = nullptr, hi = nullptr;
+  cudaStream_t side = nullptr, hi = nullptr, back = nullptr;       // bulk / chain / background (lowest priority)
   cudaEvent_t fork[OV_MAX_PANELS + 1] = {};
-  cudaEvent_t fork0 = nullptr, join = nullptr, join_hi = nullptr;
+  cudaEvent_t fork0 = nullptr, join = nullptr, join_hi = nullptr, early_fork = nullptr, early_done = nullptr;
 };
 // one side stream + event set per (device, caller stream): two evaluations in flight on two streams do not serialise each other
 OverlapCtx* overlap_ctx(int device, cudaStream_t user) {
@@ -738,8 +746,14 @@ OverlapCtx* overlap_ctx(int device, cudaStream_t user) {
   OverlapCtx& c = ctx[used];
   int lo = 0, hi = 0;
   if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;   // lo = least priority (what default streams have), hi = greatest
-  if (cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+  // three levels where the device has them (B200: 0 .. -5): chain > bulk > background; with two levels bulk and background share the lower one
+  int mid = (lo + hi) / 2;
+  if (mid == hi && lo != hi) mid = lo;
+  if (cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, mid) != cudaSuccess) return nullptr;
   if (cudaStreamCreateWithPriority(&c.hi, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&c.back, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&c.early_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&c.early_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   if (cudaEventCreateWithFlags(&c.fork0, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   if (cudaEventCreateWithFlags(&c.join_hi, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   for (int i = 0; i <= OV_MAX_PANELS; ++i)
@@ -774,7 +788,13 @@ static bool lookahead_env() {
   return v != 0;
 }
 
-static int potrf_lookahead(double* A, int n, long ld, double* dinv, double* logdet_parts, int* info, cudaStream_t st, OverlapCtx* cx) {
+// early_blocks > 0 (a power of two, < n / 128) with early_tmp: as soon as the chain has passed block column early_blocks, the inverse of the
+// leading early_blocks x early_blocks block of L - which is final from then on - is formed on the background stream (yielding launches, lowest
+// priority): it fills the SMs that the chain-bound second half of the factorisation leaves idle.  On return A's leading block holds Z11 = L11^-1;
+// the caller finishes with trtri_lower(..., rest_from = 128 * early_blocks).  Returns LA_NO_EARLY if the group boundaries never allowed it.
+constexpr int LA_NO_EARLY = -7;
+static int potrf_lookahead(double* A, int n, long ld, double* dinv, double* logdet_parts, int* info, cudaStream_t st, OverlapCtx* cx,
+                           int early_blocks = 0, double* early_tmp = nullptr) {
   const int nblk = n / DB;
   const long strideD = (long)nblk * DB * DB;
   static const int LA_TAIL = env_int("RC_POTRF_LA_TAIL", 16), YIELD = std::max(1, env_int("RC_POTRF_YIELD", 2));
@@ -807,6 +827,7 @@ static int potrf_lookahead(double* A, int n, long ld, double* dinv, double* logd
   };
   cudaEvent_t evF[2] = {cx->fork[0], cx->fork[1]}, evB[2] = {cx->fork[2], cx->fork[3]};
   bool bulk_pending = false;                     // a bulk update whose event the chain has not waited for yet
+  bool early_launched = false;
   int last_bulk = -1;
   // RC_POTRF_TIMELINE=1 (diagnostic, host-blocking): timestamps after every F_g / U_g on the chain and every B_g on the bulk stream
   static const bool timeline = env_int("RC_POTRF_TIMELINE", 0) != 0;
@@ -824,6 +845,16 @@ static int potrf_lookahead(double* A, int n, long ld, double* dinv, double* logd
   for (int g = 0; g < G; ++g) {
     if ((rc = factor_group_on_chain(g))) return rc;
     mark('F', g, hi);
+    if (early_blocks > 0 && !early_launched && start[g + 1] >= early_blocks && start[g + 1] < nblk) {
+      static const int YIELD_BACK = std::max(1, env_int("RC_EARLY_TRTRI_YIELD", 1));
+      RC_CUDA_OK(cudaEventRecord(cx->early_fork, hi));
+      RC_CUDA_OK(cudaStreamWaitEvent(cx->back, cx->early_fork, 0));
+      if ((rc = launch_diag_invert_all(A, ld, 0, dinv, strideD, early_blocks, 1, cx->back))) return rc;
+      if ((rc = trtri_lower(A, early_blocks * DB, ld, 0, 1, dinv, early_tmp, 0, cx->back, 0, nblk, YIELD_BACK))) return rc;
+      RC_CUDA_OK(cudaEventRecord(cx->early_done, cx->back));
+      early_launched = true;
+      mark('E', g, hi);
+    }
     if (g + 1 == G) break;
     const bool split = g + 2 < G && nblk - start[g + 2] >= LA_TAIL;
     if (split) {
@@ -846,9 +877,13 @@ static int potrf_lookahead(double* A, int n, long ld, double* dinv, double* logd
     }
     mark('U', g, hi);
   }
-  if ((rc = launch_diag_invert_all(A, ld, 0, dinv, strideD, nblk, 1, hi))) return rc;
+  {   // the 128 x 128 inverses of the blocks the background work has not done already
+    const int b_first = early_launched ? early_blocks : 0;
+    if ((rc = launch_diag_invert_all(A + (long)b_first * DB * (ld + 1), ld, 0, dinv + (long)b_first * DB * DB, strideD, nblk - b_first, 1, hi))) return rc;
+  }
   RC_CUDA_OK(cudaEventRecord(cx->join_hi, hi));
   RC_CUDA_OK(cudaStreamWaitEvent(st, cx->join_hi, 0));
+  if (early_launched) RC_CUDA_OK(cudaStreamWaitEvent(st, cx->early_done, 0));
   if (last_bulk >= 0) {                          // every bulk update has been waited for by the chain already; join the stream itself for capture
     RC_CUDA_OK(cudaEventRecord(cx->join, lo));
     RC_CUDA_OK(cudaStreamWaitEvent(st, cx->join, 0));
@@ -864,7 +899,7 @@ static int potrf_lookahead(double* A, int n, long ld, double* dinv, double* logd
     fprintf(stderr, "\n");
     for (cudaEvent_t e : tl_ev) cudaEventDestroy(e);
   }
-  return 0;
+  return (early_blocks > 0 && !early_launched) ? LA_NO_EARLY : 0;
 }
 
 int potrf_lower(double* A, int n, long ld, long strideA, int batch, double* dinv, double* logdet_parts, int* info, cudaStream_t st, bool lookahead) {
@@ -897,8 +932,21 @@ int potrf_trtri_lower(double* A, int n, long ld, double* dinv, double* logdet_pa
   RC_CUDA_OK(cudaGetDevice(&dev));
   const bool aligned = potrf_group_env() == 0 || (8 % potrf_group_env()) == 0;      // panel boundaries (multiples of 8 blocks) must fall on group boundaries
   OverlapCtx* cx = (aligned && panels >= 2 && nblk >= 2 * panels && potrf_trtri_tmp_doubles(n, panels) <= tmp_doubles) ? overlap_ctx(dev, st) : nullptr;
-  if (!cx) {   // small problem (nothing to hide) or no scratch: plain sequence
+  if (!cx) {   // no panel overlap asked for (the default), small problem or no scratch
     RC_REQUIRE(tmp_doubles >= (size_t)n * n / 4, -2, "potrf_trtri_lower: scratch too small");
+    static const bool early_on = env_int("RC_EARLY_TRTRI", 1) != 0;
+    static const int la_min = env_int("RC_POTRF_LA_MIN_BLOCKS", 32);
+    if (lookahead && early_on && lookahead_env() && nblk >= la_min && ld >= n && ld % 2 == 0) {
+      // look-ahead factorisation with the inverse of the leading block (the largest power of two of blocks below nblk) formed in its second half
+      int early = 1;
+      while (2 * early < nblk) early *= 2;
+      if (OverlapCtx* la = overlap_ctx(dev, st)) {
+        rc = potrf_lookahead(A, n, ld, dinv, logdet_parts, info, st, la, early, tmp);
+        if (rc == 0) return trtri_lower(A, n, ld, 0, 1, dinv, tmp, 0, st, early * DB);
+        if (rc != LA_NO_EARLY) return rc;
+        return trtri_lower(A, n, ld, 0, 1, dinv, tmp, 0, st);        // the group boundaries never reached the block: plain inverse
+      }
+    }
     if ((rc = potrf_lower(A, n, ld, 0, 1, dinv, logdet_parts, info, st, lookahead))) return rc;
     return trtri_lower(A, n, ld, 0, 1, dinv, tmp, 0, st);
   }

@@ -24,7 +24,10 @@ int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, con
                    cudaStream_t st);
 
 // A (holding L) <- L^-1 in place; tmp needs n*n/4 doubles per matrix.
-int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double* dinv, double* tmp, long strideT, cudaStream_t st);
+// rest_from > 0: the leading rest_from x rest_from block is inverted already (a call with n = rest_from and strideD_blocks = blocks of the whole
+// matrix); strideD_blocks: blocks per matrix in dinv (0 = n / 128); tiles_per_cta > 0: yielding launches.
+int trtri_lower(double* A, int n, long ld, long strideA, int batch, const double* dinv, double* tmp, long strideT, cudaStream_t st, int rest_from = 0,
+                int strideD_blocks = 0, int tiles_per_cta = 0);
 
 // potrf_lower + trtri_lower of ONE matrix with the independent part of the inverse running on a side stream inside the factorisation's
 // idle phases (chol.cu); on return (in stream order) A holds Z = L^-1, dinv the block inverses, logdet_parts / info as potrf_lower.
