@@ -227,6 +227,48 @@ WORKER = textwrap.dedent('''
 ''')
 
 
+FOLD_WORKER = textwrap.dedent('''
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, sys.argv[1])
+    from romcomma import distributed
+    distributed.init_from_env('gloo')
+    from romcomma.user import run
+    r = distributed.rank()
+    run.Fold = lambda repo, k: k                                   # the job only needs the fold number here
+    repo = SimpleNamespace(folds=range(5), L=1, N=10)
+    done = run._each_owned_fold(repo, lambda k: 10 * k, side_by_side=False)
+    assert done == [10 * k for k in range(5) if k % 2 == r], done
+    def job(k):
+        if k == 3:
+            raise ValueError('fold 3 is broken')                    # fold 3 belongs to rank 1
+        return k
+    try:
+        run._each_owned_fold(repo, job, side_by_side=False)
+        print('rank', r, 'no error')
+    except ValueError as e:
+        print('rank', r, 'own error:', e)
+    except RuntimeError as e:
+        print('rank', r, 'peer error:', e)
+    distributed.barrier()                                          # nobody is left behind: both ranks reach the barrier
+    print('rank', r, 'ok')
+''')
+
+
+def test_world_size_2_fold_failure_is_agreed_on(tmp_path):
+    """user.run shards the folds over the ranks; when one rank's fold raises, the other ranks learn about it (one all-reduce of an error flag)
+    and raise too instead of waiting at the collecting barrier until the backend times out (round-1 advice)."""
+    script = tmp_path / 'fold_worker.py'
+    script.write_text(FOLD_WORKER)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29537', WORLD_SIZE='2', OMP_NUM_THREADS='1')
+    procs = [subprocess.Popen([sys.executable, str(script), str(ROOT / 'rom-comma_b200')], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert 'rank 0 peer error' in outs[0] and 'rank 1 own error: fold 3 is broken' in outs[1], outs
+    assert 'rank 0 ok' in outs[0] and 'rank 1 ok' in outs[1]
+
+
 def test_world_size_2_gloo_gather(tmp_path):
     script = tmp_path / 'worker.py'
     script.write_text(WORKER)
