@@ -364,7 +364,7 @@ size_t grad_workspace_bytes(int n_pad, int L, int M, int batch) {
 int grad_reduce(GradArgs a, int n_pad, int batch, double* out, cudaStream_t st) {
   RC_REQUIRE(n_pad % GT == 0, -2, "grad_reduce: n_pad must be a multiple of 64");
   a.nvals = grad_nvals(a.L, a.M);
-  a.slots = grad_slots(a.L, a.N);
+  a.slots = a.Nz ? a.L : grad_slots(a.L, a.N);     // per-problem sample counts (folds): a small problem packs more outputs into one 64-row tile
   const long t = n_pad / GT, tiles = t * (t + 1) / 2;
   const size_t smem = (size_t)(2 * GT * a.M + 2 * GT + 32 + 16 * a.slots * a.M) * sizeof(double) + 4 * GT * sizeof(int);
   RC_REQUIRE(smem <= 200 * 1024, -2, "grad_reduce: M=%d / slots=%d need %zu bytes of shared memory (> 200 KB)", a.M, a.slots, smem);

@@ -537,6 +537,21 @@ def test_sobol_lattice_form_all_subsets(C, N, M, L, diag):
     assert_close(parts, V, rtol=1e-10, atol=1e-12 * scale, what='row-tile parts add up (lattice form)')
 
 
+def test_lml_grad_multi_tiny_problems_many_outputs(C):
+    """A batch whose smaller problems pack several outputs into one 64-row tile (found by tools/fuzz_parity.py: the gradient reduction sized its
+    per-tile output slots for the largest problem of the batch)."""
+    L, M = 4, 4
+    probs = [random_problem(N, M, L, seed=90 + N, full_F=True, full_E=False) for N in (64, 9, 23, 3)]
+    plan = C.LmlGradMultiPlan([C.dev(p[0]) for p in probs], [C.dev(p[1]) for p in probs], L, C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES)
+    res = plan.unpack(plan(C.dev(np.concatenate([p[2] for p in probs])), C.dev(np.stack([p[3] for p in probs])), C.dev(np.stack([p[4] for p in probs]))).cpu().numpy())
+    assert plan.info.cpu().tolist() == [0] * 4
+    for z, p in enumerate(probs):
+        ref = gp.lml_grad_mo(*p)
+        assert_close(res[z]['lml'], ref['lml'], what=f'lml[{z}]')
+        for k in ('dF', 'dE', 'dls'):
+            assert_close(res[z][k], ref[k], atol=1e-10 * L * p[0].shape[0] + 1e-9, what=f'{k}[{z}]')
+
+
 @pytest.mark.parametrize('L', [1, 2])
 def test_lml_grad_multi_independent_problems(C, L):
     """rc_lml_grad_multi: problems with their OWN inputs, outputs and sample counts (folds) in one batched call.  Problems of equal padded size

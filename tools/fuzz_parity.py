@@ -68,5 +68,52 @@ while time.time() - t0 < budget:
             err = np.abs(v - ref_v)
             bound = 1e-10 + 1e-8 * np.abs(ref_v) + 8 * np.finfo(float).eps * absum
             assert np.all(err <= bound), f'{tag} sobol mask={m:b}: max err/bound {np.max(err / bound):.2f}, max abs err {err.max():.3e}'
+        # round 2: the lattice form (lists holding at least half of a block of 2^min(6,M) subsets) against the sweep form / the one-exp-per-subset
+        # kernel, which the same subsets reach through a sparse list; row-tile parts of a multi-GPU sweep
+        if M >= 3:
+            KL = min(6, M)
+            block = int(rng.integers(0, 1 << (M - KL))) << KL
+            dense = [block | lo for lo in rng.permutation(1 << KL)[: int(rng.integers((1 << KL) // 2, (1 << KL) + 1))]]
+            Vd = C.sobol_contract(dX, Phi, g0KY, L, True, dense).cpu().numpy()
+            Vs = np.stack([C.sobol_contract(dX, Phi, g0KY, L, True, [m]).cpu().numpy()[0] for m in dense[:4]])
+            cal0 = sobol.ClosedSobol(X, ls, F, KiY, True)
+            worst_sum = np.zeros((L, L))               # sum |terms| of these subsets: what the rounding of ANY evaluation order scales with
+            for m in dense[:4]:
+                idx = [i for i in range(M) if (m >> i) & 1]
+                perm = idx + [i for i in range(M) if i not in idx]
+                for l in range(L):
+                    for j in range(L):
+                        H = sobol.H_block(X[:, perm], cal0.Phi[l, 0][perm], cal0.Phi[j, 0][perm], 0, len(idx))
+                        worst_sum[l, j] = max(worst_sum[l, j], np.abs(cal0.g0KY[l, 0]) @ (np.abs(H) @ np.abs(cal0.g0KY[j, 0])))
+            bound = 1e-10 + 1e-8 * np.abs(Vs) + 16 * np.finfo(float).eps * worst_sum
+            assert np.all(np.abs(Vd[:4] - Vs) <= bound), f'{tag} lattice form vs single subsets: {np.max(np.abs(Vd[:4] - Vs) / bound):.2f} of the bound'
+            nparts = int(rng.integers(2, 5))
+            tot = sum(C.sobol_contract(dX, Phi, g0KY, L, True, dense, None, r, nparts).cpu().numpy() for r in range(nparts))
+            assert np.all(np.abs(tot - Vd) <= 1e-10 + 1e-8 * np.abs(Vd) + 16 * np.finfo(float).eps * worst_sum.max()), f'{tag} lattice parts add up'
+
+        # round 2: errors with the MIXED rank equation against the oracle (small N only: the oracle is O(L^2 N^2) per subset and call)
+        if N <= 200 and M <= 6:
+            from oracle import sobol_error
+            cho = gp.k_cho_mo(X, ls, F, E)
+            fac = C.Factorization(C.gram(dX, None, args[0], args[1], args[2], lower_only=True, pad_to=L * N, pad_identity=True))
+            refe = sobol_error.ClosedSobolWithError(X, ls, Fd, KiY, cho, is_T_partial=False)
+            m0 = int(rng.integers(0, M))
+            m1 = int(rng.integers(m0 + 1, M + 1))
+            Ve, We, Wm = (t.cpu().numpy() for t in C.sobol_error(dX, C.dev(ls), C.dev(Fd), Phi, g0, g0KY, fac, [C.slice_mask(m0, m1)], mixed=True))
+            out = refe.marginalize((m0, m1))
+            assert np.all(np.abs(We[0] - out['W']) <= 1e-7 * out['W_scale'] + 1e-10), f'{tag} W[{m0}:{m1}]'
+            assert np.all(np.abs(Wm[0] - out['WMm']) <= 1e-7 * out['WMm_scale'] + 1e-10), f'{tag} WMm[{m0}:{m1}]'
+    # round 2: independent problems in one batched call (rc_lml_grad_multi) - this problem beside two smaller random ones
+    if L * N <= 600:
+        others = [random_problem(max(2, int(rng.integers(2, N + 1))), M, L, seed=int(rng.integers(1 << 30)), full_F=full_F) for _ in range(2)]
+        probs = [(X, Y, ls, F, E)] + others
+        mp = C.LmlGradMultiPlan([C.dev(p[0]) for p in probs], [C.dev(p[1]) for p in probs], L, C.RC_GRAD_VARIANCE | C.RC_GRAD_LENGTHSCALES)
+        outm = mp.unpack(mp(C.dev(np.concatenate([p[2] for p in probs])), C.dev(np.stack([p[3] for p in probs])), C.dev(np.stack([p[4] for p in probs]))).cpu().numpy())
+        assert mp.info.cpu().tolist() == [0, 0, 0], tag
+        for z, pz in enumerate(probs):
+            rz = ref if z == 0 else gp.lml_grad_mo(*pz)
+            assert_close(outm[z]['lml'], rz['lml'], what=f'{tag} multi[{z}] lml')
+            for k in ('dF', 'dE', 'dls'):
+                assert_close(outm[z][k], rz[k], atol=1e-10 * L * pz[0].shape[0], what=f'{tag} multi[{z}] {k}')
     cases += 1
 print(f'fuzz ok: {cases} random cases in {time.time() - t0:.0f} s')
