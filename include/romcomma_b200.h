@@ -39,6 +39,12 @@ long rc_launch_count(void);
  * FP64 tensor-core (DMMA.8x8x4) TFLOP/s and FP64 exp() evaluations per second (in 1e9/s). scratch: >= 8 bytes of device memory. */
 int rc_measure_dmma_tflops(double* scratch, double* tflops_host);
 int rc_measure_exp_gexps(double* scratch, double* gexps_host);
+/* The same loop over the table form of the exp (csrc/common.cuh: exp_tab, 9 FP64 instructions + one shared-memory lookup), which the
+ * register form of the Sobol sweep kernel runs. */
+int rc_measure_exp_tab_gexps(double* scratch, double* gexps_host);
+/* Test hook: y[i] = exp(x[i]) evaluated by the device exp of the pairwise kernels; form 0 = polynomial (exp_pairwise), 1 = table (exp_tab).
+ * x, y: device pointers, n elements. */
+int rc_debug_exp(const double* x, double* y, long n, int form, rc_stream_t stream);
 
 /* Per-launch profile of the dominant kernel (gemm_dmma_kernel: FP64 DMMA tiles behind potrf / trtri / lauum / trsm), for bench.py's
  * roofline: between rc_profile_begin() and rc_profile_end() every GEMM launch is bracketed by CUDA events on its own stream.

@@ -115,6 +115,47 @@ __device__ __forceinline__ double exp_pairwise(double x) {
   return __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
 }
 
+// Table form of the same exp for the kernels that are bound by FP64 issue slots: 9 FP64 instructions instead of 14.
+//   x = (32 e + j) ln2/32 + r,  |r| <= ln2/64:   exp(x) = 2^e * T[j] * (1 + r (1 + r g(r))),   T[j] = 2^(j/32) from a 256-byte table in
+// SHARED memory (exp_table_fill; one 8-byte LDS per call - the table's 32 entries sit on 16 bank pairs, so a warp's lookup costs 2-4
+// wavefronts), g the degree-3 Chebyshev interpolant of (e^r - 1 - r)/r^2 (tools/exp_poly.py table: max relative error of the polynomial
+// 2.8e-16; with the rounding of T[j] and of the last FMA 5e-16 overall, tighter than the degree-10 form above).  The reduction is ONE FMA
+// with ln2/32 rounded to double (relative error 3.3e-17): r is off by 3.3e-17 |x|, i.e. the result carries a relative error of that size -
+// below one ulp for |x| < 3, and on terms of size e^x an absolute error <= 3.3e-17 |x| e^x <= 1.3e-17 otherwise.  Same range
+// convention as exp_pairwise (x < -708 -> -708; x > 709 is the caller's business).
+static __constant__ double rc_exp2_table[32] = {
+    1.00000000000000000e+00, 1.02189714865411663e+00, 1.04427378242741375e+00, 1.06714040067682370e+00,
+    1.09050773266525769e+00, 1.11438674259589243e+00, 1.13878863475669156e+00, 1.16372485877757748e+00,
+    1.18920711500272103e+00, 1.21524735998046896e+00, 1.24185781207348400e+00, 1.26905095719173322e+00,
+    1.29683955465100964e+00, 1.32523664315974132e+00, 1.35425554693689265e+00, 1.38390988196383202e+00,
+    1.41421356237309515e+00, 1.44518080697704665e+00, 1.47682614593949935e+00, 1.50916442759342284e+00,
+    1.54221082540794074e+00, 1.57598084510788650e+00, 1.61049033194925428e+00, 1.64575547815396495e+00,
+    1.68179283050742900e+00, 1.71861929812247793e+00, 1.75625216037329945e+00, 1.79470907500310717e+00,
+    1.83400808640934243e+00, 1.87416763411029996e+00, 1.91520656139714740e+00, 1.95714412417540018e+00,
+};
+// Every thread with threadIdx.x < 32 copies one entry; the caller's next __syncthreads() publishes the table.
+__device__ __forceinline__ void exp_table_fill(double* tab) {
+  if (threadIdx.x < 32) tab[threadIdx.x] = rc_exp2_table[threadIdx.x];
+}
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
+  // x < -708 -> (-708.00002, -708]: ONE unsigned min on the high word (negative doubles order by magnitude there; positive values and
+  // positive NaNs lie below the bound and pass; -inf and negative NaNs become -708, i.e. ~0)
+  x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC0862000u), __double2loint(x));
+  const double magic = 6755399441055744.0;
+  const double t = fma(x, 4.61662413084468283841e+01, magic);      // 32 / ln 2
+  const double k = t - magic;
+  const double r = fma(k, -2.16608493924982901946e-02, x);         // ln 2 / 32
+  const int ki = __double2loint(t);
+  const double T = tab[ki & 31];
+  double s = 8.33335685528634532e-03;
+  s = fma(s, r, 4.16668302325693199e-02);
+  s = fma(s, r, 1.66666666666312663e-01);
+  s = fma(s, r, 4.99999999997592204e-01);
+  s = fma(s, r, 1.0);
+  const double p = fma(T * r, s, T);
+  return __hiloint2double(__double2hiint(p) + (ki & ~31) * 32768, __double2loint(p));   // 2^(ki >> 5) into the exponent field
+}
+
 // Programmatic dependent launch: a kernel launched through launch_pdl may start (CTA scheduling, barrier / register set-up, descriptor
 // prefetch) while its predecessor in the stream drains; it must execute pdl_wait() before its first access to global memory, which also
 // makes the predecessor's writes visible.  pdl_launch_dependents() at the top of a kernel lets ITS successor do the same.  Kernels

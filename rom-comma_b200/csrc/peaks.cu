@@ -3,6 +3,7 @@
 // FP64 entry, so bench.py measures these on the box it runs on and says so next to every fraction.
 #include "../../include/romcomma_b200.h"
 #include "common.cuh"
+#include <algorithm>
 
 namespace rc {
 
@@ -34,6 +35,34 @@ __global__ void exp_peak_kernel(double* out, int iters) {
     }
   }
   if (s == 123.456) out[0] = s;
+}
+
+// The table form (exp_tab): the same loop, the table in shared memory as in the kernels that use it.
+__global__ void exp_tab_peak_kernel(double* out, int iters) {
+  __shared__ double etab[32];
+  exp_table_fill(etab);
+  __syncthreads();
+  double x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = -1e-3 * (threadIdx.x + i + 1);
+  double s = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s += exp_tab(x[i], etab);
+      x[i] *= 1.0000001;
+    }
+  }
+  if (s == 123.456) out[0] = s;
+}
+
+// Test hook: y[i] = exp(x[i]) through either device form.
+__global__ void exp_eval_kernel(const double* __restrict__ x, double* __restrict__ y, long n, int form) {
+  __shared__ double etab[32];
+  exp_table_fill(etab);
+  __syncthreads();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = form == 0 ? exp_pairwise(x[i]) : exp_tab(x[i], etab);
 }
 
 template <typename Launch>
@@ -87,6 +116,26 @@ int rc_measure_exp_gexps(double* scratch, double* gexps) {
   int rc = time_best([&] { exp_peak_kernel<<<sms * 2, threads>>>(scratch, iters); }, 5, &ms);
   if (rc) return rc;
   *gexps = (double)sms * 2 * threads * iters * 4.0 / ms * 1e-6;
+  return 0;
+}
+
+int rc_measure_exp_tab_gexps(double* scratch, double* gexps) {
+  RC_REQUIRE(scratch && gexps, -2, "rc_measure_exp_tab_gexps: null pointer");
+  int dev, sms;
+  RC_CUDA_OK(cudaGetDevice(&dev));
+  RC_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int iters = 2000, threads = 1024;
+  float ms;
+  int rc = time_best([&] { exp_tab_peak_kernel<<<sms * 2, threads>>>(scratch, iters); }, 5, &ms);
+  if (rc) return rc;
+  *gexps = (double)sms * 2 * threads * iters * 4.0 / ms * 1e-6;
+  return 0;
+}
+
+int rc_debug_exp(const double* x, double* y, long n, int form, rc_stream_t stream) {
+  RC_REQUIRE(x && y && n > 0 && (form == 0 || form == 1), -2, "rc_debug_exp: bad argument");
+  exp_eval_kernel<<<(unsigned)std::min<long>((n + 255) / 256, 4096), 256, 0, (cudaStream_t)stream>>>(x, y, n, form);
+  RC_LAUNCH_OK();
   return 0;
 }
 

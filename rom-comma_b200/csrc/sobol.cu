@@ -370,6 +370,150 @@ __global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs 
 }
 
 
+// Round 2, second form of the sweep kernel (M <= 12): the h values of a pass stay in REGISTERS and the exp is the table form (exp_tab).
+// The kernel above keeps two 256-thread CTAs per SM by parking h in shared memory; by ncu's wavefront count that parking, the 8-byte operand
+// loads and the bank conflicts of the stride-2 column reads cost 8 shared-memory cycles per warp-exp against 10.6 cycles of the FP64 pipe - the
+// two pipes were nearly co-critical, so a cheaper exp alone would only have moved the bound.  Here: 128 threads per CTA, three CTAs per SM
+// (168 registers per thread: 3M accumulators + M x 2RU live h), row operands {gamma x, su} and column operands {y, sv} interleaved so that one
+// 16-byte load fetches both (1.5 wavefronts per warp-exp), one table lookup per exp (2-4 wavefronts), 9 + 7 FP64 instructions per exp.
+// Same tiles, same outputs, same per-CTA partial sums as sobol_sweep_kernel (the finish kernels do not know the difference).
+constexpr int SRTHREADS = 128;
+
+template <int M, int RU>
+__global__ void __launch_bounds__(SRTHREADS, 3) sobol_sweep_reg_kernel(SobolPairArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double etab[32];
+  constexpr int nv = 3 * M, MP = (M + 1) & ~1;             // MP: M rounded up to even (16-byte alignment of what follows)
+  double* gam = sm;                                        // [M]
+  double* cu = gam + MP;                                   // -1/2 gamma p
+  double* cv = cu + MP;                                    // -1/2 gamma q
+  double* lp = cv + MP;                                    // -1/2 log psi
+  double2* rowd = reinterpret_cast<double2*>(lp + MP);     // [M][64]  { gamma_m x, cu_m x^2 + lp_m }
+  double2* cold = rowd + M * ST;                           // [M][64]  { y, cv_m y^2 }
+  double* cr = reinterpret_cast<double*>(cold + M * ST);   // [64]
+  double* cc = cr + ST;                                    // [64]
+  double* wpart = cc + ST;                                 // [4][3*M]
+
+  const int pidx = blockIdx.y;
+  int a = (int)((sqrt(8.0 * (double)pidx + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
+  while (a * (a + 1) / 2 > pidx) --a;
+  const int b = pidx - a * (a + 1) / 2;
+  const int ti = p.part + (int)(blockIdx.x / p.T) * p.nparts, tj = blockIdx.x % p.T;
+  double* out = p.parts + ((long)pidx * gridDim.x + blockIdx.x) * nv;
+  if (a == b && tj > ti) {   // covered by the mirrored tile (weight 2)
+    for (int s = threadIdx.x; s < nv; s += SRTHREADS) out[s] = 0.0;
+    return;
+  }
+  exp_table_fill(etab);
+  for (int m = threadIdx.x; m < M; m += SRTHREADS) {
+    const double pp = p.Phi[a * M + m], qq = p.Phi[b * M + m];
+    const double psi = 1.0 - pp * qq, g = pp * qq / psi;
+    gam[m] = g;
+    cu[m] = -0.5 * g * pp;
+    cv[m] = -0.5 * g * qq;
+    lp[m] = -0.5 * log(psi);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ST * M; e += SRTHREADS) {
+    const int r = e / M, m = e - r * M;
+    const int gi = ti * ST + r, gj = tj * ST + r;
+    const double x = gi < p.N ? p.X[(long)gi * M + m] : 0.0;
+    const double y = gj < p.N ? p.X[(long)gj * M + m] : 0.0;
+    rowd[m * ST + r] = make_double2(gam[m] * x, fma(cu[m] * x, x, lp[m]));
+    cold[m * ST + r] = make_double2(y, cv[m] * y * y);
+  }
+  for (int r = threadIdx.x; r < ST; r += SRTHREADS) {
+    const int gi = ti * ST + r, gj = tj * ST + r;
+    cr[r] = gi < p.N ? p.c[(long)a * p.N + gi] : 0.0;     // rows/columns beyond N carry zero weight
+    cc[r] = gj < p.N ? p.c[(long)b * p.N + gj] : 0.0;
+  }
+  __syncthreads();
+
+  constexpr int NP = 2 * RU;   // pairs per thread per pass
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // accF[m] = F[m] for m >= 1 (F[0] is P[1]);  accP[k-1] = P[k];  accS[k] = S[k] for 1 <= k <= M-2 (S[M-1] is F[M-1]);  accS[0] = E
+  double accF[M], accP[M], accS[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) accF[m] = accP[m] = accS[m] = 0.0;
+#pragma unroll 1
+  for (int pass = 0; pass < (ST / (8 * RU)) * 2; ++pass) {
+    const int r0 = (pass >> 1) * 8 * RU + ty * RU, c0 = (pass & 1) * 32 + tx * 2;
+    double w[NP], run[NP], h[M][NP];
+    {
+      const double2 ccv = *reinterpret_cast<const double2*>(cc + c0);
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const double cru = cr[r0 + u];
+        w[2 * u] = cru * ccv.x;
+        w[2 * u + 1] = cru * ccv.y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      run[q] = w[q];
+      accS[0] += w[q];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {     // exps, singles and prefixes
+      const double2 d0 = cold[m * ST + c0], d1 = cold[m * ST + c0 + 1];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const double2 rw = rowd[m * ST + r0 + u];
+        h[m][2 * u] = exp_tab(fma(rw.x, d0.x, rw.y + d0.y), etab);
+        h[m][2 * u + 1] = exp_tab(fma(rw.x, d1.x, rw.y + d1.y), etab);
+      }
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        if (m >= 1) accF[m] = fma(w[q], h[m][q], accF[m]);
+        run[q] *= h[m][q];
+        accP[m] += run[q];
+      }
+    }
+    if constexpr (M >= 3) {
+#pragma unroll
+      for (int q = 0; q < NP; ++q) run[q] = w[q] * h[M - 1][q];
+#pragma unroll
+      for (int m = M - 2; m >= 1; --m) {   // suffixes S[m] = prod_{j >= m} h_j
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          run[q] *= h[m][q];
+          accS[m] += run[q];
+        }
+      }
+    }
+  }
+  // warp reductions in a fixed order, then one partial per CTA.  wpart slots: [0,M) F, [M,2M) P[k] at M+k-1, [2M,3M) S[k] at 2M+k, E at 2M
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const double pr = warp_sum(accP[m]);
+    const double f = m >= 1 ? warp_sum(accF[m]) : pr;
+    if (lane == 0) {
+      wpart[warp * nv + m] = f;
+      wpart[warp * nv + M + m] = pr;
+    }
+    if (m == 0 || (m >= 1 && m <= M - 2)) {
+      const double sf = warp_sum(accS[m]);
+      if (lane == 0) wpart[warp * nv + 2 * M + m] = sf;
+    } else if (m == M - 1 && M >= 2) {
+      if (lane == 0) wpart[warp * nv + 2 * M + m] = f;
+    }
+  }
+  __syncthreads();
+  const double wgt = (a == b && ti != tj) ? 2.0 : 1.0;
+  for (int s = threadIdx.x; s < nv; s += SRTHREADS) {
+    // output index -> wpart slot:  F[m] -> m ; P[k] (s = M+k-1) -> M+k-1 ; S[k] (s = 2M+k-1) -> 2M+k ; E (s = 3M-1) -> 2M
+    int slot;
+    if (s < 2 * M) slot = s;
+    else if (s < 3 * M - 1) slot = s + 1;
+    else slot = 2 * M;
+    double v = 0.0;
+    for (int wdx = 0; wdx < SRTHREADS / 32; ++wdx) v += wpart[wdx * nv + slot];
+    out[s] = v * wgt;
+  }
+}
+
+
 // ---- all-subsets ("lattice") form -----------------------------------------------------------------------------------------
 // The product form holds for EVERY subset:  H_S = prod_{m in S} h_m.  A block of the subset lattice = the 2^KL subsets that share their
 // high mask bits hi (inputs KL..M-1) and run through all patterns lo of the KL low inputs:  H_(hi,lo) = H_hi * prod_{m in lo} h_m.  Per sample
@@ -584,6 +728,15 @@ static int launch_sweep(const SobolPairArgs& a, int npairs, cudaStream_t st) {
   return 0;
 }
 
+template <int M, int RU>
+static int launch_sweep_reg(const SobolPairArgs& a, int npairs, cudaStream_t st) {
+  const size_t smem = (size_t)(4 * ((M + 1) & ~1) + 4 * M * ST + 2 * ST + (SRTHREADS / 32) * 3 * M) * sizeof(double);
+  static_assert((4 * 14 + 4 * 12 * ST + 2 * ST + 4 * 36) * sizeof(double) <= 48 * 1024, "fits the default dynamic shared memory limit");
+  sobol_sweep_reg_kernel<M, RU><<<dim3(a.T * ((a.T - a.part + a.nparts - 1) / a.nparts), npairs), SRTHREADS, smem, st>>>(a);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
 // index of a structured subset in the sweep kernel's output, or -1 for a general subset
 int sobol_sweep_index(unsigned long long mask, int M) {
   const unsigned long long full = (M >= 64) ? ~0ull : ((1ull << M) - 1ull);
@@ -733,8 +886,27 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
     if (!structured.empty()) {
       SobolPairArgs a{};
       a.X = X; a.N = N; a.M = M; a.Phi = Phi; a.c = c; a.P = P; a.T = T; a.ns = 3 * M; a.parts = parts; a.part = part; a.nparts = nparts;
-      int rc = M <= 4 ? launch_sweep<4, 2>(a, npairs, st) : M <= 8 ? launch_sweep<8, 2>(a, npairs, st)
-               : M <= 12 ? launch_sweep<12, 2>(a, npairs, st) : launch_sweep<20, 1>(a, npairs, st);
+      // RC_SOBOL_SWEEP=park selects the round-1 form (h parked in shared memory, polynomial exp) for every M; default: registers + table exp up to M = 12
+      static const bool reg_form = [] { const char* e = getenv("RC_SOBOL_SWEEP"); return !e || e[0] != 'p'; }();
+      int rc;
+      if (reg_form && M <= 12) {
+        switch (M) {
+          case 1: rc = launch_sweep_reg<1, 2>(a, npairs, st); break;
+          case 2: rc = launch_sweep_reg<2, 2>(a, npairs, st); break;
+          case 3: rc = launch_sweep_reg<3, 2>(a, npairs, st); break;
+          case 4: rc = launch_sweep_reg<4, 2>(a, npairs, st); break;
+          case 5: rc = launch_sweep_reg<5, 2>(a, npairs, st); break;
+          case 6: rc = launch_sweep_reg<6, 2>(a, npairs, st); break;
+          case 7: rc = launch_sweep_reg<7, 2>(a, npairs, st); break;
+          case 8: rc = launch_sweep_reg<8, 2>(a, npairs, st); break;
+          case 9: rc = launch_sweep_reg<9, 1>(a, npairs, st); break;
+          case 10: rc = launch_sweep_reg<10, 1>(a, npairs, st); break;
+          case 11: rc = launch_sweep_reg<11, 1>(a, npairs, st); break;
+          default: rc = launch_sweep_reg<12, 1>(a, npairs, st); break;
+        }
+      } else
+        rc = M <= 4 ? launch_sweep<4, 2>(a, npairs, st) : M <= 8 ? launch_sweep<8, 2>(a, npairs, st)
+             : M <= 12 ? launch_sweep<12, 2>(a, npairs, st) : launch_sweep<20, 1>(a, npairs, st);
       if (rc) return rc;
       // contiguous runs of output slots are finished together (<= SOBOL_MAX_SLICES per launch)
       size_t i = 0;

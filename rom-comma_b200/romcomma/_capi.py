@@ -26,6 +26,8 @@ _SIGNATURES = {
     'rc_launch_count': (ctypes.c_long, []),
     'rc_measure_dmma_tflops': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
     'rc_measure_exp_gexps': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
+    'rc_measure_exp_tab_gexps': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
+    'rc_debug_exp': (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p]),
     'rc_debug_tile_order': (ctypes.c_int, [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     'rc_profile_begin': (ctypes.c_int, []),
     'rc_profile_end': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -150,7 +152,17 @@ def measure_peaks() -> dict:
     torch.cuda.synchronize()
     check(lib().rc_measure_dmma_tflops(ptr(scratch), ctypes.byref(tf)), 'rc_measure_dmma_tflops')
     check(lib().rc_measure_exp_gexps(ptr(scratch), ctypes.byref(ge)), 'rc_measure_exp_gexps')
-    return {'dmma_tflops': tf.value, 'exp_gexps': ge.value}
+    gt = ctypes.c_double(0.0)
+    check(lib().rc_measure_exp_tab_gexps(ptr(scratch), ctypes.byref(gt)), 'rc_measure_exp_tab_gexps')
+    return {'dmma_tflops': tf.value, 'exp_gexps': ge.value, 'exp_tab_gexps': gt.value}
+
+
+def debug_exp(x: torch.Tensor, form: int) -> torch.Tensor:
+    """exp(x) through the device exp of the pairwise kernels (form 0: polynomial, 1: table) - a test hook."""
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib().rc_debug_exp(ptr(x), ptr(y), x.numel(), form, stream_ptr()), 'rc_debug_exp')
+    return y
 
 
 class gemm_profile:

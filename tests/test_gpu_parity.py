@@ -458,6 +458,47 @@ def test_sobol_sweep_form_all_widths(C, N, M, L):
         assert_close(V[k], cal._V(*s), what=f'slice {s}')
 
 
+@pytest.mark.parametrize('M', list(range(1, 13)))
+def test_sobol_sweep_register_form_every_M(C, M):
+    """The register form of the sweep kernel is instantiated per M (1..12; two rows per thread up to M = 8, one beyond): every instantiation,
+    with ragged tiles (N = 150: 2.3 tiles) and two outputs, on all structured slices incl. the empty one, against the oracle."""
+    N, L = 150, 2
+    X, Y, ls, F, E = random_problem(N, M, L, seed=100 + M, full_E=False)
+    KiY = gp.k_inv_y_mo(X, Y, ls, F, E)
+    dX = C.dev(X)
+    Phi, g0, g0KY = C.sobol_prepare(dX, C.dev(ls), C.dev(np.diag(F).copy()), C.dev(KiY.reshape(L, N)), True)
+    slices = [(m, m + 1) for m in range(M)] + [(0, m + 1) for m in range(M)] + [(m + 1, M) for m in range(M)] + [(0, M)]
+    V = C.sobol_contract(dX, Phi, g0KY, L, True, [C.slice_mask(*s) for s in slices]).cpu().numpy()
+    cal = sobol.ClosedSobol(X, ls, F, KiY, True)
+    for k, s in enumerate(slices):
+        assert_close(V[k], cal._V(*s), what=f'M={M} slice {s}')
+
+
+@pytest.mark.parametrize('form,bound', [(0, 1.0e-15), (1, 6.0e-16)])
+def test_device_exp_forms_against_long_double(C, form, bound):
+    """The two device exps of the pairwise kernels (polynomial: exp_pairwise; table: exp_tab) against an 80-bit exp: maximum relative error on
+    the range the kernels use, the single-FMA reduction of the table form on large arguments (error grows as 3.3e-17 |x|), the clamp below
+    -708, NaN propagation, and exactness at 0."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-40.0, 2.0, 400000), rng.uniform(-1.0, 1.0, 100000), np.linspace(-0.7, 0.7, 100001)])
+    y = C.debug_exp(C.dev(x), form).cpu().numpy()
+    ref = np.exp(x.astype(np.longdouble))
+    rel = np.abs((y.astype(np.longdouble) - ref) / ref).astype(np.float64)
+    assert rel.max() <= bound + (3.4e-17 * 40 if form == 1 else 0.0), (form, rel.max())
+    inner = np.abs(x) <= 1.0
+    assert rel[inner].max() <= bound, (form, rel[inner].max())
+    big = rng.uniform(-700.0, 700.0, 100000)
+    yb = C.debug_exp(C.dev(big), form).cpu().numpy()
+    refb = np.exp(big.astype(np.longdouble))
+    relb = np.abs((yb.astype(np.longdouble) - refb) / refb).astype(np.float64)
+    assert relb.max() <= bound + (3.4e-17 * 700 if form == 1 else 0.0), (form, relb.max())
+    special = np.array([0.0, -708.0, -709.0, -1e4, -1e300, -np.inf, np.nan])
+    ys = C.debug_exp(C.dev(special), form).cpu().numpy()
+    assert ys[0] == 1.0
+    assert np.all(ys[1:6] >= 0.0) and np.all(ys[1:6] < 1e-300)
+    assert np.isnan(ys[6])
+
+
 @pytest.mark.parametrize('N', [300, 700])
 def test_lml_grad_plan_cuda_graph_replay_is_bit_identical(C, N):
     """Opt-in CUDA-graph replay of the evaluation (LmlGradPlan(use_graph=True)): same bits as the eager launches, for changing hyper-parameters.
