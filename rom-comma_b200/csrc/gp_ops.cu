@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
   double* out = p.out + (long)z * p.stride_out;
 
   const int Nr = p.Nz ? p.Nz[z] : p.N, Nc = p.Nz ? p.Nz[z] : p.N2;       // per-problem sample counts (folds) only exist for the square training gram
+  __shared__ double etab[32];
+  exp_table_fill(etab);
   stage_scaled(sr, li, ni, p.X + (long)z * p.stride_X, Nr, p.M, ls, p.L, (long)ti * GT);
   for (int s = 0; s < ntj; ++s)
     stage_scaled(sc + s * GT * p.M, lj + s * GT, nj + s * GT, p.X2 + (long)z * p.stride_X, Nc, p.M, ls, p.L, (long)(tj0 + s) * GT);
@@ -102,8 +104,8 @@ __global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
       for (int u = 0; u < 4; ++u) {
         const long gi = (long)ti * GT + ty * 4 + u;
         double2* dst = reinterpret_cast<double2*>(out + gi * p.ld_out + (long)tj * GT + tx * 4);
-        dst[0] = make_double2(f * exp_pairwise(-0.5 * acc[u][0]), f * exp_pairwise(-0.5 * acc[u][1]));
-        dst[1] = make_double2(f * exp_pairwise(-0.5 * acc[u][2]), f * exp_pairwise(-0.5 * acc[u][3]));
+        dst[0] = make_double2(f * exp_tab(-0.5 * acc[u][0], etab), f * exp_tab(-0.5 * acc[u][1], etab));
+        dst[1] = make_double2(f * exp_tab(-0.5 * acc[u][2], etab), f * exp_tab(-0.5 * acc[u][3], etab));
       }
       continue;
     }
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(GTHREADS) gram_kernel(GramArgs p) {
         const int l_j = lj[s * GT + c], n_j = nj[s * GT + c];
         double val;
         if (l_i >= 0 && l_j >= 0) {
-          val = exp_pairwise(-0.5 * acc[u][v]);
+          val = exp_tab(-0.5 * acc[u][v], etab);
           if (F) val *= F[l_i * p.L + l_j];
           if (E && n_i == n_j) val += E[l_i * p.L + l_j];
         } else {
@@ -221,6 +223,8 @@ __global__ void __launch_bounds__(GTHREADS) grad_reduce_kernel(GradArgs p) {
   const double* X = p.X + (long)z * p.stride_X;
   if (p.diag_blocks_only && ((long)ti * GT) / Nz > ((long)tj * GT + GT - 1) / Nz) return;   // tile lies wholly in off-diagonal blocks
   if ((long)tj * GT >= (long)L * Nz) return;                                                 // columns are all padding (smaller fold of a batch)
+  __shared__ double etab[32];
+  exp_table_fill(etab);
   stage_scaled(sr, li, ni, X, Nz, M, ls, L, (long)ti * GT);
   stage_scaled(sc, lj, nj, X, Nz, M, ls, L, (long)tj * GT);
   for (int r = threadIdx.x; r < GT; r += GTHREADS) {
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(GTHREADS) grad_reduce_kernel(GradArgs p) {
       const bool valid = li[r] >= 0 && lj[c] >= 0 && gj <= gi && (!p.diag_blocks_only || li[r] == lj[c]);
       const double wgt = (gj < gi && li[r] == lj[c]) ? 2.0 : 1.0;   // diagonal (l,l) blocks are symmetric: count the mirror
       const double W = valid ? (ar[r] * ac[c] - kv[v]) : 0.0;
-      const double U = exp_pairwise(-0.5 * d2[u][v]);
+      const double U = exp_tab(-0.5 * d2[u][v], etab);
       wu[u][v] = wgt * W * U;
       wn[u][v] = (valid && ni[r] == nj[c]) ? wgt * W : 0.0;
       wfu[u][v] = (valid && gj < gi) ? W * U * F[li[r] * L + lj[c]] : 0.0;

@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(STHREADS) sobol_pair_kernel(SobolPairArgs p) {
     for (int s = threadIdx.x; s < ns; s += STHREADS) out[s] = 0.0;
     return;
   }
+  __shared__ double etab[32];
+  exp_table_fill(etab);
   for (int m = threadIdx.x; m < M; m += STHREADS) {
     const double pp = p.Phi[a * M + m], qq = p.Phi[b * M + m];
     const double psi = 1.0 - pp * qq, g = pp * qq / psi;
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(STHREADS) sobol_pair_kernel(SobolPairArgs p) {
     for (int u = 0; u < 4; ++u) {
       double rowacc = 0.0;
 #pragma unroll
-      for (int v = 0; v < 4; ++v) rowacc = fma(ccc[v], exp_pairwise(fmin(e[u][v], 708.0)), rowacc);
+      for (int v = 0; v < 4; ++v) rowacc = fma(ccc[v], exp_tab(fmin(e[u][v], 708.0), etab), rowacc);
       acc = fma(crr[u], rowacc, acc);
     }
     acc = warp_sum(acc);
@@ -579,6 +581,8 @@ __global__ void __launch_bounds__(STHREADS, 1) sobol_lattice_kernel(SobolLattice
   const int b = pidx - a * (a + 1) / 2;
   const int ti = p.part + (int)blockIdx.x * p.nparts, tid = threadIdx.x;       // only this rank's row tiles are launched
   double* out = p.parts + (((long)pidx * gridDim.x + blockIdx.x) * p.nhi + blockIdx.z) * NLO;
+  __shared__ double etab[32];
+  exp_table_fill(etab);
   for (int m = tid; m < M; m += STHREADS) {
     const double pp = p.Phi[a * M + m], qq = p.Phi[b * M + m];
     const double psi = 1.0 - pp * qq, g = pp * qq / psi;
@@ -658,10 +662,10 @@ __global__ void __launch_bounds__(STHREADS, 1) sobol_lattice_kernel(SobolLattice
         const int cidx = tx + 16 * v;
         double e = shr + svh[cidx];
         for (int k = 0; k < nh; ++k) e = fma(gxh[k * ST + r], yyh[k * ST + cidx], e);
-        const double H = wr * cc[cidx] * exp_pairwise(fmin(e, 708.0));
+        const double H = wr * cc[cidx] * exp_tab(fmin(e, 708.0), etab);
         double h[KL];
 #pragma unroll
-        for (int m = 0; m < KL; ++m) h[m] = exp_pairwise(fma(gxl[m * ST + r], yyl[m * ST + cidx], sul[m * ST + r] + svl[m * ST + cidx]));
+        for (int m = 0; m < KL; ++m) h[m] = exp_tab(fma(gxl[m * ST + r], yyl[m * ST + cidx], sul[m * ST + r] + svl[m * ST + cidx]), etab);
         acc[0] += H;
         lattice_walk<KL, 0, 0>(acc, h, H);
       }

@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(ETHREADS) sobol_error_matvec_kernel(ErrMatvecA
   const int tid = threadIdx.x;
   const int row0 = rc * RCH, col0 = tj * EC;
 
+  __shared__ double etab[32];
+  exp_table_fill(etab);
   for (int m = tid; m < M; m += ETHREADS) {
     cA[m] = p.coef[(0L * J + job) * M + m];
     cB[m] = p.coef[(1L * J + job) * M + m];
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(ETHREADS) sobol_error_matvec_kernel(ErrMatvecA
       for (int u = 0; u < 4; ++u) {
         const double w = wl[rbase + u];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) colacc[v] = fma(w, exp_pairwise(fmin(e[u][v], 708.0)), colacc[v]);
+        for (int v = 0; v < 4; ++v) colacc[v] = fma(w, exp_tab(fmin(e[u][v], 708.0), etab), colacc[v]);
       }
     }
 #pragma unroll
@@ -242,6 +244,8 @@ __global__ void __launch_bounds__(ETHREADS, 2) sobol_error_sweep_kernel(ErrMatve
   const int li = job % (p.L * p.L), l = li / p.L;
   const int tid = threadIdx.x;
   const int row0 = rc * RCH, col0 = tj * SW_EC;
+  __shared__ double etab[32];
+  exp_table_fill(etab);
   for (int m = tid; m < M; m += ETHREADS) {
     cA[m] = p.coef[(0L * J + job) * M + m];
     cB[m] = p.coef[(1L * J + job) * M + m];
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(ETHREADS, 2) sobol_error_sweep_kernel(ErrMatve
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const double x = xs[(long)m * RCH + r0 + q];
-          const double h = exp_pairwise(fma(x, b0, fma(ca * x, x, ck) + v0));
+          const double h = exp_tab(fma(x, b0, fma(ca * x, x, ck) + v0), etab);
           if (m >= 1) hme[(m * 4 + q) * ETHREADS] = h;
           f = fma(w[q], h, f);
           run[q] *= h;
