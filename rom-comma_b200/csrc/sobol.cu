@@ -93,6 +93,7 @@ struct SobolPairArgs {
   int ns;
   double* parts;       // [npairs][T*T][ns]
   int part, nparts;    // this call evaluates the row tiles ti with ti % nparts == part (multi-GPU: partial V, summed by the caller)
+  int chunk;           // register form of the sweep kernel: column tiles per CTA
   unsigned long long masks[SOBOL_MAX_SLICES];
 };
 
@@ -391,9 +392,9 @@ __global__ void __launch_bounds__(SRTHREADS, 3) sobol_sweep_reg_kernel(SobolPair
   double* cv = cu + MP;                                    // -1/2 gamma q
   double* lp = cv + MP;                                    // -1/2 log psi
   double2* rowd = reinterpret_cast<double2*>(lp + MP);     // [M][64]  { gamma_m x, cu_m x^2 + lp_m }
-  double2* cold = rowd + M * ST;                           // [M][64]  { y, cv_m y^2 }
+  double2* cold = rowd + M * ST;                           // [M][64]  { y, cv_m y^2 }   of the current column tile
   double* cr = reinterpret_cast<double*>(cold + M * ST);   // [64]
-  double* cc = cr + ST;                                    // [64]
+  double* cc = cr + ST;                                    // [64]    column weights of the current tile (x 2 for a mirrored tile)
   double* wpart = cc + ST;                                 // [4][3*M]
 
   const int pidx = blockIdx.y;
@@ -401,9 +402,12 @@ __global__ void __launch_bounds__(SRTHREADS, 3) sobol_sweep_reg_kernel(SobolPair
   while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
   while (a * (a + 1) / 2 > pidx) --a;
   const int b = pidx - a * (a + 1) / 2;
-  const int ti = p.part + (int)(blockIdx.x / p.T) * p.nparts, tj = blockIdx.x % p.T;
+  // CTA = (pair of output rows, row tile, chunk of column tiles): the row data, the accumulators and the reduction are paid once per chunk
+  const int nchunks = (p.T + p.chunk - 1) / p.chunk;
+  const int ti = p.part + (int)(blockIdx.x / nchunks) * p.nparts, tj0 = (int)(blockIdx.x % nchunks) * p.chunk;
+  const int tj1 = min(tj0 + p.chunk, a == b ? ti + 1 : p.T);        // a == b: tiles above the diagonal are covered by their mirror (weight 2)
   double* out = p.parts + ((long)pidx * gridDim.x + blockIdx.x) * nv;
-  if (a == b && tj > ti) {   // covered by the mirrored tile (weight 2)
+  if (tj0 >= tj1) {
     for (int s = threadIdx.x; s < nv; s += SRTHREADS) out[s] = 0.0;
     return;
   }
@@ -419,18 +423,14 @@ __global__ void __launch_bounds__(SRTHREADS, 3) sobol_sweep_reg_kernel(SobolPair
   __syncthreads();
   for (int e = threadIdx.x; e < ST * M; e += SRTHREADS) {
     const int r = e / M, m = e - r * M;
-    const int gi = ti * ST + r, gj = tj * ST + r;
+    const int gi = ti * ST + r;
     const double x = gi < p.N ? p.X[(long)gi * M + m] : 0.0;
-    const double y = gj < p.N ? p.X[(long)gj * M + m] : 0.0;
     rowd[m * ST + r] = make_double2(gam[m] * x, fma(cu[m] * x, x, lp[m]));
-    cold[m * ST + r] = make_double2(y, cv[m] * y * y);
   }
   for (int r = threadIdx.x; r < ST; r += SRTHREADS) {
-    const int gi = ti * ST + r, gj = tj * ST + r;
+    const int gi = ti * ST + r;
     cr[r] = gi < p.N ? p.c[(long)a * p.N + gi] : 0.0;     // rows/columns beyond N carry zero weight
-    cc[r] = gj < p.N ? p.c[(long)b * p.N + gj] : 0.0;
   }
-  __syncthreads();
 
   constexpr int NP = 2 * RU;   // pairs per thread per pass
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -439,48 +439,63 @@ __global__ void __launch_bounds__(SRTHREADS, 3) sobol_sweep_reg_kernel(SobolPair
 #pragma unroll
   for (int m = 0; m < M; ++m) accF[m] = accP[m] = accS[m] = 0.0;
 #pragma unroll 1
-  for (int pass = 0; pass < (ST / (8 * RU)) * 2; ++pass) {
-    const int r0 = (pass >> 1) * 8 * RU + ty * RU, c0 = (pass & 1) * 32 + tx * 2;
-    double w[NP], run[NP], h[M][NP];
-    {
-      const double2 ccv = *reinterpret_cast<const double2*>(cc + c0);
-#pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const double cru = cr[r0 + u];
-        w[2 * u] = cru * ccv.x;
-        w[2 * u + 1] = cru * ccv.y;
-      }
+  for (int tj = tj0; tj < tj1; ++tj) {
+    if (tj > tj0) __syncthreads();                         // everybody has finished with the previous column tile
+    for (int e = threadIdx.x; e < ST * M; e += SRTHREADS) {
+      const int r = e / M, m = e - r * M;
+      const int gj = tj * ST + r;
+      const double y = gj < p.N ? p.X[(long)gj * M + m] : 0.0;
+      cold[m * ST + r] = make_double2(y, cv[m] * y * y);
     }
-#pragma unroll
-    for (int q = 0; q < NP; ++q) {
-      run[q] = w[q];
-      accS[0] += w[q];
+    for (int r = threadIdx.x; r < ST; r += SRTHREADS) {
+      const int gj = tj * ST + r;
+      cc[r] = gj < p.N ? p.c[(long)b * p.N + gj] * ((a == b && tj != ti) ? 2.0 : 1.0) : 0.0;
     }
+    __syncthreads();
+#pragma unroll 1
+    for (int pass = 0; pass < (ST / (8 * RU)) * 2; ++pass) {
+      const int r0 = (pass >> 1) * 8 * RU + ty * RU, c0 = (pass & 1) * 32 + tx * 2;
+      double w[NP], run[NP], h[M][NP];
+      {
+        const double2 ccv = *reinterpret_cast<const double2*>(cc + c0);
 #pragma unroll
-    for (int m = 0; m < M; ++m) {     // exps, singles and prefixes
-      const double2 d0 = cold[m * ST + c0], d1 = cold[m * ST + c0 + 1];
-#pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const double2 rw = rowd[m * ST + r0 + u];
-        h[m][2 * u] = exp_tab(fma(rw.x, d0.x, rw.y + d0.y), etab);
-        h[m][2 * u + 1] = exp_tab(fma(rw.x, d1.x, rw.y + d1.y), etab);
+        for (int u = 0; u < RU; ++u) {
+          const double cru = cr[r0 + u];
+          w[2 * u] = cru * ccv.x;
+          w[2 * u + 1] = cru * ccv.y;
+        }
       }
 #pragma unroll
       for (int q = 0; q < NP; ++q) {
-        if (m >= 1) accF[m] = fma(w[q], h[m][q], accF[m]);
-        run[q] *= h[m][q];
-        accP[m] += run[q];
+        run[q] = w[q];
+        accS[0] += w[q];
       }
-    }
-    if constexpr (M >= 3) {
 #pragma unroll
-      for (int q = 0; q < NP; ++q) run[q] = w[q] * h[M - 1][q];
+      for (int m = 0; m < M; ++m) {     // exps, singles and prefixes
+        const double2 d0 = cold[m * ST + c0], d1 = cold[m * ST + c0 + 1];
 #pragma unroll
-      for (int m = M - 2; m >= 1; --m) {   // suffixes S[m] = prod_{j >= m} h_j
+        for (int u = 0; u < RU; ++u) {
+          const double2 rw = rowd[m * ST + r0 + u];
+          h[m][2 * u] = exp_tab(fma(rw.x, d0.x, rw.y + d0.y), etab);
+          h[m][2 * u + 1] = exp_tab(fma(rw.x, d1.x, rw.y + d1.y), etab);
+        }
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
+          if (m >= 1) accF[m] = fma(w[q], h[m][q], accF[m]);
           run[q] *= h[m][q];
-          accS[m] += run[q];
+          accP[m] += run[q];
+        }
+      }
+      if constexpr (M >= 3) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) run[q] = w[q] * h[M - 1][q];
+#pragma unroll
+        for (int m = M - 2; m >= 1; --m) {   // suffixes S[m] = prod_{j >= m} h_j
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            run[q] *= h[m][q];
+            accS[m] += run[q];
+          }
         }
       }
     }
@@ -502,7 +517,6 @@ __global__ void __launch_bounds__(SRTHREADS, 3) sobol_sweep_reg_kernel(SobolPair
     }
   }
   __syncthreads();
-  const double wgt = (a == b && ti != tj) ? 2.0 : 1.0;
   for (int s = threadIdx.x; s < nv; s += SRTHREADS) {
     // output index -> wpart slot:  F[m] -> m ; P[k] (s = M+k-1) -> M+k-1 ; S[k] (s = 2M+k-1) -> 2M+k ; E (s = 3M-1) -> 2M
     int slot;
@@ -511,7 +525,7 @@ __global__ void __launch_bounds__(SRTHREADS, 3) sobol_sweep_reg_kernel(SobolPair
     else slot = 2 * M;
     double v = 0.0;
     for (int wdx = 0; wdx < SRTHREADS / 32; ++wdx) v += wpart[wdx * nv + slot];
-    out[s] = v * wgt;
+    out[s] = v;
   }
 }
 
@@ -732,11 +746,24 @@ static int launch_sweep(const SobolPairArgs& a, int npairs, cudaStream_t st) {
   return 0;
 }
 
+// Column tiles per CTA of the register form: long enough to amortise the row staging and the reduction, short enough to leave a few
+// waves of CTAs per SM (RC_SOBOL_CHUNK overrides).
+static int sweep_chunk(int T, int own_rows, int npairs) {
+  static const int forced = [] { const char* e = getenv("RC_SOBOL_CHUNK"); return e ? atoi(e) : 0; }();
+  if (forced > 0) return forced < T ? forced : T;
+  const long slots = 3L * device_sm_count();
+  int chunk = 8;
+  while (chunk > 1 && (long)own_rows * ((T + chunk - 1) / chunk) * npairs < 6 * slots) chunk /= 2;
+  return chunk < T ? chunk : T;
+}
+
 template <int M, int RU>
-static int launch_sweep_reg(const SobolPairArgs& a, int npairs, cudaStream_t st) {
+static int launch_sweep_reg(SobolPairArgs& a, int npairs, cudaStream_t st) {
   const size_t smem = (size_t)(4 * ((M + 1) & ~1) + 4 * M * ST + 2 * ST + (SRTHREADS / 32) * 3 * M) * sizeof(double);
   static_assert((4 * 14 + 4 * 12 * ST + 2 * ST + 4 * 36) * sizeof(double) <= 48 * 1024, "fits the default dynamic shared memory limit");
-  sobol_sweep_reg_kernel<M, RU><<<dim3(a.T * ((a.T - a.part + a.nparts - 1) / a.nparts), npairs), SRTHREADS, smem, st>>>(a);
+  const int own_rows = (a.T - a.part + a.nparts - 1) / a.nparts;
+  a.chunk = sweep_chunk(a.T, own_rows, npairs);
+  sobol_sweep_reg_kernel<M, RU><<<dim3(own_rows * ((a.T + a.chunk - 1) / a.chunk), npairs), SRTHREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
   return 0;
 }
@@ -893,6 +920,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
       // RC_SOBOL_SWEEP=park selects the round-1 form (h parked in shared memory, polynomial exp) for every M; default: registers + table exp up to M = 12
       static const bool reg_form = [] { const char* e = getenv("RC_SOBOL_SWEEP"); return !e || e[0] != 'p'; }();
       int rc;
+      long partials = (long)T * own_rows;        // per pair of output rows
       if (reg_form && M <= 12) {
         switch (M) {
           case 1: rc = launch_sweep_reg<1, 2>(a, npairs, st); break;
@@ -908,6 +936,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
           case 11: rc = launch_sweep_reg<11, 1>(a, npairs, st); break;
           default: rc = launch_sweep_reg<12, 1>(a, npairs, st); break;
         }
+        partials = (long)own_rows * ((T + a.chunk - 1) / a.chunk);
       } else
         rc = M <= 4 ? launch_sweep<4, 2>(a, npairs, st) : M <= 8 ? launch_sweep<8, 2>(a, npairs, st)
              : M <= 12 ? launch_sweep<12, 2>(a, npairs, st) : launch_sweep<20, 1>(a, npairs, st);
@@ -921,7 +950,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
           map.idx[j - i] = sidx[j];
           ++j;
         }
-        sobol_finish_map_kernel<<<dim3((unsigned)(j - i), L * L), 256, 0, st>>>(parts, P, Lp, L, (long)T * own_rows, 3 * M, map,
+        sobol_finish_map_kernel<<<dim3((unsigned)(j - i), L * L), 256, 0, st>>>(parts, P, Lp, L, partials, 3 * M, map,
                                                                                 V + (long)structured[i] * L * L, nullptr);
         RC_LAUNCH_OK();
         i = j;
