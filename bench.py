@@ -408,17 +408,19 @@ def run_b200(args):
     exps_reference = len(masks) * N * N * L * L            # what the reference's formulation evaluates: one exp per (pair, slice), no symmetry
     sobol = {'metric': 'sobol_sweeps_per_s', 'value': 1e3 / sobol_ms, 'unit': 'sweeps/s', 'ms_per_sweep': sobol_ms, 'slices': len(masks),
              'scaling': 'strong (row tiles of the sample-pair space sharded over ranks, one NCCL all-reduce of the partial V)' if world > 1 else 'single GPU',
-             'roofline': {'bound': 'fp64 exp/ALU', 'achieved': exps / world / (sobol_ms * 1e-3) * 1e-9, 'peak': peaks['exp_gexps'], 'unit': 'Gexp/s',
-                          'frac': exps / world / (sobol_ms * 1e-3) * 1e-9 / peaks['exp_gexps'], 'exps_per_sweep': exps,
+             'roofline': {'bound': 'fp64 exp/ALU', 'achieved': exps / world / (sobol_ms * 1e-3) * 1e-9, 'peak': peaks['exp_tab_gexps'], 'unit': 'Gexp/s',
+                          'frac': exps / world / (sobol_ms * 1e-3) * 1e-9 / peaks['exp_tab_gexps'], 'exps_per_sweep': exps,
                           'reference_exps_per_sweep': exps_reference,
-                          'fp64_instructions_per_exp': 21.25,
-                          'fp64_pipe_frac': exps / world / (sobol_ms * 1e-3) * 21.25 / (peaks['dmma_tflops'] * 0.5e12),
+                          'peak_polynomial_exp': peaks['exp_gexps'],
+                          'fp64_instructions_per_exp': 15.5,
+                          'fp64_pipe_frac': exps / world / (sobol_ms * 1e-3) * 15.5 / (peaks['dmma_tflops'] * 0.5e12),
                           'note': 'achieved = M exps per (sample pair, pair of output rows) actually required by the factorised integrand / sweep time '
-                                  '(per GPU: divided by the number of ranks, which split the pair space); peak = register-resident loop of the kernels\' own '
-                                  'branch-free exp (14 FP64 instructions; libm\'s exp, ~30 instructions, measures 845 Gexp/s) timed live. Besides its exp the '
-                                  'kernel issues ~7 FP64 instructions per exp (argument, weights, prefix/suffix products, sums): 21.25 in all by SASS count at '
-                                  'M = 8, so fp64_pipe_frac = exps x 21.25 / time against the FP64 FMA issue rate (measured DMMA TFLOP/s / 2 per lane-op) '
-                                  'is the share of the FP64 pipe the sweep keeps busy'}}
+                                  '(per GPU: divided by the number of ranks, which split the pair space); peak = register-resident loop of the exp the sweep '
+                                  'kernel runs (table form: 9 FP64 instructions + one shared-memory lookup; peak_polynomial_exp = the same loop over the 14-instruction '
+                                  'polynomial form of round 1; libm\'s exp, ~30 instructions, measures 845 Gexp/s), timed live. Besides its exp the kernel issues 6.5 '
+                                  'FP64 instructions per exp (argument, weights, prefix/suffix products, sums): 15.5 in all by SASS count at M = 8 (21.25 in round 1), '
+                                  'so fp64_pipe_frac = exps x 15.5 / time against the FP64 FMA issue rate (measured DMMA TFLOP/s / 2 per lane-op) is the share of '
+                                  'the FP64 pipe the sweep keeps busy'}}
 
     # ---- Sobol sweep WITH errors (ClosedSobolWithError, gsa/calibrators.py:146-402; on by default in the reference's scripts): V, W for the same
     #      25 slices; needs the Cholesky factor of the noisy gram (factorised once, outside the timed loop, as the calibrator holds it).

@@ -208,6 +208,20 @@ int rc_sobol_error_mixed(const double* X, int N, int M, const double* Lam, const
                          const unsigned long long* masks_host, int nslices, void* work, size_t work_bytes, double* V, double* W, double* WMm,
                          rc_stream_t stream);
 
+/* ---- fold data on the device ------------------------------------------------------------------------------------------------
+ * rc_column_stats: the statistics Normalization.__init__ stores in normalization.csv (romcomma/data/storage.py:544-558) for data (N, C)
+ * row-major: stats (5, C) rows = mean, std (ddof = 1, as pandas), rng = 2 sqrt(3) std, min = mean - sqrt(3) std, max = mean + sqrt(3) std.
+ * rc_normalize: Normalization.apply_to (direction = +1, :469-485: the first M columns -> norm.ppf(clip((x - min) / rng, margin, 1 - margin)),
+ * the others -> (y - mean) / std) and undo_from (direction = -1, :487-503), with stats in the layout above (the caller may pass the statistics
+ * of OTHER data, as Fold.from_dfs does with the fold's training rows, :430-435).  In place (out == data) is allowed.
+ * rc_test_metrics: the columns GPR.test adds to test.csv and its test_summary.csv row (romcomma/gpr/models.py:235-272) from truth, predictive
+ * mean and sd, each (n, L): reals (n, 2L) = [ Abs Error | Z Score ], flags (n, L + 2) = outlier per output, any, all (0/1),
+ * summary (3L + 2) = RMSE (L), mean SD (L), outlier fractions (L + 2). */
+int rc_column_stats(const double* data, int N, int C, double* stats, rc_stream_t stream);
+int rc_normalize(const double* data, long N, int M, int C, const double* stats, double margin, int direction, double* out, rc_stream_t stream);
+int rc_test_metrics(const double* truth, const double* mean, const double* sd, int n, int L, double* reals, double* flags, double* summary,
+                    rc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,10 @@ _SIGNATURES = {
     'rc_measure_exp_tab_gexps': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
     'rc_debug_exp': (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p]),
     'rc_debug_tile_order': (ctypes.c_int, [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    'rc_column_stats': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_void_p]),
+    'rc_normalize': (ctypes.c_int, [c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_double, ctypes.c_int, c_double_p,
+                                    ctypes.c_void_p]),
+    'rc_test_metrics': (ctypes.c_int, [c_double_p] * 3 + [ctypes.c_int, ctypes.c_int] + [c_double_p] * 3 + [ctypes.c_void_p]),
     'rc_profile_begin': (ctypes.c_int, []),
     'rc_profile_end': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'rc_gram': (ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p, c_double_p,
@@ -431,6 +435,34 @@ def predict_gradient(X, xs, ls, variance, KinvY, fac: Factorization):
     check(lib().rc_predict_gradient_finish(ptr(C), c_pad, c_pad * c_pad, ptr(xs), o, M, ptr(ls), ptr(variance), L, ptr(var), stream_ptr()),
           'rc_predict_gradient_finish')
     return mean, var
+
+
+def column_stats(data: torch.Tensor) -> torch.Tensor:
+    """(5, C) rows mean, std (ddof = 1), rng, min, max of data (N, C): the rows of a fold's normalization.csv (data/storage.py:544-558)."""
+    N, Cc = data.shape
+    stats = torch.empty((5, Cc), dtype=torch.float64, device=data.device)
+    check(lib().rc_column_stats(ptr(data.contiguous()), N, Cc, ptr(stats), stream_ptr()), 'rc_column_stats')
+    return stats
+
+
+def normalize(data: torch.Tensor, M: int, stats: torch.Tensor, margin: float = 1.0E-12, undo: bool = False) -> torch.Tensor:
+    """Normalization.apply_to (or undo_from) of data (N, M + L) on the device with statistics in the column_stats layout (data/storage.py:469-503)."""
+    data = data.contiguous()
+    N, Cc = data.shape
+    out = torch.empty_like(data)
+    check(lib().rc_normalize(ptr(data), N, M, Cc, ptr(stats.contiguous()), margin, -1 if undo else 1, ptr(out), stream_ptr()), 'rc_normalize')
+    return out
+
+
+def test_metrics(truth: torch.Tensor, mean: torch.Tensor, sd: torch.Tensor):
+    """GPR.test's numbers (gpr/models.py:235-272): -> reals (n, 2L) [Abs Error | Z Score], flags (n, L + 2), summary (3L + 2), all on the device."""
+    n, L = truth.shape
+    reals = torch.empty((n, 2 * L), dtype=torch.float64, device=truth.device)
+    flags = torch.empty((n, L + 2), dtype=torch.float64, device=truth.device)
+    summary = torch.empty(3 * L + 2, dtype=torch.float64, device=truth.device)
+    check(lib().rc_test_metrics(ptr(truth.contiguous()), ptr(mean.contiguous()), ptr(sd.contiguous()), n, L, ptr(reals), ptr(flags), ptr(summary),
+                                stream_ptr()), 'rc_test_metrics')
+    return reals, flags, summary
 
 
 def sobol_prepare(X, Lam, F, KinvY, is_F_diagonal: bool):

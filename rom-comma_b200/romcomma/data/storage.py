@@ -331,6 +331,34 @@ class Normalization:
         values[:, M:] = centre + spread * values[:, M:]
         return pd.DataFrame(values, index=df.index, columns=df.columns)
 
+    # ---- the same maps on the device (rc_column_stats / rc_normalize): samples that are already in HBM - synthetic designs, predictions on their
+    #      way back to physical units - are normalised where they are.  Device only: these raise without the CUDA library.
+    def stats_tensor(self):
+        """ The (5, M + L) statistics of this Normalization (rows mean, std, rng, min, max) as a device tensor."""
+        from romcomma._tensors import as_device
+        df = self.frame.df
+        return as_device(np.stack([df.loc[row].to_numpy(dtype=float) for row in ('mean', 'std', 'rng', 'min', 'max')]))
+
+    @staticmethod
+    def stats_of_tensor(data):
+        """ The statistics ``__init__`` computes from ``data`` (N, M + L), on the device (reference data/storage.py:544-558)."""
+        from romcomma import _capi
+        return _capi.column_stats(data)
+
+    def apply_to_tensor(self, data, stats=None):
+        """ ``apply_to`` for a device tensor (N, M + L); ``stats`` defaults to this Normalization's (reference data/storage.py:469-485)."""
+        from romcomma import _capi
+        if not self._is_applicable:
+            return data
+        return _capi.normalize(data, self._fold.M, self.stats_tensor() if stats is None else stats, self.UNIFORM_MARGIN)
+
+    def undo_from_tensor(self, data, stats=None):
+        """ ``undo_from`` for a device tensor (N, M + L) (reference data/storage.py:487-503)."""
+        from romcomma import _capi
+        if not self._is_applicable:
+            return data
+        return _capi.normalize(data, self._fold.M, self.stats_tensor() if stats is None else stats, self.UNIFORM_MARGIN, undo=True)
+
     def unscale_Y(self, dfY: pd.DataFrame) -> pd.DataFrame:
         """ Standard deviations of normalised outputs in the units of the raw outputs (a scale, so no shift)."""
         if not self._is_applicable:

@@ -154,6 +154,11 @@ class GPR(Model):
     def predict(self, x: NP.Matrix, y_instead_of_f: bool = True) -> Tuple[NP.Matrix, NP.Matrix]:
         """ The distribution of y (or f) at the (o,M) inputs x as (mean (o,L), std (o,L))."""
 
+    def _predict_device(self, x: NP.Matrix, y_instead_of_f: bool = True):
+        """ ``predict`` as device tensors (mean (o,L), std (o,L)); implementations that predict on the device override this to skip the round trip."""
+        mean, std = self.predict(x, y_instead_of_f)
+        return as_device(mean), as_device(std)
+
     def predict_df(self, x: NP.Matrix, y_instead_of_f: bool = True, is_normalized: bool = True) -> pd.DataFrame:
         """ Predictions as a DataFrame with M+L+L columns (X, Mean, SD)."""
         Y_heading = self._fold.meta['data']['Y_heading']
@@ -178,22 +183,20 @@ class GPR(Model):
         data = self._fold.test_data.df
         Y_heading = self._fold.meta['data']['Y_heading']
         outputs = list(data[Y_heading].columns)
-        truth = data[Y_heading].to_numpy(dtype=float)
-        mean, std = self.predict(self._fold.test_x.values)
-        error = truth - mean
-        z_score = error / std
-        is_outlier = z_score ** 2 > 4.0
+        L = len(outputs)
+        # prediction, errors, z scores, outlier flags and the summary row stay on the device (rc_test_metrics); ONE copy brings the table back
+        mean_d, std_d = self._predict_device(self._fold.test_x.values)
+        reals_d, flags_d, summary_d = _capi.test_metrics(as_device(data[Y_heading].to_numpy(dtype=float)), mean_d, std_d)
+        table = torch.cat([mean_d, std_d, reals_d, flags_d], dim=1).cpu().numpy()
+        summary_row = summary_d.cpu().numpy()                                  # RMSE (L) | mean SD (L) | outlier fractions (L + 2)
 
         def columns(label, names=outputs):
             return pd.MultiIndex.from_tuples([(label, name) for name in names])
 
-        reals = pd.DataFrame(np.concatenate([mean, std, np.abs(error), z_score], axis=1), index=data.index,
-                             columns=columns('Mean').append([columns('SD'), columns('Abs Error'), columns('Z Score')]))
-        flags = pd.DataFrame(np.concatenate([is_outlier, is_outlier.any(axis=1, keepdims=True), is_outlier.all(axis=1, keepdims=True)], axis=1),
-                             index=data.index, columns=columns('Outlier').append(columns('Outlier', ['Any Output', 'All Outputs'])))
+        reals = pd.DataFrame(table[:, :4 * L], index=data.index, columns=columns('Mean').append([columns('SD'), columns('Abs Error'), columns('Z Score')]))
+        flags = pd.DataFrame(table[:, 4 * L:] != 0.0, index=data.index, columns=columns('Outlier').append(columns('Outlier', ['Any Output', 'All Outputs'])))
         result = Frame(self.test_csv, pd.concat([data, reals, flags], axis=1))
-        summary = pd.DataFrame([np.concatenate([np.sqrt(np.mean(error ** 2, axis=0)), std.mean(axis=0), flags.to_numpy(dtype=float).mean(axis=0)])],
-                               columns=columns('RMSE').append([columns('SD'), flags.columns]))
+        summary = pd.DataFrame([summary_row], columns=columns('RMSE').append([columns('SD'), flags.columns]))
         Frame(self.test_summary_csv, summary)
         return result
 
@@ -290,14 +293,17 @@ class MOGP(GPR):
         self._fac_cache = (key, fac)
         return fac, L, batch
 
-    def predict(self, X: NP.Matrix, y_instead_of_f: bool = True) -> Tuple[NP.Matrix, NP.Matrix]:
+    def _predict_device(self, X: NP.Matrix, y_instead_of_f: bool = True):
+        """ ``predict`` without the copy to the host: (mean (o,L), std (o,L)) as device tensors."""
         ls, F, E, L, batch = self._hyper()
         mean, var = gf.predict_core(as_device(self._X), as_device(self._Y), ls, F, E, as_device(np.asarray(X, dtype=FLOAT())), L, batch, y_instead_of_f,
-                                    fac=self._factorize()[0])
-        mean, var = mean.cpu().numpy(), var.cpu().numpy()                       # (batch, o, L_problem)
-        mean = np.concatenate(list(mean), axis=1)
-        var = np.concatenate(list(var), axis=1)
-        return np.atleast_2d(mean), np.atleast_2d(np.sqrt(var))
+                                    fac=self._factorize()[0])                   # (batch, o, L_problem)
+        o = mean.shape[1]
+        return mean.permute(1, 0, 2).reshape(o, -1).contiguous(), torch.sqrt(var).permute(1, 0, 2).reshape(o, -1).contiguous()
+
+    def predict(self, X: NP.Matrix, y_instead_of_f: bool = True) -> Tuple[NP.Matrix, NP.Matrix]:
+        mean, std = self._predict_device(X, y_instead_of_f)
+        return np.atleast_2d(mean.cpu().numpy()), np.atleast_2d(std.cpu().numpy())
 
     def predict_gradient(self, x: NP.Matrix, y_instead_of_f: bool = True):
         """ The gradient GP dy/dx at the (o,M) inputs x (reference gpr/models.py:386-415): mean (o,L,M) and cov (O,o,L,M,m).

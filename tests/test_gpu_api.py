@@ -125,6 +125,24 @@ def test_user_run_gpr_and_gsa_layout_and_values(small_repo):
         rm, rv = gp.predict_rbf(X, Y[:, l], ls[l], var[l], noise[l], xs)
         assert_close(mean[:, l], rm, what='variant mean')
         assert_close(std[:, l], np.sqrt(rv), what='variant std (quirk Q6: predict returns the standard deviation)')
+    # GPR.test (device metrics, rc_test_metrics): test.csv and test_summary.csv against the oracle's restatement of gpr/models.py:235-272
+    from oracle import normalization
+    tx, ty = fold.test_x.values, fold.test_y.values
+    tm = np.stack([gp.predict_rbf(X, Y[:, l], ls[l], var[l], noise[l], tx)[0] for l in range(2)], axis=1)
+    ts = np.sqrt(np.stack([gp.predict_rbf(X, Y[:, l], ls[l], var[l], noise[l], tx)[1] for l in range(2)], axis=1))
+    r_ref, f_ref, s_ref = normalization.test_metrics(ty, tm, ts)
+    tcsv = pd.read_csv(fold.folder / 'gpr.v.a' / 'test.csv', header=[0, 1], index_col=0)
+    assert_close(tcsv['Mean'].values, tm, what='test.csv Mean')
+    assert_close(tcsv['Abs Error'].values, r_ref[:, :2], what='test.csv Abs Error')
+    assert_close(tcsv['Z Score'].values, r_ref[:, 2:], what='test.csv Z Score')
+    assert np.array_equal(tcsv['Outlier'].values.astype(float), f_ref), 'test.csv Outlier flags'
+    scsv = pd.read_csv(fold.folder / 'gpr.v.a' / 'test_summary.csv', header=[0, 1], index_col=0)
+    assert_close(scsv.values.reshape(-1), s_ref, what='test_summary.csv (RMSE, SD, outlier fractions)')
+    # the fold's normalisation on the device reproduces the normalised data the fold holds (host pandas path, data/storage.py:469-485)
+    raw_rows = repo.data.df.loc[fold.data.df.index].to_numpy(dtype=float)
+    stats = fold.normalization.stats_of_tensor(torch.tensor(raw_rows).cuda())
+    normed = fold.normalization.apply_to_tensor(torch.tensor(raw_rows).cuda(), stats).cpu().numpy()
+    assert_close(normed, fold.data.df.to_numpy(dtype=float), what='apply_to_tensor vs the fold csv')
     assert_close(gpv.K_cho.numpy(), gp.k_cho_rbf(X, ls, var, noise), what='K_cho (L,N,N)')
     KiY = gpv.K_inv_Y.numpy()
     assert KiY.shape == (2, 1, X.shape[0])
@@ -402,3 +420,59 @@ def test_predict_gradient_and_full_covariance_against_oracle(small_repo):
     Av = np.linalg.solve(np.linalg.cholesky(Kv), gp.gram_rbf(X, xs0, ls[0], var[0]))
     assert tuple(vc.shape) == (1, 6, 6)
     assert_close(vc.numpy()[0], gp.gram_rbf(xs0, xs0, ls[0], var[0]) - Av.T @ Av, what='variant full covariance')
+
+
+# ---- fold data on the device: normalisation and GPR.test's numbers ---------------------------------------------------------
+@pytest.mark.parametrize('name', ['ref_cov_a', 'ref_var_a', 'ref_cov_b', 'ref_var_b'])
+def test_device_normalisation_reproduces_the_reference_run(name):
+    """rc_column_stats + rc_normalize on the raw rows of the fold the reference fitted: the X and Y the reference's own Normalization produced
+    (tests/golden/ref_*.npz), the oracle's statistics, and undo_from back to the raw rows where the clip did not bite."""
+    from conftest import GOLDEN
+    from oracle import normalization
+    from romcomma import _capi as C
+    g = np.load(GOLDEN / f'{name}.npz')
+    raw, M = g['raw'], g['X'].shape[1]
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('tests_golden_scenario_for_normalisation', GOLDEN / 'scenario.py')
+    scenario = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(scenario)
+    K = scenario.CASES[name]['K']
+    rows = raw[g[f'fold.{K if K > 0 else 0}.train_index']]                     # the fold the scenario fits: the improper one when there is one
+    assert rows.shape[0] == g['X'].shape[0]
+    d = C.dev(rows)
+    st = C.column_stats(d)
+    assert_close(st.cpu().numpy(), normalization.stats(rows), rtol=1e-12, atol=1e-14, what='mean, std, rng, min, max')
+    out = C.normalize(d, M, st)
+    assert_close(out.cpu().numpy()[:, :M], g['X'], what='normalised X vs the reference run')
+    assert_close(out.cpu().numpy()[:, M:], g['Y'], what='normalised Y vs the reference run')
+    back = C.normalize(out, M, st, undo=True).cpu().numpy()
+    ref_back = normalization.undo_from(normalization.apply_to(rows, M, normalization.stats(rows)), M, normalization.stats(rows))
+    assert_close(back, ref_back, what='undo_from')
+
+
+def test_device_normalisation_clips_and_handles_large_folds():
+    """20000 x 13 samples with outliers beyond [min, max]: the clip at UNIFORM_MARGIN (probit = -+7.03), against the oracle."""
+    from oracle import normalization
+    from romcomma import _capi as C
+    rng = np.random.default_rng(11)
+    data = rng.normal(size=(20000, 13)) * rng.uniform(0.1, 50.0, 13) + rng.uniform(-5, 5, 13)
+    data[::97, :5] *= 40.0
+    st = normalization.stats(data)
+    out = C.normalize(C.dev(data), 10, C.column_stats(C.dev(data))).cpu().numpy()
+    ref = normalization.apply_to(data, 10, st)
+    assert np.abs(ref[:, :10]).max() > 7.0, 'the clip is exercised'
+    assert_close(out, ref, what='apply_to')
+
+
+@pytest.mark.parametrize('n,L', [(1, 1), (205, 1), (300, 3), (2048, 4)])
+def test_device_test_metrics(n, L):
+    from oracle import normalization
+    from romcomma import _capi as C
+    rng = np.random.default_rng(n + L)
+    truth, mean = rng.normal(size=(n, L)), rng.normal(size=(n, L)) * 0.3
+    sd = rng.uniform(0.2, 1.5, (n, L))
+    reals, flags, summary = (t.cpu().numpy() for t in C.test_metrics(C.dev(truth), C.dev(mean), C.dev(sd)))
+    r_ref, f_ref, s_ref = normalization.test_metrics(truth, mean, sd)
+    assert_close(reals, r_ref, rtol=1e-13, atol=0, what='abs error, z score')
+    assert np.array_equal(flags, f_ref), 'outlier flags'
+    assert_close(summary, s_ref, rtol=1e-12, atol=1e-15, what='RMSE, mean SD, outlier fractions')
