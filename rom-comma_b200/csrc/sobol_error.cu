@@ -18,6 +18,7 @@
 #include "sobol.h"
 #include "chol.h"
 #include "common.cuh"
+#include <cstdlib>
 #include <algorithm>
 #include <vector>
 
@@ -353,6 +354,134 @@ static int launch_error_sweep(const ErrMatvecArgs& a, cudaStream_t st) {
   return 0;
 }
 
+// Register form of the sweep mat-vec (round 2; same changes as sobol.cu: sobol_sweep_reg_kernel): the k_m of a step stay in registers, one
+// instantiation per M, row operands { x, cA x^2 + cK } and column operands { cC y, cB y^2 } interleaved for 16-byte loads, 128 threads and
+// three CTAs per SM.  A CTA owns 16 columns and walks ALL rows in stages of SWR_ROWS (accumulators persist), so there is ONE partial per
+// (job, column) instead of one per 512-row chunk: the gather kernel reads 1/8 of the bytes.  Thread (ty, tx): column tx, RQ rows per step.
+constexpr int SWR_THREADS = 128;
+constexpr int SWR_ROWS = 128;    // rows per stage
+
+template <int M, int RQ>
+__global__ void __launch_bounds__(SWR_THREADS, 3) sobol_error_sweep_reg_kernel(ErrMatvecArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int nv = 3 * M, MP = (M + 1) & ~1;
+  double* cA = sm;                                          // [M]
+  double* cB = cA + MP;
+  double* cC = cB + MP;
+  double* cK = cC + MP;
+  double2* rowd = reinterpret_cast<double2*>(cK + MP);      // [M][SWR_ROWS]  { x, cA_m x^2 + cK_m }
+  double2* cold = rowd + M * SWR_ROWS;                      // [M][16]        { cC_m y, cB_m y^2 }
+  double* wl = reinterpret_cast<double*>(cold + M * SW_EC); // [SWR_ROWS]     left weights
+  double* red = wl + SWR_ROWS;                              // [8][16]
+  __shared__ double etab[32];
+
+  const int job = blockIdx.y, J = p.J;
+  const int li = job % (p.L * p.L), l = li / p.L;
+  const int tid = threadIdx.x;
+  const int col0 = blockIdx.x * SW_EC;
+  const double* wsrc = (job >= 2 * p.L * p.L ? p.c2 : p.c) + (long)l * p.N;
+  exp_table_fill(etab);
+  for (int m = tid; m < M; m += SWR_THREADS) {
+    cA[m] = p.coef[(0L * J + job) * M + m];
+    cB[m] = p.coef[(1L * J + job) * M + m];
+    cC[m] = p.coef[(2L * J + job) * M + m];
+    cK[m] = p.coef[(3L * J + job) * M + m];
+  }
+  __syncthreads();
+  for (int e = tid; e < SW_EC * M; e += SWR_THREADS) {
+    const int r = e / M, m = e - r * M;
+    const int gj = col0 + r;
+    const double y = gj < p.N ? p.X[(long)gj * M + m] : 0.0;
+    cold[m * SW_EC + r] = make_double2(cC[m] * y, cB[m] * y * y);
+  }
+
+  const int ty = tid >> 4, tx = tid & 15;       // RQ rows per step (ty), one column (tx)
+  // accF[m] = F[m] for m >= 1 (F[0] is P[1]);  accP[k-1] = P[k];  accS[k] = S[k] for 1 <= k <= M-2 (S[M-1] is F[M-1]);  accS[0] = E
+  double accF[M], accP[M], accS[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) accF[m] = accP[m] = accS[m] = 0.0;
+#pragma unroll 1
+  for (int row0 = 0; row0 < p.N; row0 += SWR_ROWS) {
+    if (row0 > 0) __syncthreads();               // everybody has finished with the previous stage
+    for (int e = tid; e < SWR_ROWS * M; e += SWR_THREADS) {
+      const int r = e / M, m = e - r * M;
+      const int gi = row0 + r;
+      const double x = gi < p.N ? p.X[(long)gi * M + m] : 0.0;
+      rowd[m * SWR_ROWS + r] = make_double2(x, fma(cA[m] * x, x, cK[m]));
+    }
+    for (int r = tid; r < SWR_ROWS; r += SWR_THREADS) {
+      const int gi = row0 + r;
+      wl[r] = gi < p.N ? wsrc[gi] : 0.0;         // rows beyond N carry zero weight
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int sub = 0; sub < SWR_ROWS / (8 * RQ); ++sub) {
+      const int r0 = sub * 8 * RQ + RQ * ty;
+      double w[RQ], run[RQ], h[M][RQ];
+#pragma unroll
+      for (int q = 0; q < RQ; ++q) {
+        w[q] = wl[r0 + q];
+        run[q] = w[q];
+        accS[0] += w[q];
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const double2 cd = cold[m * SW_EC + tx];
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+          const double2 rw = rowd[m * SWR_ROWS + r0 + q];
+          h[m][q] = exp_tab(fma(rw.x, cd.x, rw.y + cd.y), etab);
+          if (m >= 1) accF[m] = fma(w[q], h[m][q], accF[m]);
+          run[q] *= h[m][q];
+          accP[m] += run[q];
+        }
+      }
+      if constexpr (M >= 3) {
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) run[q] = w[q] * h[M - 1][q];
+#pragma unroll
+        for (int m = M - 2; m >= 1; --m) {
+#pragma unroll
+          for (int q = 0; q < RQ; ++q) {
+            run[q] *= h[m][q];
+            accS[m] += run[q];
+          }
+        }
+      }
+    }
+  }
+  // column sums over the 8 thread rows, one output value at a time (fixed order).  Output slots: F[m] -> m; P[k] -> M+k-1; S[k] -> 2M+k-1; E -> 3M-1
+  double* outbase = p.parts + ((long)job * nv) * ((long)p.T * SW_EC) + col0;
+  auto reduce_store = [&](double v, int slot) {
+    red[ty * SW_EC + tx] = v;
+    __syncthreads();
+    if (tid < SW_EC) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < SWR_THREADS / 16; ++k) t += red[k * SW_EC + tid];
+      outbase[(long)slot * ((long)p.T * SW_EC) + tid] = t;
+    }
+    __syncthreads();
+  };
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    reduce_store(accP[m], M + m);                                 // P[k], k = m + 1
+    reduce_store(m >= 1 ? accF[m] : accP[0], m);                  // F[0] = P[1]
+    if (m >= 1 && m <= M - 2) reduce_store(accS[m], 2 * M + m - 1);
+    if (m == M - 1 && M >= 2) reduce_store(accF[m], 2 * M + m - 1);   // S[M-1] = F[M-1]
+  }
+  reduce_store(accS[0], 3 * M - 1);
+}
+
+template <int M, int RQ>
+static int launch_error_sweep_reg(const ErrMatvecArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)(4 * ((M + 1) & ~1) + 2 * M * SWR_ROWS + 2 * M * SW_EC + SWR_ROWS + (SWR_THREADS / 16) * SW_EC) * sizeof(double);
+  static_assert((4 * 12 + 2 * 12 * SWR_ROWS + 2 * 12 * SW_EC + SWR_ROWS + 8 * SW_EC) * sizeof(double) <= 48 * 1024, "default dynamic shared memory limit");
+  sobol_error_sweep_reg_kernel<M, RQ><<<dim3(a.T, a.J), SWR_THREADS, smem, st>>>(a);
+  RC_LAUNCH_OK();
+  return 0;
+}
+
 // slice -> (column of the mat-vec output, destination row of V / W); passed by value
 struct ErrMap {
   int col[32];
@@ -568,7 +697,28 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
   if (sweep_form) {
     sw.X = X; sw.N = N; sw.M = M; sw.coef = coef; sw.c = g0KY; sw.c2 = ct; sw.L = L; sw.J = J;
     sw.RCH = SW_RCH; sw.RC = (N + SW_RCH - 1) / SW_RCH; sw.T = (N + SW_EC - 1) / SW_EC; sw.ns = 3 * M; sw.parts = parts;
-    int rc = M <= 4 ? launch_error_sweep<4>(sw, st) : M <= 8 ? launch_error_sweep<8>(sw, st) : launch_error_sweep<12>(sw, st);
+    // RC_SOBOL_SWEEP=park selects the round-1 form (k_m parked in shared memory, one partial per 512-row chunk)
+    static const bool reg_form = [] { const char* e = getenv("RC_SOBOL_SWEEP"); return !e || e[0] != 'p'; }();
+    int rc;
+    if (reg_form) {
+      sw.RC = 1; sw.RCH = SWR_ROWS;
+      switch (M) {
+        case 1: rc = launch_error_sweep_reg<1, 4>(sw, st); break;
+        case 2: rc = launch_error_sweep_reg<2, 4>(sw, st); break;
+        case 3: rc = launch_error_sweep_reg<3, 4>(sw, st); break;
+        case 4: rc = launch_error_sweep_reg<4, 4>(sw, st); break;
+        case 5: rc = launch_error_sweep_reg<5, 4>(sw, st); break;
+        case 6: rc = launch_error_sweep_reg<6, 4>(sw, st); break;
+        case 7: rc = launch_error_sweep_reg<7, 4>(sw, st); break;
+        case 8: rc = launch_error_sweep_reg<8, 4>(sw, st); break;
+        case 9: rc = launch_error_sweep_reg<9, 2>(sw, st); break;
+        case 10: rc = launch_error_sweep_reg<10, 2>(sw, st); break;
+        case 11: rc = launch_error_sweep_reg<11, 2>(sw, st); break;
+        default: rc = launch_error_sweep_reg<12, 2>(sw, st); break;
+      }
+    } else {
+      rc = M <= 4 ? launch_error_sweep<4>(sw, st) : M <= 8 ? launch_error_sweep<8>(sw, st) : launch_error_sweep<12>(sw, st);
+    }
     if (rc) return rc;
   }
   if (mixed) {   // the full model first: psi^FULL_ii for the MIXED dots of every chunk below
