@@ -93,6 +93,14 @@ int rc_trsv(const double* A, int n_pad, long ld, long strideA, int batch, const 
 /* B <- L^-1 B, B is n_pad x nrhs_pad (multiple of 128): `A = Lm^-1 Kmn` of gpflow base_conditional (romcomma/gpf/models.py:97). */
 int rc_trsm_fwd(const double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* B, int nrhs_pad, long ldb,
                 long strideB, rc_stream_t stream);
+/* The same solve for ONE large factor (batch = 1) through inverted diagonal super-blocks of 1024 rows: rc_trsm_sbinv_prepare inverts them once
+ * per factor into sbwork (rc_trsm_sbinv_bufsize(n_pad, nrhs_max) bytes, caller-owned, reusable until the factor changes); rc_trsm_fwd_sbinv
+ * then spends one triangular product and one rank-1024 update per super-block instead of 2 n_pad/128 latency-sized launches (n = 16384:
+ * 512 right-hand sides 9.8 -> 7.7 ms).  nrhs_pad <= the nrhs_max sbwork was sized for.  Results agree with rc_trsm_fwd to rounding. */
+size_t rc_trsm_sbinv_bufsize(int n_pad, int nrhs_max);
+int rc_trsm_sbinv_prepare(const double* A, int n_pad, long ld, const void* work, void* sbwork, rc_stream_t stream);
+int rc_trsm_fwd_sbinv(const double* A, int n_pad, long ld, const void* work, const void* sbwork, int nrhs_max, double* B, int nrhs_pad, long ldb,
+                      rc_stream_t stream);
 /* A (holding L) <- L^-1 in place, Kinv (lower 128-tiles) <- L^-T L^-1.  Kinv doubles as scratch and must hold n_pad*ldk doubles
  * per matrix.  Provides the explicit inverse behind the analytic gradient that replaces tf.GradientTape through
  * CholeskyGrad (romcomma/gpr/models.py:359-361). */

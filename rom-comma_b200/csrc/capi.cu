@@ -212,6 +212,27 @@ int rc_trsm_fwd(const double* A, int n_pad, long ld, long strideA, int batch, co
   return trsm_lower_fwd(A, n_pad, ld, strideA, batch, w.dinv, B, nrhs_pad, ldb, strideB, (cudaStream_t)stream);
 }
 
+size_t rc_trsm_sbinv_bufsize(int n_pad, int nrhs_max) { return align256(trsm_sbinv_workspace_doubles(n_pad, nrhs_max) * sizeof(double)); }
+
+int rc_trsm_sbinv_prepare(const double* A, int n_pad, long ld, const void* work, void* sbwork, rc_stream_t stream) {
+  RC_REQUIRE(A && work && sbwork, -2, "rc_trsm_sbinv_prepare: null pointer");
+  RC_REQUIRE(n_pad > 0 && n_pad % TILE == 0 && ld >= n_pad && ld % 2 == 0, -2, "rc_trsm_sbinv_prepare: n_pad=%d must be a positive multiple of 128, ld=%ld even and >= it", n_pad, ld);
+  PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, 1);
+  return trsm_sbinv_prepare(A, n_pad, ld, w.dinv, static_cast<double*>(sbwork), (cudaStream_t)stream);
+}
+
+int rc_trsm_fwd_sbinv(const double* A, int n_pad, long ld, const void* work, const void* sbwork, int nrhs_max, double* B, int nrhs_pad, long ldb,
+                      rc_stream_t stream) {
+  RC_REQUIRE(A && work && sbwork && B, -2, "rc_trsm_fwd_sbinv: null pointer");
+  RC_REQUIRE(n_pad > 0 && n_pad % TILE == 0 && ld >= n_pad && ld % 2 == 0, -2, "rc_trsm_fwd_sbinv: n_pad=%d must be a positive multiple of 128, ld=%ld even and >= it", n_pad, ld);
+  RC_REQUIRE(nrhs_pad > 0 && nrhs_pad % TILE == 0 && nrhs_pad <= nrhs_max && ldb >= nrhs_pad && ldb % 2 == 0, -2,
+             "rc_trsm_fwd_sbinv: nrhs_pad=%d must be a positive multiple of 128 and <= nrhs_max=%d, ldb=%ld even and >= it", nrhs_pad, nrhs_max, ldb);
+  PotrfWork w = split_potrf_work(const_cast<void*>(work), n_pad, 1);
+  const double* sb = static_cast<const double*>(sbwork);
+  double* Tbuf = const_cast<double*>(sb) + trsm_sbinv_workspace_doubles(n_pad, nrhs_max) - (size_t)1024 * nrhs_max;
+  return trsm_lower_fwd_sbinv(A, n_pad, ld, w.dinv, sb, Tbuf, B, nrhs_pad, ldb, (cudaStream_t)stream);
+}
+
 int rc_potri(double* A, int n_pad, long ld, long strideA, int batch, const void* work, double* Kinv, long ldk, long strideK, rc_stream_t stream) {
   RC_REQUIRE(A && work && Kinv, -2, "rc_potri: null pointer");
   RC_CHECK_FACTOR_ARGS("rc_potri");

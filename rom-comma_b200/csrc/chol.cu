@@ -637,6 +637,59 @@ int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, con
   return 0;
 }
 
+// Few right-hand sides against a large factor (Sobol error columns, predictions: nrhs <= 1024 at n = 16384).  The block substitution above is
+// then 2 n/128 latency-sized launches of at most nrhs/128 (diagonal block) and (n/128 - k) nrhs/128 (rank-128 update) tiles: 10 ms for
+// 1.4e11 flop.  Here the diagonal SUPER-blocks of TRSM_SBI rows are inverted once per factor (trsm_sbinv_prepare: a batched trtri_lower on a
+// copy, 3 levels), so that a super-block costs one triangular product T = Z_sb B_sb (out of place, copied back) and ONE rank-TRSM_SBI update
+// of everything below - n / TRSM_SBI steps with K = 1024 updates instead of n / 128 with K = 128.  Rows beyond the last full super-block take
+// the block substitution.  work: trsm_sbinv_workspace_doubles(n, nrhs_max) doubles = [Z: nsb x SBI x SBI][trtri tmp: nsb x SBI^2/4][T: SBI x nrhs].
+constexpr int TRSM_SBI = 1024;
+size_t trsm_sbinv_workspace_doubles(int n, int nrhs) {
+  const size_t nsb = (size_t)(n / TRSM_SBI);
+  return nsb * TRSM_SBI * TRSM_SBI + nsb * (TRSM_SBI * (size_t)TRSM_SBI / 4) + (size_t)TRSM_SBI * nrhs;
+}
+int trsm_sbinv_prepare(const double* A, int n, long ld, const double* dinv, double* work, cudaStream_t st) {
+  const int nsb = n / TRSM_SBI;
+  if (nsb == 0) return 0;
+  double* Z = work;
+  double* tmp = Z + (size_t)nsb * TRSM_SBI * TRSM_SBI;
+  for (int z = 0; z < nsb; ++z)
+    RC_CUDA_OK(cudaMemcpy2DAsync(Z + (size_t)z * TRSM_SBI * TRSM_SBI, TRSM_SBI * sizeof(double), A + (long)z * TRSM_SBI * (ld + 1), ld * sizeof(double),
+                                 TRSM_SBI * sizeof(double), TRSM_SBI, cudaMemcpyDeviceToDevice, st));
+  return trtri_lower(Z, TRSM_SBI, TRSM_SBI, (long)TRSM_SBI * TRSM_SBI, nsb, dinv, tmp, (long)TRSM_SBI * TRSM_SBI / 4, st, 0, TRSM_SBI / DB, 0);
+}
+int trsm_lower_fwd_sbinv(const double* A, int n, long ld, const double* dinv, const double* work, double* Tbuf, double* B, int nrhs, long ldb,
+                         cudaStream_t st) {
+  RC_REQUIRE(n % DB == 0 && nrhs % DB == 0, -2, "trsm_lower_fwd_sbinv: n=%d and nrhs=%d must be multiples of 128", n, nrhs);
+  const int nsb = n / TRSM_SBI, nblk = n / DB, SBB = TRSM_SBI / DB;
+  const double* Z = work;
+  int rc;
+  for (int z = 0; z < nsb; ++z) {
+    double* Bz = B + (long)z * TRSM_SBI * ldb;
+    GemmArgs g{};   // T = Z_z * B_z   (Z_z lower, stored [m][k]  ->  k < m0 + 128)
+    g.A = Z + (size_t)z * TRSM_SBI * TRSM_SBI; g.lda = TRSM_SBI;
+    g.B = Bz; g.ldb = ldb;
+    g.C = Tbuf; g.ldc = nrhs;
+    g.M = TRSM_SBI; g.N = nrhs; g.K = TRSM_SBI; g.alpha = 1.0; g.beta = 0.0; g.kmode = K_LT_M1;
+    if ((rc = launch_gemm_ws<false, true>(g, 1, st))) return rc;
+    RC_CUDA_OK(cudaMemcpy2DAsync(Bz, ldb * sizeof(double), Tbuf, nrhs * sizeof(double), nrhs * sizeof(double), TRSM_SBI, cudaMemcpyDeviceToDevice, st));
+    const int r0 = (z + 1) * SBB;
+    if (r0 < nblk) {   // B[below] -= L[below, super-block z] * B_z
+      GemmArgs u{};
+      u.A = A + (long)r0 * DB * ld + (long)z * TRSM_SBI; u.lda = ld;
+      u.B = Bz; u.ldb = ldb;
+      u.C = B + (long)r0 * DB * ldb; u.ldc = ldb;
+      u.M = (nblk - r0) * DB; u.N = nrhs; u.K = TRSM_SBI; u.alpha = -1.0; u.beta = 1.0; u.kmode = K_FULL;
+      if ((rc = launch_gemm_ws<false, true>(u, 1, st))) return rc;
+    }
+  }
+  const int k_tail = nsb * SBB;
+  if (k_tail < nblk)   // the ragged rest: block substitution on the trailing (n - k_tail*128) rows, already updated by everything above
+    return trsm_lower_fwd(A + (long)k_tail * DB * (ld + 1), (nblk - k_tail) * DB, ld, 0, 1, dinv + (long)k_tail * DB * DB, B + (long)k_tail * DB * ldb, nrhs,
+                          ldb, 0, st);
+  return 0;
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // Triangular inverse (in place) and K^-1 = L^-T L^-1 (out of place, lower triangle).
 // ----------------------------------------------------------------------------------------------------------------

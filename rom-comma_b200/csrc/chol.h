@@ -23,6 +23,14 @@ int trsv_lower(const double* A, int n, long ld, long strideA, int batch, const d
 int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, const double* dinv, double* B, int nrhs, long ldb, long strideB,
                    cudaStream_t st);
 
+// The same for few right-hand sides against one large factor: the diagonal super-blocks of 1024 rows are inverted once (prepare; work =
+// trsm_sbinv_workspace_doubles(n, nrhs_max) doubles, the last 1024 * nrhs_max of them the product buffer Tbuf), then every super-block is one
+// triangular product and one rank-1024 update.
+size_t trsm_sbinv_workspace_doubles(int n, int nrhs);
+int trsm_sbinv_prepare(const double* A, int n, long ld, const double* dinv, double* work, cudaStream_t st);
+int trsm_lower_fwd_sbinv(const double* A, int n, long ld, const double* dinv, const double* work, double* Tbuf, double* B, int nrhs, long ldb,
+                         cudaStream_t st);
+
 // A (holding L) <- L^-1 in place; tmp needs n*n/4 doubles per matrix.
 // rest_from > 0: the leading rest_from x rest_from block is inverted already (a call with n = rest_from and strideD_blocks = blocks of the whole
 // matrix); strideD_blocks: blocks per matrix in dinv (0 = n / 128); tiles_per_cta > 0: yielding launches.

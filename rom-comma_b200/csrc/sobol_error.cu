@@ -573,8 +573,9 @@ __global__ void sobol_error_W_kernel(const double* __restrict__ R, const double*
 
 namespace {
 struct ErrLayout {
-  size_t coef, pre, parts, B, partial, partial2, R, Rm, ct, psifull, total;
+  size_t coef, pre, parts, B, partial, partial2, R, Rm, ct, psifull, sbinv, total;
   int RCH, RC, T, chunk_slices, ncols, kinds;
+  bool use_sbinv;
   long ldb, strideB;
 };
 inline size_t al(size_t b) { return (b + 255) / 256 * 256; }
@@ -614,6 +615,11 @@ ErrLayout err_layout(int N, int M, int L, int nslices, int n_pad, int chol_batch
     o.ct = off; off += al((size_t)L * N * sizeof(double));
     o.psifull = off; off += al((size_t)L * n_pad * sizeof(double));
   }
+  // one large factor, few columns: triangular solves through inverted diagonal super-blocks (chol.cu: trsm_lower_fwd_sbinv); RC_TRSM_SBINV=0 disables
+  static const bool sbinv_on = [] { const char* e = getenv("RC_TRSM_SBINV"); return !e || atoi(e) != 0; }();
+  o.use_sbinv = sbinv_on && chol_batch == 1 && n_pad >= 4096 && o.ncols <= 1024;
+  o.sbinv = off;
+  if (o.use_sbinv) off += al(trsm_sbinv_workspace_doubles(n_pad, o.ncols) * sizeof(double));
   o.total = off;
   return o;
 }
@@ -643,6 +649,12 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
   double* ct = mixed ? reinterpret_cast<double*>(base + lay.ct) : nullptr;
   double* psifull = mixed ? reinterpret_cast<double*>(base + lay.psifull) : nullptr;
   const int J = lay.kinds * L * L;
+  double* sbwork = lay.use_sbinv ? reinterpret_cast<double*>(base + lay.sbinv) : nullptr;
+  double* sbT = lay.use_sbinv ? sbwork + trsm_sbinv_workspace_doubles(n_pad, lay.ncols) - (size_t)1024 * lay.ncols : nullptr;
+  if (lay.use_sbinv) {
+    int rc0 = trsm_sbinv_prepare(Achol, n_pad, ld, dinv, sbwork, st);
+    if (rc0) return rc0;
+  }
   RC_ENSURE_SMEM(sobol_error_matvec_kernel, 220 * 1024);
   sobol_error_coeff_kernel<<<(J * M + 255) / 256, 256, 0, st>>>(Phi, Lam, F, L, M, lay.kinds, coef, pre);
   RC_LAUNCH_OK();
@@ -672,7 +684,8 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
     sobol_error_gather_kernel<<<dim3(ns, L * L), 256, 0, st>>>(parts, L, N, RC, nv, ncols_u, g0KY, g0, pre, chol_batch, B, lay.ldb, lay.strideB, map,
                                                                keep_full ? nullptr : V, R, keep_full ? nullptr : Rm);
     RC_LAUNCH_OK();
-    int rc = trsm_lower_fwd(Achol, n_pad, ld, strideA, chol_batch, dinv, B, lay.ncols, lay.ldb, lay.strideB, st);
+    int rc = lay.use_sbinv ? trsm_lower_fwd_sbinv(Achol, n_pad, ld, dinv, sbwork, sbT, B, lay.ncols, lay.ldb, st)
+                           : trsm_lower_fwd(Achol, n_pad, ld, strideA, chol_batch, dinv, B, lay.ncols, lay.ldb, lay.strideB, st);
     if (rc) return rc;
     if (keep_full) {
       sobol_error_keep_psifull_kernel<<<dim3((n_pad + 255) / 256, L), 256, 0, st>>>(B, lay.ldb, lay.strideB, L, n_pad, chol_batch, psifull);

@@ -29,6 +29,10 @@ _SIGNATURES = {
     'rc_measure_exp_tab_gexps': (ctypes.c_int, [c_double_p, ctypes.c_void_p]),
     'rc_debug_exp': (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p]),
     'rc_debug_tile_order': (ctypes.c_int, [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    'rc_trsm_sbinv_bufsize': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    'rc_trsm_sbinv_prepare': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'rc_trsm_fwd_sbinv': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.c_int,
+                                         ctypes.c_long, ctypes.c_void_p]),
     'rc_column_stats': (ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_void_p]),
     'rc_normalize': (ctypes.c_int, [c_double_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_double, ctypes.c_int, c_double_p,
                                     ctypes.c_void_p]),
@@ -254,8 +258,19 @@ class Factorization:
                             self.n_pad, int(transpose), stream_ptr()), 'rc_trsv')
         return x
 
+    SBINV_MIN_N, SBINV_MAX_RHS = 4096, 2048
+
     def trsm_fwd_(self, B: torch.Tensor) -> torch.Tensor:
-        """B: (batch, n_pad, c_pad) with c_pad a multiple of 128; overwritten by L^-1 B."""
+        """B: (batch, n_pad, c_pad) with c_pad a multiple of 128; overwritten by L^-1 B.  One large factor and few columns: through the
+        inverted diagonal super-blocks (rc_trsm_fwd_sbinv), which are formed on first use and kept with the factor."""
+        if self.batch == 1 and self.n_pad >= self.SBINV_MIN_N and B.shape[2] <= self.SBINV_MAX_RHS and os.environ.get('RC_TRSM_SBINV', '1') != '0':
+            if getattr(self, '_sbwork', None) is None:
+                self._sbwork = workspace(lib().rc_trsm_sbinv_bufsize(self.n_pad, self.SBINV_MAX_RHS), self.A.device)
+                check(lib().rc_trsm_sbinv_prepare(ptr(self.A), self.n_pad, self.n_pad, raw_ptr(self.work), raw_ptr(self._sbwork), stream_ptr()),
+                      'rc_trsm_sbinv_prepare')
+            check(lib().rc_trsm_fwd_sbinv(ptr(self.A), self.n_pad, self.n_pad, raw_ptr(self.work), raw_ptr(self._sbwork), self.SBINV_MAX_RHS, ptr(B),
+                                          B.shape[2], B.shape[2], stream_ptr()), 'rc_trsm_fwd_sbinv')
+            return B
         check(lib().rc_trsm_fwd(ptr(self.A), self.n_pad, self.n_pad, self.n_pad * self.n_pad, self.batch, raw_ptr(self.work), ptr(B), B.shape[2],
                                 B.shape[2], B.shape[1] * B.shape[2], stream_ptr()), 'rc_trsm_fwd')
         return B
@@ -263,6 +278,7 @@ class Factorization:
     def inverse_(self) -> torch.Tensor:
         """Overwrites the factor by L^-1 and returns K^-1 (lower 128-tiles valid)."""
         Kinv = torch.empty_like(self.A)
+        self._sbwork = None                       # the factor is about to be overwritten: its inverted super-blocks go with it
         check(lib().rc_potri(ptr(self.A), self.n_pad, self.n_pad, self.n_pad * self.n_pad, self.batch, raw_ptr(self.work), ptr(Kinv), self.n_pad,
                              self.n_pad * self.n_pad, stream_ptr()), 'rc_potri')
         return Kinv

@@ -115,6 +115,26 @@ def test_trsm_wide_right_hand_sides(C, n, nrhs, sb, monkeypatch):
     assert float(Bp[0, n:, :].abs().sum()) == 0.0 and float(Bp[0, :, nrhs:].abs().sum()) == 0.0, 'padding must stay zero'
 
 
+@pytest.mark.parametrize('n,nrhs', [(4096, 128), (4480, 384), (5120, 1024)])
+def test_trsm_through_inverted_super_blocks(C, n, nrhs, monkeypatch):
+    """rc_trsm_fwd_sbinv (one large factor, few right-hand sides: diagonal super-blocks of 1024 rows inverted once, then one triangular product
+    and one rank-1024 update per super-block; n = 4480 leaves a ragged rest of three blocks for the block substitution) against the block
+    substitution of rc_trsm_fwd and against L X = B."""
+    rng = np.random.default_rng(n)
+    G = rng.normal(size=(n, 64))
+    A = G @ G.T / 64 + np.diag(rng.uniform(0.5, 2.0, n))
+    fac = C.Factorization(C.dev(A)[None].clone())
+    fac.raise_if_failed()
+    B0 = C.dev(rng.normal(size=(1, n, nrhs)))
+    X = fac.trsm_fwd_(B0.clone())
+    assert getattr(fac, '_sbwork', None) is not None, 'the super-block path ran'
+    monkeypatch.setenv('RC_TRSM_SBINV', '0')
+    Xref = fac.trsm_fwd_(B0.clone())
+    assert_close(X.cpu().numpy(), Xref.cpu().numpy(), rtol=1e-9, atol=1e-11, what='super-block inverses vs block substitution')
+    Lm = C.extract_lower(fac.A, n)[0]
+    assert_close((Lm @ X[0]).cpu().numpy(), B0[0].cpu().numpy(), rtol=1e-9, atol=1e-10, what='L X = B')
+
+
 def test_potrf_batched(C):
     rng = np.random.default_rng(0)
     Ks = []
