@@ -642,7 +642,10 @@ int trsm_lower_fwd(const double* A, int n, long ld, long strideA, int batch, con
 // 1.4e11 flop.  Here the diagonal SUPER-blocks of TRSM_SBI rows are inverted once per factor (trsm_sbinv_prepare: a batched trtri_lower on a
 // copy, 3 levels), so that a super-block costs one triangular product T = Z_sb B_sb (out of place, copied back) and ONE rank-TRSM_SBI update
 // of everything below - n / TRSM_SBI steps with K = 1024 updates instead of n / 128 with K = 128.  Rows beyond the last full super-block take
-// the block substitution.  work: trsm_sbinv_workspace_doubles(n, nrhs_max) doubles = [Z: nsb x SBI x SBI][trtri tmp: nsb x SBI^2/4][T: SBI x nrhs].
+// the block substitution.  (Measured and dropped: a look-ahead as in potrf_lookahead - the triangular products and the next super-block's rows
+// as a chain on the high-priority stream underneath yielding updates, same bits - gained 0.27 ms at 512 columns (7.21 -> 6.95 ms) and lost
+// 0.4 ms at 2048: the 32-tile chain kernels still need their SMs and the yielding updates run 5 % slower.)
+// work: trsm_sbinv_workspace_doubles(n, nrhs_max) doubles = [Z: nsb x SBI x SBI][trtri tmp: nsb x SBI^2/4][T: SBI x nrhs].
 constexpr int TRSM_SBI = 1024;
 size_t trsm_sbinv_workspace_doubles(int n, int nrhs) {
   const size_t nsb = (size_t)(n / TRSM_SBI);

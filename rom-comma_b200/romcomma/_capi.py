@@ -258,7 +258,7 @@ class Factorization:
                             self.n_pad, int(transpose), stream_ptr()), 'rc_trsv')
         return x
 
-    SBINV_MIN_N, SBINV_MAX_RHS = 4096, 2048
+    SBINV_MIN_N, SBINV_MAX_RHS = 4096, int(os.environ.get('RC_TRSM_SBINV_MAX', '4096'))
 
     def trsm_fwd_(self, B: torch.Tensor) -> torch.Tensor:
         """B: (batch, n_pad, c_pad) with c_pad a multiple of 128; overwritten by L^-1 B.  One large factor and few columns: through the

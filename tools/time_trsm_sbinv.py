@@ -25,7 +25,7 @@ def timed(fn, reps=3):
     return a.elapsed_time(b) / reps
 
 g = torch.Generator('cuda').manual_seed(3)
-for nrhs in (128, 512, 1024, 2048):
+for nrhs in [int(v) for v in os.environ.get('NRHS', '128,512,1024,2048').split(',')]:
     B0 = torch.randn(1, n_pad, nrhs, dtype=torch.float64, device='cuda', generator=g)
     B = B0.clone()
     ms_copy = timed(lambda: B.copy_(B0))
