@@ -398,3 +398,50 @@ def test_lockstep_broker_batches_concurrent_optimisers(monkeypatch):
     assert max(batched) >= 2 and len(batched) < n_alone, 'optimisers that run side by side must share launches (how many at a time depends on thread timing)'
     with pytest.raises(_capi.RomcommaB200Error):                         # a failed Cholesky in one problem raises in that thread, the others finish
         lockstep.run_together([lambda: fit(targets[0], starts[0]), lambda: fit(targets[1], starts[1], poison=True)])
+
+
+def test_exp_tab_constants():
+    """The table form of the device exp (csrc/common.cuh: exp_tab, the exp of the Sobol sweep / lattice / error, gram and gradient kernels):
+    (a) the polynomial literals are the coefficients tools/exp_poly.py derives for g(r) = (e^r - 1 - r)/r^2 on |r| <= ln2/64 and
+    1 + r(1 + r g(r)) is within 3e-16 of exp there; (b) the 32 table entries are 2^(j/32) correctly rounded; (c) the scale 32/ln2 and the
+    one-step reduction constant ln2/32 are the doubles nearest to those numbers; (d) a numpy emulation of the whole function (FMAs in long
+    double, which over-states nothing that matters here) stays within 6e-16 of exp on [-40, 2] and within 6e-16 + 3.4e-17 |x| beyond."""
+    import re
+    import subprocess
+    import sys
+    from decimal import Decimal, getcontext
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    src = (root / 'rom-comma_b200' / 'csrc' / 'common.cuh').read_text()
+    body = src[src.index('__device__ __forceinline__ double exp_tab('):]
+    body = body[:body.index('// Programmatic dependent launch')]
+    lead = float(re.search(r'double s = ([0-9.e+-]+);', body).group(1))
+    lits = [float(v) for v in re.findall(r's = fma\(s, r, ([0-9.e+-]+)\);', body)]
+    assert lits[-1] == 1.0 and len(lits) == 4
+    coef_src = ([lead] + lits[:-1])[::-1]                      # c0 .. c3 of g
+    out = subprocess.run([sys.executable, str(root / 'tools' / 'exp_poly.py'), 'table'], capture_output=True, text=True, check=True).stdout
+    nums = [float(v) for v in re.findall(r'-?\d\.\d+e[+-]\d+', out)]
+    assert coef_src == nums[:4], 'common.cuh does not hold the coefficients tools/exp_poly.py derives for the table form'
+    assert nums[4] < 3e-16
+    getcontext().prec = 60
+    tab_src = [float(v) for v in re.findall(r'(\d\.\d{17}e[+-]\d\d),', src[src.index('rc_exp2_table[32] = {'):src.index('};', src.index('rc_exp2_table[32] = {'))])]
+    assert len(tab_src) == 32
+    assert tab_src == [float(Decimal(2) ** (Decimal(j) / Decimal(32))) for j in range(32)]
+    ln2 = Decimal(2).ln()
+    scale = float(re.search(r'fma\(x, ([0-9.e+-]+), magic\)', body).group(1))
+    step = -float(re.search(r'fma\(k, (-[0-9.e+-]+), x\)', body).group(1))
+    assert scale == float(Decimal(32) / ln2) and step == float(ln2 / Decimal(32))
+    ld = np.longdouble
+    x = np.concatenate([np.random.default_rng(3).uniform(-40.0, 2.0, 200000), np.random.default_rng(4).uniform(-700.0, 700.0, 50000)])
+    k = np.rint(x * scale)
+    r = (x.astype(ld) - k.astype(ld) * ld(step)).astype(np.float64)           # one FMA: exact product, one rounding
+    ki = k.astype(np.int64)
+    T = np.array(tab_src)[ki & 31]
+    s = np.full_like(r, lead)
+    for c in lits:
+        s = (s.astype(ld) * r + ld(c)).astype(np.float64)
+    p = (T.astype(ld) + (T * r).astype(ld) * s).astype(np.float64)
+    y = np.ldexp(p, ki >> 5)
+    rel = np.abs(y.astype(ld) / np.exp(x.astype(ld)) - 1).astype(np.float64)
+    assert rel[:200000].max() < 6e-16 + 3.4e-17 * 40
+    assert np.all(rel <= 6e-16 + 3.4e-17 * np.abs(x))
