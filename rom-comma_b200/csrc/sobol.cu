@@ -565,6 +565,50 @@ __device__ __forceinline__ void lattice_walk(double (&acc)[1 << KL], const doubl
   }
 }
 
+// The same sums with the last three inputs flattened (KL >= 4): their seven products q[t] are formed once per sample pair (4 multiplications),
+// the binary tree runs over the first U = KL - 3 inputs only, and every node S of it (product P, the root included) feeds its seven
+// descendants S | t << U with ONE FMA each.  A binary tree spends two instructions on a node that accumulates AND propagates and one on a leaf
+// (1.5 per subset); flattened, KL = 6 costs 4 + 14 + 56 = 74 FP64 instructions per sample pair for the 63 subsets instead of 94.
+template <int KL, int S, int B>
+__device__ __forceinline__ void lattice_flat_children(double (&acc)[1 << KL], const double (&h)[KL], const double (&q)[8], double P);
+template <int KL, int S, int B>
+__device__ __forceinline__ void lattice_flat_node(double (&acc)[1 << KL], const double (&h)[KL], const double (&q)[8], double P) {
+  constexpr int U = KL - 3;
+#pragma unroll
+  for (int t = 1; t < 8; ++t) acc[S | (t << U)] = fma(P, q[t], acc[S | (t << U)]);
+  lattice_flat_children<KL, S, B>(acc, h, q, P);
+}
+template <int KL, int S, int B>
+__device__ __forceinline__ void lattice_flat_children(double (&acc)[1 << KL], const double (&h)[KL], const double (&q)[8], double P) {
+  constexpr int U = KL - 3;
+  if constexpr (B < U) {
+    constexpr int child = S | (1 << B);
+    const double Pc = P * h[B];
+    acc[child] += Pc;
+    lattice_flat_node<KL, child, B + 1>(acc, h, q, Pc);
+    lattice_flat_children<KL, S, B + 1>(acc, h, q, P);
+  }
+}
+template <int KL>
+__device__ __forceinline__ void lattice_accumulate(double (&acc)[1 << KL], const double (&h)[KL], double H) {
+  acc[0] += H;
+  if constexpr (KL >= 4) {
+    constexpr int U = KL - 3;
+    double q[8];
+    q[1] = h[U];
+    q[2] = h[U + 1];
+    q[4] = h[U + 2];
+    q[3] = q[1] * q[2];
+    q[5] = q[1] * q[4];
+    q[6] = q[2] * q[4];
+    q[7] = q[3] * q[4];
+    q[0] = 1.0;
+    lattice_flat_node<KL, 0, 0>(acc, h, q, H);
+  } else {
+    lattice_walk<KL, 0, 0>(acc, h, H);
+  }
+}
+
 template <int KL>
 __global__ void __launch_bounds__(STHREADS, 1) sobol_lattice_kernel(SobolLatticeArgs p) {
   constexpr int NLO = 1 << KL;
@@ -681,8 +725,7 @@ __global__ void __launch_bounds__(STHREADS, 1) sobol_lattice_kernel(SobolLattice
         double h[KL];
 #pragma unroll
         for (int m = 0; m < KL; ++m) h[m] = exp_tab(fma(gxl[m * ST + r], yyl[m * ST + cidx], sul[m * ST + r] + svl[m * ST + cidx]), etab);
-        acc[0] += H;
-        lattice_walk<KL, 0, 0>(acc, h, H);
+        lattice_accumulate<KL>(acc, h, H);
       }
     }
   }

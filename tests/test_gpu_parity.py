@@ -672,3 +672,12 @@ def test_capi_rejects_bad_arguments(C):
     assert lib.rc_potri(C.ptr(A), 250, 256, 256 * 256, 1, C.raw_ptr(work), C.ptr(A), 256, 256 * 256, C.stream_ptr()) == -2
     assert lib.rc_pad_identity(None, 10, 100, C.ptr(A), 256, 256, 256 * 256, 1, C.stream_ptr()) == -2
     assert lib.rc_extract_lower(C.ptr(A), 256, 256 * 256, None, 10, 100, 1, 0, C.stream_ptr()) == -2
+    # round 2: the data kernels, the super-block solve and the exp hook
+    assert lib.rc_column_stats(C.ptr(A), 1, 4, C.ptr(A), C.stream_ptr()) == -2 and b'fewer than two rows' in lib.rc_last_error()
+    assert lib.rc_normalize(C.ptr(A), 10, 5, 4, C.ptr(A), 1e-12, 1, C.ptr(A), C.stream_ptr()) == -2                 # M > columns
+    assert lib.rc_normalize(C.ptr(A), 10, 2, 4, C.ptr(A), 1e-12, 0, C.ptr(A), C.stream_ptr()) == -2 and b'direction' in lib.rc_last_error()
+    assert lib.rc_normalize(C.ptr(A), 10, 2, 4, C.ptr(A), 0.7, 1, C.ptr(A), C.stream_ptr()) == -2 and b'margin' in lib.rc_last_error()
+    assert lib.rc_test_metrics(C.ptr(A), C.ptr(A), None, 10, 2, C.ptr(A), C.ptr(A), C.ptr(A), C.stream_ptr()) == -2
+    assert lib.rc_trsm_sbinv_prepare(C.ptr(A), 200, 256, C.raw_ptr(work), C.raw_ptr(work), C.stream_ptr()) == -2
+    assert lib.rc_trsm_fwd_sbinv(C.ptr(A), 256, 256, C.raw_ptr(work), C.raw_ptr(work), 128, C.ptr(A), 256, 256, C.stream_ptr()) == -2   # nrhs > nrhs_max
+    assert lib.rc_debug_exp(C.ptr(A), C.ptr(A), 16, 2, C.stream_ptr()) == -2
