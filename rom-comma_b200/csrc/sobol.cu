@@ -797,7 +797,7 @@ static int sweep_chunk(int T, int own_rows, int npairs) {
   if (forced > 0) return forced < T ? forced : T;
   const long slots = 3L * device_sm_count();
   int chunk = 8;
-  while (chunk > 1 && (long)own_rows * ((T + chunk - 1) / chunk) * npairs < 6 * slots) chunk /= 2;
+  while (chunk > 1 && (long)own_rows * ((T + chunk - 1) / chunk) * npairs < 5 * slots) chunk /= 2;   // tools/time_sweep_part.py: within 2 % of the best chunk for 1, 2, 4 and 8 ranks
   return chunk < T ? chunk : T;
 }
 
