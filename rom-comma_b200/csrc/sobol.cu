@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs 
 constexpr int SRTHREADS = 128;
 
 template <int M, int RU>
-__global__ void __launch_bounds__(SRTHREADS, 3) sobol_sweep_reg_kernel(SobolPairArgs p) {
+__global__ void __launch_bounds__(SRTHREADS, (M <= 12 ? 3 : 2)) sobol_sweep_reg_kernel(SobolPairArgs p) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double etab[32];
   constexpr int nv = 3 * M, MP = (M + 1) & ~1;             // MP: M rounded up to even (16-byte alignment of what follows)
@@ -804,7 +804,7 @@ static int sweep_chunk(int T, int own_rows, int npairs) {
 template <int M, int RU>
 static int launch_sweep_reg(SobolPairArgs& a, int npairs, cudaStream_t st) {
   const size_t smem = (size_t)(4 * ((M + 1) & ~1) + 4 * M * ST + 2 * ST + (SRTHREADS / 32) * 3 * M) * sizeof(double);
-  static_assert((4 * 14 + 4 * 12 * ST + 2 * ST + 4 * 36) * sizeof(double) <= 48 * 1024, "fits the default dynamic shared memory limit");
+  static_assert((4 * 20 + 4 * 20 * ST + 2 * ST + 4 * 60) * sizeof(double) <= 48 * 1024, "fits the default dynamic shared memory limit");
   const int own_rows = (a.T - a.part + a.nparts - 1) / a.nparts;
   a.chunk = sweep_chunk(a.T, own_rows, npairs);
   sobol_sweep_reg_kernel<M, RU><<<dim3(own_rows * ((a.T + a.chunk - 1) / a.chunk), npairs), SRTHREADS, smem, st>>>(a);
@@ -965,7 +965,7 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
       static const bool reg_form = [] { const char* e = getenv("RC_SOBOL_SWEEP"); return !e || e[0] != 'p'; }();
       int rc;
       long partials = (long)T * own_rows;        // per pair of output rows
-      if (reg_form && M <= 12) {
+      if (reg_form) {                   // M <= 20 here: three CTAs per SM up to M = 12, two (up to 255 registers) beyond
         switch (M) {
           case 1: rc = launch_sweep_reg<1, 2>(a, npairs, st); break;
           case 2: rc = launch_sweep_reg<2, 2>(a, npairs, st); break;
@@ -978,7 +978,15 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
           case 9: rc = launch_sweep_reg<9, 1>(a, npairs, st); break;
           case 10: rc = launch_sweep_reg<10, 1>(a, npairs, st); break;
           case 11: rc = launch_sweep_reg<11, 1>(a, npairs, st); break;
-          default: rc = launch_sweep_reg<12, 1>(a, npairs, st); break;
+          case 12: rc = launch_sweep_reg<12, 1>(a, npairs, st); break;
+          case 13: rc = launch_sweep_reg<13, 1>(a, npairs, st); break;
+          case 14: rc = launch_sweep_reg<14, 1>(a, npairs, st); break;
+          case 15: rc = launch_sweep_reg<15, 1>(a, npairs, st); break;
+          case 16: rc = launch_sweep_reg<16, 1>(a, npairs, st); break;
+          case 17: rc = launch_sweep_reg<17, 1>(a, npairs, st); break;
+          case 18: rc = launch_sweep_reg<18, 1>(a, npairs, st); break;
+          case 19: rc = launch_sweep_reg<19, 1>(a, npairs, st); break;
+          default: rc = launch_sweep_reg<20, 1>(a, npairs, st); break;
         }
         partials = (long)own_rows * ((T + a.chunk - 1) / a.chunk);
       } else
