@@ -362,7 +362,7 @@ constexpr int SWR_THREADS = 128;
 constexpr int SWR_ROWS = 128;    // rows per stage
 
 template <int M, int RQ>
-__global__ void __launch_bounds__(SWR_THREADS, 3) sobol_error_sweep_reg_kernel(ErrMatvecArgs p) {
+__global__ void __launch_bounds__(SWR_THREADS, (M <= 12 ? 3 : 2)) sobol_error_sweep_reg_kernel(ErrMatvecArgs p) {
   extern __shared__ __align__(16) double sm[];
   constexpr int nv = 3 * M, MP = (M + 1) & ~1;
   double* cA = sm;                                          // [M]
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(SWR_THREADS, 3) sobol_error_sweep_reg_kernel(E
 template <int M, int RQ>
 static int launch_error_sweep_reg(const ErrMatvecArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(4 * ((M + 1) & ~1) + 2 * M * SWR_ROWS + 2 * M * SW_EC + SWR_ROWS + (SWR_THREADS / 16) * SW_EC) * sizeof(double);
-  static_assert((4 * 12 + 2 * 12 * SWR_ROWS + 2 * 12 * SW_EC + SWR_ROWS + 8 * SW_EC) * sizeof(double) <= 48 * 1024, "default dynamic shared memory limit");
+  static_assert((4 * 20 + 2 * 20 * SWR_ROWS + 2 * 20 * SW_EC + SWR_ROWS + 8 * SW_EC) * sizeof(double) <= 48 * 1024, "default dynamic shared memory limit");
   sobol_error_sweep_reg_kernel<M, RQ><<<dim3(a.T, a.J), SWR_THREADS, smem, st>>>(a);
   RC_LAUNCH_OK();
   return 0;
@@ -603,7 +603,7 @@ ErrLayout err_layout(int N, int M, int L, int nslices, int n_pad, int chol_batch
   o.pre = off; off += al((size_t)L * sizeof(double));
   {
     const size_t general = (size_t)J * o.RC * o.chunk_slices * o.T * EC;                                        // [J][RC][chunk][T*64]
-    const size_t sweep = M <= 12 ? (size_t)J * ((N + SW_RCH - 1) / SW_RCH) * 3 * M * ((N + SW_EC - 1) / SW_EC) * SW_EC : 0;   // [J][RC'][3M][T'*32]
+    const size_t sweep = M <= 20 ? (size_t)J * ((N + SW_RCH - 1) / SW_RCH) * 3 * M * ((N + SW_EC - 1) / SW_EC) * SW_EC : 0;   // [J][RC'][3M][T'*32]
     o.parts = off; off += al((general > sweep ? general : sweep) * sizeof(double));
   }
   o.B = off; off += al((size_t)chol_batch * o.strideB * sizeof(double));
@@ -668,9 +668,12 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
   const long stride_partial = (long)chunks * lay.ncols;
   const unsigned long long full_mask = (M >= 64) ? ~0ull : ((1ull << M) - 1ull);
   // Structured slices (singles, prefixes, suffixes, full, empty) share ONE sweep-form launch; general subsets take the summed-exponent kernel.
+  // RC_SOBOL_SWEEP=park selects the round-1 form of the sweep kernel (k_m parked in shared memory, one partial per 512-row chunk, M <= 12)
+  static const bool reg_form = [] { const char* e = getenv("RC_SOBOL_SWEEP"); return !e || e[0] != 'p'; }();
+  const int sweep_max_M = reg_form ? 20 : 12;
   std::vector<int> structured, scol, general;
   for (int s = 0; s < nslices; ++s) {
-    const int k = M <= 12 ? sobol_sweep_index(masks[s], M) : -1;
+    const int k = M <= sweep_max_M ? sobol_sweep_index(masks[s], M) : -1;
     if (k >= 0) {
       structured.push_back(s);
       scol.push_back(k);
@@ -705,13 +708,11 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
     a.X = X; a.N = N; a.M = M; a.coef = coef; a.c = g0KY; a.c2 = ct; a.L = L; a.J = J; a.T = lay.T; a.RC = lay.RC; a.RCH = lay.RCH; a.ns = ns; a.parts = parts;
     return a;
   };
-  const bool sweep_form = M <= 12 && (!structured.empty() || mixed);
+  const bool sweep_form = M <= sweep_max_M && (!structured.empty() || mixed);
   ErrMatvecArgs sw{};
   if (sweep_form) {
     sw.X = X; sw.N = N; sw.M = M; sw.coef = coef; sw.c = g0KY; sw.c2 = ct; sw.L = L; sw.J = J;
     sw.RCH = SW_RCH; sw.RC = (N + SW_RCH - 1) / SW_RCH; sw.T = (N + SW_EC - 1) / SW_EC; sw.ns = 3 * M; sw.parts = parts;
-    // RC_SOBOL_SWEEP=park selects the round-1 form (k_m parked in shared memory, one partial per 512-row chunk)
-    static const bool reg_form = [] { const char* e = getenv("RC_SOBOL_SWEEP"); return !e || e[0] != 'p'; }();
     int rc;
     if (reg_form) {
       sw.RC = 1; sw.RCH = SWR_ROWS;
@@ -727,7 +728,15 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
         case 9: rc = launch_error_sweep_reg<9, 2>(sw, st); break;
         case 10: rc = launch_error_sweep_reg<10, 2>(sw, st); break;
         case 11: rc = launch_error_sweep_reg<11, 2>(sw, st); break;
-        default: rc = launch_error_sweep_reg<12, 2>(sw, st); break;
+        case 12: rc = launch_error_sweep_reg<12, 2>(sw, st); break;
+        case 13: rc = launch_error_sweep_reg<13, 2>(sw, st); break;
+        case 14: rc = launch_error_sweep_reg<14, 2>(sw, st); break;
+        case 15: rc = launch_error_sweep_reg<15, 2>(sw, st); break;
+        case 16: rc = launch_error_sweep_reg<16, 2>(sw, st); break;
+        case 17: rc = launch_error_sweep_reg<17, 2>(sw, st); break;
+        case 18: rc = launch_error_sweep_reg<18, 2>(sw, st); break;
+        case 19: rc = launch_error_sweep_reg<19, 2>(sw, st); break;
+        default: rc = launch_error_sweep_reg<20, 2>(sw, st); break;
       }
     } else {
       rc = M <= 4 ? launch_error_sweep<4>(sw, st) : M <= 8 ? launch_error_sweep<8>(sw, st) : launch_error_sweep<12>(sw, st);

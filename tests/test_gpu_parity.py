@@ -379,7 +379,7 @@ def test_full_size_sobol_properties(C, cfg):
 
 
 # ---- Sobol errors (ClosedSobolWithError) -----------------------------------------------------------------------------------
-@pytest.mark.parametrize('N,M,L,covariant', [(50, 3, 2, True), (130, 5, 3, True), (70, 2, 1, False), (200, 20, 2, False), (257, 12, 3, True)])
+@pytest.mark.parametrize('N,M,L,covariant', [(50, 3, 2, True), (130, 5, 3, True), (70, 2, 1, False), (200, 20, 2, False), (257, 12, 3, True), (100, 17, 2, True)])
 def test_sobol_error_matches_oracle(C, N, M, L, covariant):
     """rc_sobol_error (V and W for a list of marginal subsets, incl. non-contiguous and empty ones) against oracle/sobol_error.py."""
     from oracle import sobol_error
