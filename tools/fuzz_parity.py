@@ -22,7 +22,7 @@ while time.time() - t0 < budget:
     N = max(N, 2)                                   # Y is standardised per column
     if L * N > 1500:
         N = 1500 // L
-    M = int(rng.integers(1, 13))
+    M = int(rng.integers(1, 13)) if rng.random() < 0.75 else int(rng.integers(13, 21))       # 13..20: the two-CTA instantiations of the sweep kernels
     full_F = bool(rng.random() < 0.5) and L > 1
     X, Y, ls, F, E = random_problem(N, M, L, seed=int(rng.integers(1 << 30)), full_F=full_F)
     dX, dY = C.dev(X), C.dev(Y)
@@ -92,7 +92,7 @@ while time.time() - t0 < budget:
             assert np.all(np.abs(tot - Vd) <= 1e-10 + 1e-8 * np.abs(Vd) + 16 * np.finfo(float).eps * worst_sum.max()), f'{tag} lattice parts add up'
 
         # round 2: errors with the MIXED rank equation against the oracle (small N only: the oracle is O(L^2 N^2) per subset and call)
-        if N <= 200 and M <= 6:
+        if N <= 200 and (M <= 6 or N <= 100):
             from oracle import sobol_error
             cho = gp.k_cho_mo(X, ls, F, E)
             fac = C.Factorization(C.gram(dX, None, args[0], args[1], args[2], lower_only=True, pad_to=L * N, pad_identity=True))
