@@ -383,8 +383,12 @@ __global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs 
 // (Measured at M = 8: one row per thread, 128 registers and four CTAs per SM instead of two rows, 168 registers and three: 1.49 -> 1.67 ms.)
 constexpr int SRTHREADS = 128;
 
+// CTAs per SM the register allocation aims for: three (168 registers) up to M = 12, two (255) beyond - and at M = 8, where the looser allocation
+// schedules better than the third CTA helps (1.48 -> 1.42 ms at cfg3; at M = 6, 7, 9, 10, 12 the same choice costs 3-9 %, tools/time_sweep_M.py).
+constexpr int sweep_reg_min_blocks(int M) { return (M == 8 || M > 12) ? 2 : 3; }
+
 template <int M, int RU>
-__global__ void __launch_bounds__(SRTHREADS, (M <= 12 ? 3 : 2)) sobol_sweep_reg_kernel(SobolPairArgs p) {
+__global__ void __launch_bounds__(SRTHREADS, sweep_reg_min_blocks(M)) sobol_sweep_reg_kernel(SobolPairArgs p) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double etab[32];
   constexpr int nv = 3 * M, MP = (M + 1) & ~1;             // MP: M rounded up to even (16-byte alignment of what follows)
@@ -912,7 +916,13 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
       std::vector<unsigned> his;
       std::vector<std::vector<int>> dests;
       for (auto& kv : blocks) {
-        if ((int)kv.second.size() * 2 < NLO) continue;
+        // Only subsets the sweep form cannot serve count towards the threshold: a list of structured slices (everything gsa.models.GSA asks for) costs
+        // M exps per pair there, less than a lattice block's KL + 1 exps and walk (M = 5, cfg3 sizes: 2.25 ms through the lattice, 0.9 through
+        // the sweep).  Once a block qualifies, the structured subsets inside it ride along (the all-subsets sweep launches no sweep kernel).
+        int unstructured = 0;
+        for (int s : kv.second)
+          if (M > 20 || sobol_sweep_index(masks[s], M) < 0) ++unstructured;
+        if (unstructured * 2 < NLO) continue;
         std::vector<int> dest(64, -1);
         for (int s : kv.second) {
           const int lo = (int)(masks[s] & (unsigned long long)(NLO - 1));
@@ -966,28 +976,14 @@ int sobol_contract(const double* X, int N, int M, const double* Phi, const doubl
       int rc;
       long partials = (long)T * own_rows;        // per pair of output rows
       if (reg_form) {                   // M <= 20 here: three CTAs per SM up to M = 12, two (up to 255 registers) beyond
+#define RC_SWEEP_CASE(MM, RR) case MM: rc = launch_sweep_reg<MM, RR>(a, npairs, st); break;
         switch (M) {
-          case 1: rc = launch_sweep_reg<1, 2>(a, npairs, st); break;
-          case 2: rc = launch_sweep_reg<2, 2>(a, npairs, st); break;
-          case 3: rc = launch_sweep_reg<3, 2>(a, npairs, st); break;
-          case 4: rc = launch_sweep_reg<4, 2>(a, npairs, st); break;
-          case 5: rc = launch_sweep_reg<5, 2>(a, npairs, st); break;
-          case 6: rc = launch_sweep_reg<6, 2>(a, npairs, st); break;
-          case 7: rc = launch_sweep_reg<7, 2>(a, npairs, st); break;
-          case 8: rc = launch_sweep_reg<8, 2>(a, npairs, st); break;
-          case 9: rc = launch_sweep_reg<9, 1>(a, npairs, st); break;
-          case 10: rc = launch_sweep_reg<10, 1>(a, npairs, st); break;
-          case 11: rc = launch_sweep_reg<11, 1>(a, npairs, st); break;
-          case 12: rc = launch_sweep_reg<12, 1>(a, npairs, st); break;
-          case 13: rc = launch_sweep_reg<13, 1>(a, npairs, st); break;
-          case 14: rc = launch_sweep_reg<14, 1>(a, npairs, st); break;
-          case 15: rc = launch_sweep_reg<15, 1>(a, npairs, st); break;
-          case 16: rc = launch_sweep_reg<16, 1>(a, npairs, st); break;
-          case 17: rc = launch_sweep_reg<17, 1>(a, npairs, st); break;
-          case 18: rc = launch_sweep_reg<18, 1>(a, npairs, st); break;
-          case 19: rc = launch_sweep_reg<19, 1>(a, npairs, st); break;
+          RC_SWEEP_CASE(1, 2) RC_SWEEP_CASE(2, 2) RC_SWEEP_CASE(3, 2) RC_SWEEP_CASE(4, 2) RC_SWEEP_CASE(5, 2) RC_SWEEP_CASE(6, 2) RC_SWEEP_CASE(7, 2)
+          RC_SWEEP_CASE(8, 2) RC_SWEEP_CASE(9, 1) RC_SWEEP_CASE(10, 1) RC_SWEEP_CASE(11, 1) RC_SWEEP_CASE(12, 1) RC_SWEEP_CASE(13, 1) RC_SWEEP_CASE(14, 1)
+          RC_SWEEP_CASE(15, 1) RC_SWEEP_CASE(16, 1) RC_SWEEP_CASE(17, 1) RC_SWEEP_CASE(18, 1) RC_SWEEP_CASE(19, 1)
           default: rc = launch_sweep_reg<20, 1>(a, npairs, st); break;
         }
+#undef RC_SWEEP_CASE
         partials = (long)own_rows * ((T + a.chunk - 1) / a.chunk);
       } else
         rc = M <= 4 ? launch_sweep<4, 2>(a, npairs, st) : M <= 8 ? launch_sweep<8, 2>(a, npairs, st)
