@@ -682,7 +682,10 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
     }
   }
   // keep_full: this chunk is the internal one holding only the full model (MIXED): no V / W output, its psi_ii columns are kept
-  auto finish_chunk = [&](const ErrMap& map, int ns, int nv, int RC, long ncols_u, bool keep_full) -> int {
+  // mode 0: V / W (/ WMm) of the chunk;  1: the internal chunk that holds only the full model (MIXED): no output, its psi_ii columns are kept;
+  // 2: a chunk whose FIRST slice is the full model: its psi_ii columns are kept, then everything of mode 0 (saves the separate solve of mode 1)
+  auto finish_chunk = [&](const ErrMap& map, int ns, int nv, int RC, long ncols_u, int mode) -> int {
+    const bool keep_full = mode == 1;
     RC_CUDA_OK(cudaMemsetAsync(B, 0, (size_t)chol_batch * lay.strideB * sizeof(double), st));
     sobol_error_gather_kernel<<<dim3(ns, L * L), 256, 0, st>>>(parts, L, N, RC, nv, ncols_u, g0KY, g0, pre, chol_batch, B, lay.ldb, lay.strideB, map,
                                                                keep_full ? nullptr : V, R, keep_full ? nullptr : Rm);
@@ -690,10 +693,10 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
     int rc = lay.use_sbinv ? trsm_lower_fwd_sbinv(Achol, n_pad, ld, dinv, sbwork, sbT, B, lay.ncols, lay.ldb, st)
                            : trsm_lower_fwd(Achol, n_pad, ld, strideA, chol_batch, dinv, B, lay.ncols, lay.ldb, lay.strideB, st);
     if (rc) return rc;
-    if (keep_full) {
+    if (mode != 0) {
       sobol_error_keep_psifull_kernel<<<dim3((n_pad + 255) / 256, L), 256, 0, st>>>(B, lay.ldb, lay.strideB, L, n_pad, chol_batch, psifull);
       RC_LAUNCH_OK();
-      return 0;
+      if (keep_full) return 0;
     }
     colnorm_partial_kernel<<<dim3((lay.ncols + 127) / 128, chunks, chol_batch), 128, 0, st>>>(B, lay.ldb, lay.strideB, lay.ncols, partial, stride_partial,
                                                                                                  psifull, n_pad, L, chol_batch, partial2);
@@ -743,20 +746,33 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
     }
     if (rc) return rc;
   }
-  if (mixed) {   // the full model first: psi^FULL_ii for the MIXED dots of every chunk below
+  // MIXED needs psi^FULL_ii for the dots of every chunk.  If the full model is itself one of the structured slices asked for (gsa.models.GSA always
+  // appends it), it is moved to the front of the list and its columns are kept from the first chunk's solve; otherwise it gets a chunk of its own.
+  bool full_in_first_chunk = false;
+  if (mixed && sweep_form) {
+    const int full_col = sobol_sweep_index(full_mask, M);
+    for (size_t q = 0; q < structured.size(); ++q)
+      if (scol[q] == full_col) {
+        std::swap(structured[0], structured[q]);
+        std::swap(scol[0], scol[q]);
+        full_in_first_chunk = true;
+        break;
+      }
+  }
+  if (mixed && !full_in_first_chunk) {   // the full model first
     ErrMap map{};
     map.dest[0] = 0;
     int rc;
     if (sweep_form) {
       map.col[0] = sobol_sweep_index(full_mask, M);
-      if ((rc = finish_chunk(map, 1, 3 * M, sw.RC, (long)sw.T * SW_EC, true))) return rc;
+      if ((rc = finish_chunk(map, 1, 3 * M, sw.RC, (long)sw.T * SW_EC, 1))) return rc;
     } else {
       ErrMatvecArgs a = general_args(1);
       a.masks[0] = full_mask;
       map.col[0] = 0;
       sobol_error_matvec_kernel<<<dim3(lay.T * lay.RC, J), ETHREADS, smem, st>>>(a);
       RC_LAUNCH_OK();
-      if ((rc = finish_chunk(map, 1, 1, lay.RC, (long)lay.T * EC, true))) return rc;
+      if ((rc = finish_chunk(map, 1, 1, lay.RC, (long)lay.T * EC, 1))) return rc;
     }
   }
   for (size_t i0 = 0; i0 < structured.size(); i0 += lay.chunk_slices) {
@@ -766,7 +782,7 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
       map.col[s] = scol[i0 + s];
       map.dest[s] = structured[i0 + s];
     }
-    int rc = finish_chunk(map, ns, 3 * M, sw.RC, (long)sw.T * SW_EC, false);
+    int rc = finish_chunk(map, ns, 3 * M, sw.RC, (long)sw.T * SW_EC, (i0 == 0 && full_in_first_chunk) ? 2 : 0);
     if (rc) return rc;
   }
   for (size_t i0 = 0; i0 < general.size(); i0 += lay.chunk_slices) {
@@ -780,7 +796,7 @@ int sobol_error(const double* X, int N, int M, const double* Lam, const double* 
     }
     sobol_error_matvec_kernel<<<dim3(lay.T * lay.RC, J), ETHREADS, smem, st>>>(a);
     RC_LAUNCH_OK();
-    int rc = finish_chunk(map, ns, ns, lay.RC, (long)lay.T * EC, false);
+    int rc = finish_chunk(map, ns, ns, lay.RC, (long)lay.T * EC, 0);
     if (rc) return rc;
   }
   return 0;
