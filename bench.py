@@ -441,8 +441,20 @@ def run_b200(args):
         q1.record()
         torch.cuda.synchronize()
         err_ms = q0.elapsed_time(q1) / 3
+        # is_T_partial=False, the setting of the reference's three scripts: the MIXED rank equation on top (W, WMm)
+        for _ in range(2):
+            C.sobol_error(dX, dLam, dFdiag, Phi, g0, g0KY, fac, masks, mixed=True)
+        torch.cuda.synchronize()
+        q0.record()
+        for _ in range(3):
+            C.sobol_error(dX, dLam, dFdiag, Phi, g0, g0KY, fac, masks, mixed=True)
+        q1.record()
+        torch.cuda.synchronize()
+        mixed_ms = q0.elapsed_time(q1) / 3
         sobol_err = {'metric': 'sobol_error_sweeps_per_s', 'value': 1e3 / err_ms, 'unit': 'sweeps/s', 'ms_per_sweep': err_ms, 'slices': len(masks),
-                     'note': 'V and W (error covariances) of the 25 slices: 2 L^2 pairwise kernels per slice + one TRSM over all (slice, l, i) right-hand sides'}
+                     'ms_per_sweep_not_partial': mixed_ms,
+                     'note': 'V and W (error covariances) of the 25 slices: 2 L^2 pairwise kernels per slice + one TRSM over all (slice, l, i) right-hand sides; '
+                             'ms_per_sweep_not_partial: with the MIXED rank equation as well (is_T_partial=False, 3 L^2 pairwise kernels per slice)'}
         del fac, Kfac
         torch.cuda.empty_cache()
 
