@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(STHREADS, 2) sobol_sweep_kernel(SobolPairArgs 
 }
 
 
-// Round 2, second form of the sweep kernel (M <= 12): the h values of a pass stay in REGISTERS and the exp is the table form (exp_tab).
+// Round 2, second form of the sweep kernel (M <= 20): the h values of a pass stay in REGISTERS and the exp is the table form (exp_tab).
 // The kernel above keeps two 256-thread CTAs per SM by parking h in shared memory; by ncu's wavefront count that parking, the 8-byte operand
 // loads and the bank conflicts of the stride-2 column reads cost 8 shared-memory cycles per warp-exp against 10.6 cycles of the FP64 pipe - the
 // two pipes were nearly co-critical, so a cheaper exp alone would only have moved the bound.  Here: 128 threads per CTA, three CTAs per SM
