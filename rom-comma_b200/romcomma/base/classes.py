@@ -91,6 +91,20 @@ class Frame:
         return self.csv.name
 
 
+def _wipe(folder: Path | str) -> Path:
+    """ Remove ``folder`` and everything below it (missing is fine); returns it as a Path."""
+    target = Path(folder)
+    shutil.rmtree(target, ignore_errors=True)
+    return target
+
+
+def _fresh(folder: Path | str) -> Path:
+    """ An existing, empty ``folder``."""
+    target = _wipe(folder)
+    target.mkdir(mode=0o777, parents=True, exist_ok=False)
+    return target
+
+
 class Data(ABC):
     """ A NamedTuple of Frames living in one folder. Subclasses provide ``NamedTuple`` (fields with default matrices)."""
 
@@ -99,10 +113,26 @@ class Data(ABC):
     class NamedTuple(NamedTuple):
         NotImplemented: Any = np.atleast_2d('NotImplemented')
 
+    # ---- construction --------------------------------------------------------------------------------------------------------------------
+    def __init__(self, folder: Path | str, **kwargs):
+        """ Fields missing from ``kwargs`` take the defaults of ``NamedTuple``; a folder that does not exist yet is created empty."""
+        where = Path(folder)
+        self._folder = where if where.exists() else _fresh(where)
+        self._frames = None
+        self.replace(**self.NamedTuple(**kwargs)._asdict())
+
+    @classmethod
+    def read(cls, folder: Path | str, **kwargs) -> 'Data':
+        """ The Data stored in ``folder``; a field given in ``kwargs`` is written instead of read."""
+        where = Path(folder)
+        stored = {name: Frame(where / name, kwargs.get(name)) for name in cls.fields}
+        return cls(where, **stored)
+
     @classmethod
     def make(cls, iterable: Iterable):
         return cls.NamedTuple._make(iterable)
 
+    # ---- the field set -------------------------------------------------------------------------------------------------------------------
     @classproperty
     def fields(cls) -> Tuple[str, ...]:
         return cls.NamedTuple._fields
@@ -111,64 +141,51 @@ class Data(ABC):
     def field_defaults(cls) -> Dict[str, Any]:
         return cls.NamedTuple._field_defaults
 
-    def __init__(self, folder: Path | str, **kwargs):
-        folder = Path(folder)
-        self._folder = folder if folder.exists() else self.empty(folder)
-        self._frames = None
-        self.replace(**self.NamedTuple(**kwargs)._asdict())
+    @property
+    def frames(self):
+        return self._frames
+
+    def __call__(self, *args, **kwargs):
+        return self._frames
 
     def asdict(self) -> Dict[str, Any]:
         return self._frames._asdict()
 
     def replace(self, **kwargs) -> 'Data':
-        for key, value in kwargs.items():
-            kwargs[key] = value if isinstance(value, Frame) else Frame(self._folder / key, np.atleast_2d(_host(value)))
-        self._frames = self.NamedTuple(**kwargs) if self._frames is None else self._frames._replace(**kwargs)
+        """ Overwrite the named fields (anything matrix-like, or a Frame) - each is written to ``<folder>/<field>.csv``."""
+        as_frames = {name: (value if isinstance(value, Frame) else Frame(self._folder / name, np.atleast_2d(_host(value)))) for name, value in kwargs.items()}
+        self._frames = self._frames._replace(**as_frames) if self._frames is not None else self.NamedTuple(**as_frames)
         return self
 
+    # ---- the folder ----------------------------------------------------------------------------------------------------------------------
     @property
     def folder(self) -> Path:
         return self._folder
 
-    @property
-    def frames(self):
-        return self._frames
-
     def move(self, dst_folder: Path | str) -> 'Data':
-        self._folder = type(self)(self.empty(dst_folder), **self.asdict()).folder
+        """ Re-home this Data in ``dst_folder`` (emptied first)."""
+        self._folder = type(self)(_fresh(dst_folder), **self.asdict()).folder
         return self
 
-    def __call__(self, *args, **kwargs):
-        return self._frames
+    @staticmethod
+    def delete(folder: Path | str) -> Path:
+        return _wipe(folder)
+
+    @staticmethod
+    def empty(folder: Path | str) -> Path:
+        return _fresh(folder)
+
+    @staticmethod
+    def copy(src_folder: Path | str, dst_folder: Path | str) -> Path:
+        target = _wipe(dst_folder)
+        shutil.copytree(src=src_folder, dst=target)
+        return target
 
     def __repr__(self) -> str:
         return str(self._folder)
 
     def __str__(self) -> str:
         return self._folder.name
-
-    @classmethod
-    def read(cls, folder: Path | str, **kwargs) -> 'Data':
-        folder = Path(folder)
-        return cls(folder, **{field: Frame(folder / field, kwargs.get(field, None)) for field in cls.fields})
-
-    @staticmethod
-    def delete(folder: Path | str) -> Path:
-        folder = Path(folder)
-        shutil.rmtree(folder, ignore_errors=True)
-        return folder
-
-    @staticmethod
-    def empty(folder: Path | str) -> Path:
-        folder = Data.delete(folder)
-        folder.mkdir(mode=0o777, parents=True, exist_ok=False)
-        return folder
-
-    @staticmethod
-    def copy(src_folder: Path | str, dst_folder: Path | str) -> Path:
-        dst_folder = Data.delete(dst_folder)
-        shutil.copytree(src=src_folder, dst=dst_folder)
-        return dst_folder
 
 
 class Model(ABC):
@@ -185,15 +202,29 @@ class Model(ABC):
 
     @abstractmethod
     def __init__(self, folder: Path | str, read_data: bool = False, **kwargs):
+        """ ``read_data``: take the Data from ``folder`` (then apply ``kwargs``) instead of starting from the defaults."""
         self._folder = Path(folder)
-        self._meta_json = self._folder / 'meta.json'
-        if read_data:
-            self._data = self.Data.read(self._folder).replace(**kwargs)
-        else:
-            self._folder.mkdir(mode=0o777, parents=True, exist_ok=True)
-            self._data = self.Data(self._folder, **kwargs)
         self._implementation = None
+        if not read_data:
+            self._folder.mkdir(mode=0o777, parents=True, exist_ok=True)
+        self._data = self.Data.read(self._folder).replace(**kwargs) if read_data else self.Data(self._folder, **kwargs)
 
+    @abstractmethod
+    def calibrate(self, method: str, **kwargs) -> Dict[str, Any]:
+        raise NotImplementedError('base.calibrate() must never be called.')
+
+    # ---- meta.json (indent 8, as the reference writes it) ---------------------------------------------------------------------------------
+    @property
+    def _meta_json(self) -> Path:
+        return self._folder / 'meta.json'
+
+    def read_meta(self) -> Dict[str, Any]:
+        return json.loads(self._meta_json.read_text())
+
+    def write_meta(self, meta: Dict[str, Any]):
+        self._meta_json.write_text(json.dumps(meta, indent=8))
+
+    # ---- accessors -----------------------------------------------------------------------------------------------------------------------
     @property
     def folder(self) -> Path:
         return self._folder
@@ -205,18 +236,6 @@ class Model(ABC):
     @data.setter
     def data(self, value: Data):
         self._data = value
-
-    @abstractmethod
-    def calibrate(self, method: str, **kwargs) -> Dict[str, Any]:
-        raise NotImplementedError('base.calibrate() must never be called.')
-
-    def read_meta(self) -> Dict[str, Any]:
-        with open(self._meta_json, mode='r') as file:
-            return json.load(file)
-
-    def write_meta(self, meta: Dict[str, Any]):
-        with open(self._meta_json, mode='w') as file:
-            json.dump(meta, file, indent=8)
 
     def __repr__(self) -> str:
         return str(self._folder)
