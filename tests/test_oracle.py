@@ -158,3 +158,33 @@ def test_literal_transliteration_matches_closed_form_full_F():
     cal = sobol.ClosedSobol(X, ls, F, KiY, False)
     for s in [(0, 3), (1, 2), (0, 1), (2, 3)]:
         assert_close(cal._V(*s), lit['V'](*s), what=f'V{s}')
+
+
+def test_oracle_test_metrics_match_a_literal_pandas_walk():
+    """oracle/normalization.py::test_metrics (the checker of rc_test_metrics) against the reference's own sequence of pandas operations in GPR.test
+    (gpr/models.py:241-270: copy the Y block, subtract the predictive mean, divide by the predictive sd, square > 4, any / all per row, then
+    sum / count per column) on a frame with the two-level header of test.csv."""
+    import pandas as pd
+    from oracle import normalization
+    rng = np.random.default_rng(8)
+    n, L = 57, 3
+    truth, mean, sd = rng.normal(size=(n, L)), rng.normal(size=(n, L)) * 0.4, rng.uniform(0.2, 1.2, (n, L))
+    cols = pd.MultiIndex.from_tuples([('Y', f'y.{l}') for l in range(L)])
+    Y = pd.DataFrame(truth, columns=cols)
+    score = Y.copy()
+    score.iloc[:] -= mean
+    abs_err = abs(score.copy())
+    score.iloc[:] /= sd
+    outliers = pd.DataFrame(score.to_numpy() ** 2 > 4.0, columns=cols)          # (the reference assigns into a copy of the Y block; pandas 2 refuses the dtype change)
+    out_np = outliers.to_numpy(dtype=float)
+    any_all = np.column_stack((np.logical_or.reduce(out_np, axis=1), np.logical_and.reduce(out_np, axis=1)))
+    rmse = ((abs_err ** 2).sum(axis=0) / abs_err.count(axis=0)) ** 0.5
+    mean_sd = pd.DataFrame(sd).sum(axis=0) / n
+    flags_ref = np.concatenate([out_np, any_all.astype(float)], axis=1)
+    reals, flags, summary = normalization.test_metrics(truth, mean, sd)
+    assert_close(reals[:, :L], abs_err.to_numpy(), rtol=1e-14, atol=0, what='Abs Error')
+    assert_close(reals[:, L:], score.to_numpy(), rtol=1e-14, atol=0, what='Z Score')
+    assert np.array_equal(flags, flags_ref)
+    assert_close(summary[:L], rmse.to_numpy(), rtol=1e-14, atol=0, what='RMSE')
+    assert_close(summary[L:2 * L], mean_sd.to_numpy(), rtol=1e-14, atol=0, what='mean SD')
+    assert_close(summary[2 * L:], flags_ref.sum(axis=0) / n, rtol=1e-14, atol=0, what='outlier fractions')
